@@ -1,0 +1,601 @@
+// f16_b200.cu - kernels and C ABI of the batched F-16 environment (include/f16_b200.h).
+//
+// One thread = one environment. A step launch loads the env's structure-of-arrays state (coalesced,
+// field-major), runs 4 FDM frames in registers (f16_model.cuh), builds the float32 observation frame
+// exactly as jsbsim_gym/jsbsim_gym.py:172-197 does, evaluates reward / termination / truncation
+// (jsbsim_gym.py:237-261, 487-509), optionally auto-resets (dummy_vec_env.py:63-72), stores the state
+// back and then each warp cooperatively shifts its 32 envs' (10,15) observation stacks - one
+// contiguous 19 200-byte span of the obs tensor - with fully coalesced 128-byte transactions.
+// The aero/engine tables (6 kB float / 12 kB double) are staged once per CTA into shared memory.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/f16_b200.h"
+#include "f16_env.cuh"
+#include "f16_host_setup.h"
+
+using namespace f16;
+
+// ------------------------------------------------------------------------------------ SoA layout
+// [K fields: NKF x np doubles][R fields: NRF x np R][E fields: NEF x np 4-byte], np = n rounded up to
+// 32; field lists and order in f16_env.cuh. Field-major, so a warp's accesses are one 128/256-byte row.
+struct Layout {
+  int64_t n, np;
+  size_t k_off, r_off, e_off, total;
+  int rsize;
+};
+static Layout make_layout(int64_t n, int mode) {
+  Layout L;
+  L.n = n;
+  L.np = (n + 31) / 32 * 32;
+  L.rsize = mode == F16_MODE_FP64 ? 8 : 4;
+  L.k_off = 0;
+  L.r_off = L.k_off + (size_t)NKF * L.np * 8;
+  L.e_off = L.r_off + (size_t)NRF * L.np * L.rsize;
+  L.total = L.e_off + (size_t)NEF * L.np * 4;
+  return L;
+}
+
+template <typename R>
+struct StatePtrs {
+  K* k;
+  R* r;
+  uint32_t* e;
+  int64_t np;
+};
+
+template <typename R>
+__device__ __forceinline__ void load_veh(Veh<R>& s, const StatePtrs<R>& p, int64_t e) {
+  int f = 0;
+#define X(m) s.m = p.k[(size_t)(f++) * p.np + e];
+  F16_KFIELDS(X)
+#undef X
+  f = 0;
+#define X(m) s.m = p.r[(size_t)(f++) * p.np + e];
+  F16_RFIELDS(X)
+#undef X
+}
+template <typename R>
+__device__ __forceinline__ void store_veh(const Veh<R>& s, const StatePtrs<R>& p, int64_t e) {
+  int f = 0;
+#define X(m) p.k[(size_t)(f++) * p.np + e] = s.m;
+  F16_KFIELDS(X)
+#undef X
+  f = 0;
+#define X(m) p.r[(size_t)(f++) * p.np + e] = s.m;
+  F16_RFIELDS(X)
+#undef X
+}
+template <typename R>
+__device__ __forceinline__ void load_env(EnvScalars& es, const StatePtrs<R>& p, int64_t e) {
+  es.gx = __uint_as_float(p.e[(size_t)EF_GOAL_X * p.np + e]);
+  es.gy = __uint_as_float(p.e[(size_t)EF_GOAL_Y * p.np + e]);
+  es.gz = __uint_as_float(p.e[(size_t)EF_GOAL_Z * p.np + e]);
+  es.last_d = __uint_as_float(p.e[(size_t)EF_LAST_DIST * p.np + e]);
+  es.step = (int32_t)p.e[(size_t)EF_STEP * p.np + e];
+  es.ep_ret = __uint_as_float(p.e[(size_t)EF_EP_RET * p.np + e]);
+  es.ep_len = (int32_t)p.e[(size_t)EF_EP_LEN * p.np + e];
+  es.episodes = p.e[(size_t)EF_EPISODES * p.np + e];
+}
+template <typename R>
+__device__ __forceinline__ void store_env(const EnvScalars& es, const StatePtrs<R>& p, int64_t e) {
+  p.e[(size_t)EF_GOAL_X * p.np + e] = __float_as_uint(es.gx);
+  p.e[(size_t)EF_GOAL_Y * p.np + e] = __float_as_uint(es.gy);
+  p.e[(size_t)EF_GOAL_Z * p.np + e] = __float_as_uint(es.gz);
+  p.e[(size_t)EF_LAST_DIST * p.np + e] = __float_as_uint(es.last_d);
+  p.e[(size_t)EF_STEP * p.np + e] = (uint32_t)es.step;
+  p.e[(size_t)EF_EP_RET * p.np + e] = __float_as_uint(es.ep_ret);
+  p.e[(size_t)EF_EP_LEN * p.np + e] = (uint32_t)es.ep_len;
+  p.e[(size_t)EF_EPISODES * p.np + e] = es.episodes;
+}
+
+// ------------------------------------------------------------------------------------ constant memory
+__constant__ MassSet c_msets[MS_COUNT];
+__constant__ double c_snapshot[F16_NUM_STATE_FIELDS];   // canonical post-reset FDM state
+__constant__ double c_snapshot_props[12];               // the 12 STATE_FORMAT properties after reset
+
+// ------------------------------------------------------------------------------------ kernels
+constexpr int BLOCK = 128;
+constexpr int WARPS = BLOCK / 32;
+
+template <typename R>
+__device__ __forceinline__ void stage_tables(Tables<R>* dst, const Tables<R>* __restrict__ src) {
+  static_assert(sizeof(Tables<R>) % 16 == 0, "table image must be a multiple of 16 bytes");
+  const int4* s4 = reinterpret_cast<const int4*>(src);
+  int4* d4 = reinterpret_cast<int4*>(dst);
+  for (int i = threadIdx.x; i < (int)(sizeof(Tables<R>) / 16); i += blockDim.x) d4[i] = __ldg(s4 + i);
+  __syncthreads();
+}
+
+struct StepArgs {
+  void* state;
+  const void* tables;
+  const float* actions;
+  float* obs;
+  float* reward;
+  uint8_t* done;
+  uint8_t* truncated;
+  float* terminal_obs;
+  float* ep_return;
+  int32_t* ep_len;
+  double* stats;
+  int64_t n, np;
+  size_t r_off, e_off;
+  uint64_t seed;
+  int64_t env_id_base;
+  uint32_t step_counter;
+  int auto_reset;
+};
+
+template <typename R>
+__device__ __forceinline__ StatePtrs<R> state_ptrs(void* state, size_t r_off, size_t e_off, int64_t np) {
+  StatePtrs<R> p;
+  char* b = (char*)state;
+  p.k = (K*)b;
+  p.r = (R*)(b + r_off);
+  p.e = (uint32_t*)(b + e_off);
+  p.np = np;
+  return p;
+}
+
+// Canonical post-reset snapshot (f16_env.cuh: compute_snapshot), one thread, always in double.
+__global__ void f16_init_snapshot_kernel(const Tables<double>* __restrict__ gT, const double* __restrict__ ic_state, double* out) {
+  __shared__ __align__(16) Tables<double> T;
+  stage_tables(&T, gT);
+  if (threadIdx.x != 0) return;
+  compute_snapshot(T, c_msets, ic_state, out);
+}
+
+// warp-cooperative write of 32 envs' observation stacks. `frame_s[l]` holds env l's newest frame,
+// flags: bit0 = env exists, bit1 = fill all ten rows with the frame (reset), bit2 = also emit the
+// shifted stack to terminal_obs with `tframe_s[l]` as its newest row.
+__device__ __forceinline__ void warp_write_obs(float* __restrict__ obs, float* __restrict__ term_obs, int64_t env0,
+                                               const float (*frame_s)[16], const float (*tframe_s)[16],
+                                               const uint8_t* flags_s) {
+  const int lane = threadIdx.x & 31;
+  constexpr int PER_ENV = F16_OBS_FRAMES * F16_OBS_FEATURES;   // 150
+  constexpr int SHIFT = F16_OBS_FEATURES;                      // 15
+  constexpr int TOTAL = 32 * PER_ENV;                          // 4800 floats = 150 warp-wide transactions
+  constexpr int U = 10;                                        // transactions in flight per batch
+  float* base = obs + env0 * PER_ENV;
+  float* tbase = term_obs ? term_obs + env0 * PER_ENV : nullptr;
+  for (int it0 = 0; it0 < TOTAL / 32; it0 += U) {
+    float v[U];
+    int el[U], jj[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int i = (it0 + u) * 32 + lane;
+      int l = i / PER_ENV;
+      int j = i - l * PER_ENV;
+      el[u] = l; jj[u] = j;
+      uint8_t fl = flags_s[l];
+      float x = 0.0f;
+      if ((fl & 1) && !(fl & 2) ) {
+        x = (j < PER_ENV - SHIFT) ? base[i + SHIFT] : frame_s[l][j - (PER_ENV - SHIFT)];
+      } else if (fl & 1) {
+        // reset: ten copies of the reset frame; the old stack is still needed for terminal_obs
+        x = (j < PER_ENV - SHIFT) ? base[i + SHIFT] : 0.0f;
+      }
+      v[u] = x;
+    }
+    __syncwarp();   // every lane's loads of this batch precede any lane's stores (in-place shift)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      int i = (it0 + u) * 32 + lane;
+      int l = el[u], j = jj[u];
+      uint8_t fl = flags_s[l];
+      if (!(fl & 1)) continue;
+      if ((fl & 4) && tbase) tbase[i] = (j < PER_ENV - SHIFT) ? v[u] : tframe_s[l][j - (PER_ENV - SHIFT)];
+      float x = v[u];
+      if (fl & 2) { int c = j % SHIFT; x = frame_s[l][c]; }
+      base[i] = x;
+    }
+    __syncwarp();
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(BLOCK) f16_step_kernel(const StepArgs a) {
+  __shared__ __align__(16) Tables<R> T;
+  __shared__ __align__(16) float frame_s[WARPS][32][16];
+  __shared__ __align__(16) float tframe_s[WARPS][32][16];
+  __shared__ uint8_t flags_s[WARPS][32];
+  stage_tables(&T, reinterpret_cast<const Tables<R>*>(a.tables));
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  int flags = 0;
+  if (e < a.n) {
+    StatePtrs<R> sp = state_ptrs<R>(a.state, a.r_off, a.e_off, a.np);
+    Veh<R> s;
+    EnvScalars es;
+    load_veh(s, sp, e);
+    load_env(es, sp, e);
+    const uint64_t gid = (uint64_t)(a.env_id_base + e);
+    float act[4];
+    if (a.actions) {
+      float4 v = reinterpret_cast<const float4*>(a.actions)[e];
+      act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
+    } else {
+      sample_action(a.seed, gid, a.step_counter, act);
+    }
+    float reward, ep_ret = 0.0f;
+    int32_t ep_len = 0;
+    flags = env_step_one<R>(s, es, T, c_msets, c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
+                            frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len);
+    a.reward[e] = reward;
+    a.done[e] = (flags & STEP_DONE) ? 1 : 0;
+    a.truncated[e] = (flags & STEP_TRUNCATED) ? 1 : 0;
+    if (flags & STEP_DONE) {
+      if (a.ep_return) a.ep_return[e] = ep_ret;
+      if (a.ep_len) a.ep_len[e] = ep_len;
+      if (a.stats) {
+        atomicAdd(a.stats + 0, 1.0);
+        atomicAdd(a.stats + 1, (double)ep_ret);
+        atomicAdd(a.stats + 2, (double)ep_len);
+        if (flags & STEP_CRASH) atomicAdd(a.stats + 3, 1.0);
+        if (flags & STEP_GOAL) atomicAdd(a.stats + 4, 1.0);
+        if (flags & STEP_TRUNCATED) atomicAdd(a.stats + 5, 1.0);
+      }
+    }
+    store_veh(s, sp, e);
+    store_env(es, sp, e);
+  }
+  flags_s[warp][lane] = (uint8_t)(flags & (STEP_ACTIVE | STEP_RESET | STEP_TERMINAL));
+  __syncwarp();
+  const int64_t env0 = (int64_t)blockIdx.x * BLOCK + warp * 32;
+  if (env0 < a.n) warp_write_obs(a.obs, a.terminal_obs, env0, frame_s[warp], tframe_s[warp], flags_s[warp]);
+}
+
+struct ResetArgs {
+  void* state;
+  const uint8_t* mask;
+  const float* goals;
+  float* obs;
+  int64_t n, np;
+  size_t r_off, e_off;
+  uint64_t seed;
+  int64_t env_id_base;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(BLOCK) f16_reset_kernel(const ResetArgs a) {
+  const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  if (e >= a.n) return;
+  if (a.mask && !a.mask[e]) return;
+  StatePtrs<R> sp = state_ptrs<R>(a.state, a.r_off, a.e_off, a.np);
+  Veh<R> s;
+  EnvScalars es;
+  load_env(es, sp, e);
+  es.episodes += 1;
+  float g[3];
+  if (a.goals) { g[0] = a.goals[e * 3 + 0]; g[1] = a.goals[e * 3 + 1]; g[2] = a.goals[e * 3 + 2]; }
+  else sample_goal(a.seed, (uint64_t)(a.env_id_base + e), es.episodes, g);
+  float fr[16];
+  env_reset_one<R>(s, es, c_snapshot, c_snapshot_props, g, fr);
+  store_veh(s, sp, e);
+  store_env(es, sp, e);
+  float* ob = a.obs + e * (F16_OBS_FRAMES * F16_OBS_FEATURES);
+  for (int r = 0; r < F16_OBS_FRAMES; ++r)
+    for (int c = 0; c < F16_OBS_FEATURES; ++c) ob[r * F16_OBS_FEATURES + c] = fr[c];
+}
+
+template <typename R>
+__global__ void f16_pack_kernel(void* state, size_t r_off, size_t e_off, int64_t n, int64_t np, int64_t first, double* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  StatePtrs<R> sp = state_ptrs<R>(state, r_off, e_off, np);
+  Veh<R> s;
+  load_veh(s, sp, first + i);
+  double a[F16_NUM_STATE_FIELDS];
+  veh_to_packed(s, a);
+  for (int f = 0; f < F16_NUM_STATE_FIELDS; ++f) out[i * F16_NUM_STATE_FIELDS + f] = a[f];
+}
+template <typename R>
+__global__ void f16_unpack_kernel(void* state, size_t r_off, size_t e_off, int64_t n, int64_t np, int64_t first, const double* in) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  StatePtrs<R> sp = state_ptrs<R>(state, r_off, e_off, np);
+  double a[F16_NUM_STATE_FIELDS];
+  for (int f = 0; f < F16_NUM_STATE_FIELDS; ++f) a[f] = in[i * F16_NUM_STATE_FIELDS + f];
+  Veh<R> s;
+  veh_from_packed(s, a);
+  store_veh(s, sp, first + i);
+}
+
+// ==================================================================================== host side
+namespace {
+
+thread_local std::string g_err;
+int64_t g_launches = 0;
+
+int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return -1;
+}
+#define CUDA_OK(call)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess) return fail("%s failed: %s", #call, cudaGetErrorString(_e));      \
+  } while (0)
+
+}  // namespace
+
+struct f16_ctx {
+  int device = 0, mode = 0;
+  Layout L;
+  void* tables_dev = nullptr;        // Tables<double> or Tables<float>
+  double* stats_dev = nullptr;
+  double* scratch_dev = nullptr;     // F16_NUM_STATE_FIELDS + 12 doubles
+  double snapshot[F16_NUM_STATE_FIELDS + 12];
+  void* state = nullptr;
+  float* obs = nullptr;
+  float* reward = nullptr;
+  uint8_t* done = nullptr;
+  uint8_t* truncated = nullptr;
+  float* terminal_obs = nullptr;
+  float* ep_return = nullptr;
+  int32_t* ep_len = nullptr;
+  float* actions_stage = nullptr;    // device staging for f16_step_host
+  int64_t env_id_base = 0;
+  uint64_t seed = 0;
+  uint32_t step_counter = 0;
+  double env_steps = 0.0;            // host-side count for stats[6]
+};
+
+template <typename R>
+static int upload_tables(f16_ctx* c) {
+  Tables<R>* h = new (std::nothrow) Tables<R>;
+  if (!h) return fail("out of host memory");
+  host::build_tables<R>(h);
+  cudaError_t e = cudaMalloc(&c->tables_dev, sizeof(Tables<R>));
+  if (e == cudaSuccess) e = cudaMemcpy(c->tables_dev, h, sizeof(Tables<R>), cudaMemcpyHostToDevice);
+  delete h;
+  if (e != cudaSuccess) return fail("table upload failed: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" {
+
+const char* f16_last_error(void) { return g_err.c_str(); }
+const char* f16_version(void) { return "f16_b200 0.1 (sm_100a)"; }
+int64_t f16_launch_count(void) { return g_launches; }
+
+int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
+  if (!out) return fail("f16_create: out is NULL");
+  *out = nullptr;
+  if (n_envs <= 0) return fail("f16_create: n_envs must be positive (got %lld)", (long long)n_envs);
+  if (mode != F16_MODE_FP64 && mode != F16_MODE_FP32) return fail("f16_create: unknown mode %d", mode);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("f16_create: no CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return fail("f16_create: device %d out of range [0,%d)", device, ndev);
+  CUDA_OK(cudaSetDevice(device));
+  f16_ctx* c = new (std::nothrow) f16_ctx;
+  if (!c) return fail("out of host memory");
+  c->device = device;
+  c->mode = mode;
+  c->L = make_layout(n_envs, mode);
+  // constants shared by every context on this device
+  MassSet ms[MS_COUNT];
+  host::build_mass_sets(ms);
+  CUDA_OK(cudaMemcpyToSymbol(c_msets, ms, sizeof(ms)));
+  int rc = mode == F16_MODE_FP64 ? upload_tables<double>(c) : upload_tables<float>(c);
+  if (rc) { delete c; return rc; }
+  CUDA_OK(cudaMalloc(&c->stats_dev, F16_NUM_STATS * sizeof(double)));
+  CUDA_OK(cudaMemset(c->stats_dev, 0, F16_NUM_STATS * sizeof(double)));
+  CUDA_OK(cudaMalloc(&c->scratch_dev, 2 * (F16_NUM_STATE_FIELDS + 12) * sizeof(double)));
+  // canonical snapshot: always computed in double, with a double table image
+  {
+    Tables<double>* hT = new (std::nothrow) Tables<double>;
+    if (!hT) { delete c; return fail("out of host memory"); }
+    host::build_tables<double>(hT);
+    Tables<double>* dT = nullptr;
+    CUDA_OK(cudaMalloc(&dT, sizeof(Tables<double>)));
+    CUDA_OK(cudaMemcpy(dT, hT, sizeof(Tables<double>), cudaMemcpyHostToDevice));
+    delete hT;
+    double ic[F16_NUM_STATE_FIELDS];
+    host::initial_condition(900.0, 5000.0, ic);
+    double* d_ic = c->scratch_dev;
+    double* d_out = c->scratch_dev + (F16_NUM_STATE_FIELDS + 12);
+    CUDA_OK(cudaMemcpy(d_ic, ic, sizeof(ic), cudaMemcpyHostToDevice));
+    f16_init_snapshot_kernel<<<1, 32>>>(dT, d_ic, d_out);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
+    CUDA_OK(cudaMemcpy(c->snapshot, d_out, sizeof(c->snapshot), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaFree(dT));
+    CUDA_OK(cudaMemcpyToSymbol(c_snapshot, c->snapshot, F16_NUM_STATE_FIELDS * sizeof(double)));
+    CUDA_OK(cudaMemcpyToSymbol(c_snapshot_props, c->snapshot + F16_NUM_STATE_FIELDS, 12 * sizeof(double)));
+  }
+  CUDA_OK(cudaMalloc(&c->actions_stage, (size_t)n_envs * F16_ACTION_DIM * sizeof(float)));
+  *out = c;
+  return 0;
+}
+
+int f16_destroy(f16_handle h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->tables_dev);
+  cudaFree(h->stats_dev);
+  cudaFree(h->scratch_dev);
+  cudaFree(h->actions_stage);
+  delete h;
+  return 0;
+}
+
+size_t f16_state_bytes(f16_handle h) { return h ? h->L.total : 0; }
+
+int f16_bind(f16_handle h, void* state, float* obs, float* reward, uint8_t* done, uint8_t* truncated, float* terminal_obs,
+             float* ep_return, int32_t* ep_len) {
+  if (!h) return fail("f16_bind: NULL handle");
+  if (!state || !obs || !reward || !done || !truncated) return fail("f16_bind: state, obs, reward, done and truncated are required");
+  if (((uintptr_t)state & 255) != 0) return fail("f16_bind: state must be 256-byte aligned");
+  CUDA_OK(cudaSetDevice(h->device));
+  h->state = state; h->obs = obs; h->reward = reward; h->done = done; h->truncated = truncated;
+  h->terminal_obs = terminal_obs; h->ep_return = ep_return; h->ep_len = ep_len;
+  CUDA_OK(cudaMemset(state, 0, h->L.total));
+  return 0;
+}
+
+int f16_set_env_id_base(f16_handle h, int64_t base) {
+  if (!h) return fail("NULL handle");
+  h->env_id_base = base;
+  return 0;
+}
+
+int f16_reset(f16_handle h, const uint8_t* mask, const float* goals, uint64_t seed, void* stream) {
+  if (!h) return fail("f16_reset: NULL handle");
+  if (!h->state) return fail("f16_reset: call f16_bind first");
+  CUDA_OK(cudaSetDevice(h->device));
+  h->seed = seed;
+  ResetArgs a;
+  a.state = h->state; a.mask = mask; a.goals = goals; a.obs = h->obs;
+  a.n = h->L.n; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
+  a.seed = seed; a.env_id_base = h->env_id_base;
+  unsigned grid = (unsigned)((h->L.n + BLOCK - 1) / BLOCK);
+  if (h->mode == F16_MODE_FP64) f16_reset_kernel<double><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+  else f16_reset_kernel<float><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream) {
+  if (!h) return fail("f16_step: NULL handle");
+  if (!h->state) return fail("f16_step: call f16_bind first");
+  CUDA_OK(cudaSetDevice(h->device));
+  StepArgs a;
+  a.state = h->state; a.tables = h->tables_dev; a.actions = actions; a.obs = h->obs; a.reward = h->reward;
+  a.done = h->done; a.truncated = h->truncated; a.terminal_obs = h->terminal_obs; a.ep_return = h->ep_return;
+  a.ep_len = h->ep_len; a.stats = h->stats_dev; a.n = h->L.n; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
+  a.seed = h->seed; a.env_id_base = h->env_id_base; a.step_counter = h->step_counter++; a.auto_reset = auto_reset;
+  unsigned grid = (unsigned)((h->L.n + BLOCK - 1) / BLOCK);
+  if (h->mode == F16_MODE_FP64) f16_step_kernel<double><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+  else f16_step_kernel<float><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+  g_launches++;
+  h->env_steps += (double)h->L.n;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int f16_step_host(f16_handle h, const float* actions_host, int auto_reset, float* obs_host, float* reward_host,
+                  uint8_t* done_host, uint8_t* truncated_host, void* stream) {
+  if (!h) return fail("f16_step_host: NULL handle");
+  if (!actions_host) return fail("f16_step_host: actions_host is NULL");
+  CUDA_OK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)h->L.n;
+  CUDA_OK(cudaMemcpyAsync(h->actions_stage, actions_host, n * F16_ACTION_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = f16_step(h, h->actions_stage, auto_reset, stream);
+  if (rc) return rc;
+  if (obs_host) CUDA_OK(cudaMemcpyAsync(obs_host, h->obs, n * F16_OBS_FRAMES * F16_OBS_FEATURES * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (reward_host) CUDA_OK(cudaMemcpyAsync(reward_host, h->reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (done_host) CUDA_OK(cudaMemcpyAsync(done_host, h->done, n, cudaMemcpyDeviceToHost, st));
+  if (truncated_host) CUDA_OK(cudaMemcpyAsync(truncated_host, h->truncated, n, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int pack_range(f16_handle h, int64_t first, int64_t count, double* dev_out, cudaStream_t st) {
+  unsigned grid = (unsigned)((count + 127) / 128);
+  if (h->mode == F16_MODE_FP64) f16_pack_kernel<double><<<grid, 128, 0, st>>>(h->state, h->L.r_off, h->L.e_off, count, h->L.np, first, dev_out);
+  else f16_pack_kernel<float><<<grid, 128, 0, st>>>(h->state, h->L.r_off, h->L.e_off, count, h->L.np, first, dev_out);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static int unpack_range(f16_handle h, int64_t first, int64_t count, const double* dev_in, cudaStream_t st) {
+  unsigned grid = (unsigned)((count + 127) / 128);
+  if (h->mode == F16_MODE_FP64) f16_unpack_kernel<double><<<grid, 128, 0, st>>>(h->state, h->L.r_off, h->L.e_off, count, h->L.np, first, dev_in);
+  else f16_unpack_kernel<float><<<grid, 128, 0, st>>>(h->state, h->L.r_off, h->L.e_off, count, h->L.np, first, dev_in);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int f16_get_state(f16_handle h, int64_t env, double* out, int n) {
+  if (!h || !h->state) return fail("f16_get_state: handle not bound");
+  if (n != F16_NUM_STATE_FIELDS) return fail("f16_get_state: n must be %d", (int)F16_NUM_STATE_FIELDS);
+  if (env < 0 || env >= h->L.n) return fail("f16_get_state: env %lld out of range", (long long)env);
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  int rc = pack_range(h, env, 1, h->scratch_dev, 0);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpy(out, h->scratch_dev, n * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int f16_set_state(f16_handle h, int64_t env, const double* in, int n) {
+  if (!h || !h->state) return fail("f16_set_state: handle not bound");
+  if (n != F16_NUM_STATE_FIELDS) return fail("f16_set_state: n must be %d", (int)F16_NUM_STATE_FIELDS);
+  if (env < 0 || env >= h->L.n) return fail("f16_set_state: env %lld out of range", (long long)env);
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(h->scratch_dev, in, n * sizeof(double), cudaMemcpyHostToDevice));
+  int rc = unpack_range(h, env, 1, h->scratch_dev, 0);
+  if (rc) return rc;
+  CUDA_OK(cudaDeviceSynchronize());
+  return 0;
+}
+int f16_pack_states(f16_handle h, double* packed_dev, void* stream) {
+  if (!h || !h->state) return fail("f16_pack_states: handle not bound");
+  CUDA_OK(cudaSetDevice(h->device));
+  return pack_range(h, 0, h->L.n, packed_dev, (cudaStream_t)stream);
+}
+int f16_unpack_states(f16_handle h, const double* packed_dev, void* stream) {
+  if (!h || !h->state) return fail("f16_unpack_states: handle not bound");
+  CUDA_OK(cudaSetDevice(h->device));
+  return unpack_range(h, 0, h->L.n, packed_dev, (cudaStream_t)stream);
+}
+int f16_set_env_step(f16_handle h, int64_t env, int32_t current_step) {
+  if (!h || !h->state) return fail("f16_set_env_step: handle not bound");
+  if (env < 0 || env >= h->L.n) return fail("f16_set_env_step: env out of range");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaDeviceSynchronize());
+  char* p = (char*)h->state + h->L.e_off + ((size_t)EF_STEP * h->L.np + env) * 4;
+  CUDA_OK(cudaMemcpy(p, &current_step, 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int f16_get_snapshot(f16_handle h, double* state_out, double* props12_out) {
+  if (!h) return fail("NULL handle");
+  if (state_out) memcpy(state_out, h->snapshot, F16_NUM_STATE_FIELDS * sizeof(double));
+  if (props12_out) memcpy(props12_out, h->snapshot + F16_NUM_STATE_FIELDS, 12 * sizeof(double));
+  return 0;
+}
+
+int f16_get_stats(f16_handle h, double* out8, int reset, void* stream) {
+  if (!h) return fail("NULL handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  if (out8) {
+    CUDA_OK(cudaMemcpy(out8, h->stats_dev, F16_NUM_STATS * sizeof(double), cudaMemcpyDeviceToHost));
+    out8[6] = h->env_steps;
+  }
+  if (reset) {
+    CUDA_OK(cudaMemset(h->stats_dev, 0, F16_NUM_STATS * sizeof(double)));
+    h->env_steps = 0.0;
+  }
+  return 0;
+}
+int f16_stats_device_ptr(f16_handle h, double** out) {
+  if (!h || !out) return fail("NULL argument");
+  *out = h->stats_dev;
+  return 0;
+}
+
+}  // extern "C"

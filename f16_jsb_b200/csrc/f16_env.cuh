@@ -1,0 +1,237 @@
+// f16_env.cuh - the env layer of one environment: everything JSBSimEnv.step / reset and
+// PositionReward.step / reset (jsbsim_gym/jsbsim_gym.py:172-331, 487-519) do around the FDM frames,
+// plus the DummyVecEnv auto-reset convention (stable_baselines3/common/vec_env/dummy_vec_env.py:63-72).
+// Per-thread code, called by the kernels in f16_b200.cu (and, for CPU-side debugging of this very
+// source, by tests/hostsim).
+#pragma once
+#include "../../include/f16_state_fields.h"
+#include "f16_model.cuh"
+
+namespace f16 {
+
+// ------------------------------------------------------------------------------------ SoA field lists
+// K fields (always double) and R fields (double in parity mode, float in throughput mode).
+#define F16_KFIELDS(X) X(q[0]) X(q[1]) X(q[2]) X(q[3]) X(ri[0]) X(ri[1]) X(ri[2]) X(vi[0]) X(vi[1]) X(vi[2]) X(epa)
+#define F16_RFIELDS(X)                                                                                 \
+  X(wi[0]) X(wi[1]) X(wi[2]) X(vi1[0]) X(vi1[1]) X(vi1[2]) X(vi2[0]) X(vi2[1]) X(vi2[2])               \
+  X(ai0[0]) X(ai0[1]) X(ai0[2]) X(ai1[0]) X(ai1[1]) X(ai1[2]) X(wdot[0]) X(wdot[1]) X(wdot[2])         \
+  X(abody[0]) X(abody[1]) X(abody[2]) X(pqr[0]) X(pqr[1]) X(pqr[2]) X(alpha) X(mach) X(vc) X(vg)       \
+  X(npy) X(npz) X(tef) X(ail) X(elev) X(sb) X(roll_ip) X(roll_I) X(pitch_ip) X(pitch_I) X(yaw_ip)      \
+  X(yaw_I) X(n2) X(aug)
+constexpr int NKF = 11, NRF = 42;
+enum { EF_GOAL_X = 0, EF_GOAL_Y, EF_GOAL_Z, EF_LAST_DIST, EF_STEP, EF_EP_RET, EF_EP_LEN, EF_EPISODES, NEF };
+
+// packed double[F16_NUM_STATE_FIELDS] (include/f16_state_fields.h) <-> Veh. The enum lists Q, WI, RI,
+// VI, EPA first and then every remaining R field in F16_RFIELDS order.
+template <typename R>
+F16_HD void veh_from_packed(Veh<R>& s, const double* a) {
+  double kk[NKF];
+  double rr[NRF];
+  kk[0] = a[F16S_Q0]; kk[1] = a[F16S_Q1]; kk[2] = a[F16S_Q2]; kk[3] = a[F16S_Q3];
+  kk[4] = a[F16S_RI_X]; kk[5] = a[F16S_RI_Y]; kk[6] = a[F16S_RI_Z];
+  kk[7] = a[F16S_VI_X]; kk[8] = a[F16S_VI_Y]; kk[9] = a[F16S_VI_Z]; kk[10] = a[F16S_EPA];
+  rr[0] = a[F16S_WI_X]; rr[1] = a[F16S_WI_Y]; rr[2] = a[F16S_WI_Z];
+  for (int i = 0; i < NRF - 3; ++i) rr[3 + i] = a[F16S_VI1_X + i];
+  int f = 0;
+#define X(m) s.m = kk[f++];
+  F16_KFIELDS(X)
+#undef X
+  f = 0;
+#define X(m) s.m = (R)rr[f++];
+  F16_RFIELDS(X)
+#undef X
+}
+template <typename R>
+F16_HD void veh_to_packed(const Veh<R>& s, double* a) {
+  double kk[NKF];
+  double rr[NRF];
+  int f = 0;
+#define X(m) kk[f++] = s.m;
+  F16_KFIELDS(X)
+#undef X
+  f = 0;
+#define X(m) rr[f++] = (double)s.m;
+  F16_RFIELDS(X)
+#undef X
+  a[F16S_Q0] = kk[0]; a[F16S_Q1] = kk[1]; a[F16S_Q2] = kk[2]; a[F16S_Q3] = kk[3];
+  a[F16S_RI_X] = kk[4]; a[F16S_RI_Y] = kk[5]; a[F16S_RI_Z] = kk[6];
+  a[F16S_VI_X] = kk[7]; a[F16S_VI_Y] = kk[8]; a[F16S_VI_Z] = kk[9]; a[F16S_EPA] = kk[10];
+  a[F16S_WI_X] = rr[0]; a[F16S_WI_Y] = rr[1]; a[F16S_WI_Z] = rr[2];
+  for (int i = 0; i < NRF - 3; ++i) a[F16S_VI1_X + i] = rr[3 + i];
+}
+
+// env-layer scalars of one environment (E fields)
+struct EnvScalars {
+  float gx, gy, gz;       // goal, metres (jsbsim_gym.py:321-323)
+  float last_d;           // PositionReward.last_distance
+  int32_t step;           // JSBSimEnv.current_step
+  float ep_ret;           // Monitor: running episode return
+  int32_t ep_len;         // Monitor: running episode length
+  uint32_t episodes;      // episodes started (Philox counter for goal sampling)
+};
+
+// ------------------------------------------------------------------------------------ observation frame
+// jsbsim_gym.py:172-197: float32 store of each double property, wrap of phi/theta/psi in float32,
+// float32 multiply of lat/lon by 6.3781e6.
+F16_HD void props_to_frame(const double* p12, float* o) {
+  for (int i = 0; i < 12; ++i) o[i] = (float)p12[i];
+  o[9] = wrap_mpi_pi_f32(o[9]);
+  o[10] = wrap_mpi_pi_f32(o[10]);
+  o[11] = wrap_mpi_pi_f32(o[11]);
+  o[0] = fmul_rn(o[0], 6.3781e6f);
+  o[1] = fmul_rn(o[1], 6.3781e6f);
+}
+template <typename R>
+F16_HD void frame_from_fdm(const Veh<R>& s, const FrameObs<R>& fo, float* o) {
+  R phi, tht, psi;
+  euler_from_tl2b<R>(fo, phi, tht, psi);
+  o[0] = (float)fo.lat;
+  o[1] = (float)fo.lon;
+  o[2] = (float)(fo.h_ft * kFtToM);
+  o[3] = (float)s.mach;
+  o[4] = (float)s.alpha;
+  o[5] = (float)fo.beta;
+  o[6] = (float)fo.pqr[0];
+  o[7] = (float)fo.pqr[1];
+  o[8] = (float)fo.pqr[2];
+  o[9] = wrap_mpi_pi_f32((float)phi);
+  o[10] = wrap_mpi_pi_f32((float)tht);
+  o[11] = wrap_mpi_pi_f32((float)psi);
+  o[0] = fmul_rn(o[0], 6.3781e6f);
+  o[1] = fmul_rn(o[1], 6.3781e6f);
+}
+// PositionReward distance (jsbsim_gym.py:499-500): float32 3-D norm, no fused multiply-add
+F16_HD float goal_distance(const float* o, float gx, float gy, float gz) {
+  float dx = fsub_rn(gx, o[0]), dy = fsub_rn(gy, o[1]), dz = fsub_rn(gz, o[2]);
+  return fsqrt_rn(fadd_rn(fadd_rn(fmul_rn(dx, dx), fmul_rn(dy, dy)), fmul_rn(dz, dz)));
+}
+// goal ~ (d cos b, d sin b, alt), d~U[1000,10000), b~U[0,2pi), alt~U[1000,4000) (jsbsim_gym.py:315-323)
+F16_HD void sample_goal(uint64_t seed, uint64_t env_id, uint32_t episode, float* g) {
+  uint32_t r[4];
+  philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), episode, 0x60A1u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  float d = 1000.0f + 9000.0f * u01_from_u32(r[0]);
+  float bearing = 6.2831853071795864769f * u01_from_u32(r[1]);
+  float alt = 1000.0f + 3000.0f * u01_from_u32(r[2]);
+  float sb, cb;
+  sincosf(bearing, &sb, &cb);
+  g[0] = d * cb; g[1] = d * sb; g[2] = alt;
+}
+// action_space.sample()-like uniform action (Box low [-1,-1,-1,0], high [1,1,1,1]; jsbsim_gym.py:143-148)
+F16_HD void sample_action(uint64_t seed, uint64_t env_id, uint32_t step_counter, float* act) {
+  uint32_t r4[4];
+  philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), step_counter, 0xAC71u, (uint32_t)seed, (uint32_t)(seed >> 32), r4);
+  act[0] = 2.0f * u01_from_u32(r4[0]) - 1.0f;
+  act[1] = 2.0f * u01_from_u32(r4[1]) - 1.0f;
+  act[2] = 2.0f * u01_from_u32(r4[2]) - 1.0f;
+  act[3] = u01_from_u32(r4[3]);
+}
+
+// ------------------------------------------------------------------------------------ snapshot bring-up
+// Canonical post-reset state, always in double: fresh FDM -> constructor's run_ic()
+// (two zero-dt frames) -> reset()'s run_ic() (two more) -> propulsion/set-running (N2 = 100 %,
+// augmentation off). Gear is still down and both internal tanks still hold their initial 1500 lb
+// during these frames; the FCS components tick with dt = 1/120. `out` receives the packed state
+// followed by the twelve STATE_FORMAT properties (jsbsim_gym.py:12-25) as doubles.
+F16_HD void compute_snapshot(const Tables<double>& T, const MassSet* msets, const double* ic_state, double* out) {
+  Veh<double> s;
+  veh_from_packed(s, ic_state);   // kinematic IC, everything else zero (fresh FDM)
+  Cmd<double> cmd = {0.0, 0.0, 0.0, 0.0};
+  FrameObs<double> fo;
+  FrameCfg cfg;
+  cfg.dt = 0.0;
+  cfg.gear = 1.0;
+  for (int ic = 0; ic < 2; ++ic) {
+    for (int k = 0; k < 2; ++k) {
+      cfg.mass_set = (ic == 0 && k == 0) ? MS_IC_FIRST : MS_IC;
+      fdm_frame<double, true>(s, T, msets, cfg, cmd, false, fo);
+    }
+    for (int i = 0; i < 3; ++i) { s.vi1[i] = s.vi[i]; s.vi2[i] = s.vi[i]; }   // InitializeDerivatives
+  }
+  s.n2 = f16data::idlen2 + 1.0 * (f16data::maxn2 - f16data::idlen2);          // InitRunning + GetSteadyState
+  s.aug = 0.0;
+  veh_to_packed(s, out);
+  double phi, tht, psi;
+  euler_from_tl2b<double>(fo, phi, tht, psi);
+  double* p = out + F16_NUM_STATE_FIELDS;
+  p[0] = fo.lat; p[1] = fo.lon; p[2] = fo.h_ft * kFtToM; p[3] = s.mach; p[4] = s.alpha; p[5] = fo.beta;
+  p[6] = fo.pqr[0]; p[7] = fo.pqr[1]; p[8] = fo.pqr[2]; p[9] = phi; p[10] = tht; p[11] = psi;
+}
+
+// ------------------------------------------------------------------------------------ reset / step of one env
+// JSBSimEnv.reset + PositionReward.reset (jsbsim_gym.py:289-331, 511-519): restore the snapshot, set
+// the goal, build the reset frame (the caller replicates it into all ten rows).
+template <typename R>
+F16_HD void env_reset_one(Veh<R>& s, EnvScalars& es, const double* snapshot, const double* snapshot_props,
+                          const float* goal, float* frame16) {
+  veh_from_packed(s, snapshot);
+  es.gx = goal[0]; es.gy = goal[1]; es.gz = goal[2];
+  float o[12];
+  props_to_frame(snapshot_props, o);
+  for (int i = 0; i < 12; ++i) frame16[i] = o[i];
+  frame16[12] = es.gx; frame16[13] = es.gy; frame16[14] = es.gz; frame16[15] = 0.0f;
+  es.last_d = goal_distance(o, es.gx, es.gy, es.gz);
+  es.step = 0;
+  es.ep_ret = 0.0f;
+  es.ep_len = 0;
+}
+
+enum { STEP_ACTIVE = 1, STEP_RESET = 2, STEP_TERMINAL = 4, STEP_DONE = 8, STEP_TRUNCATED = 16, STEP_CRASH = 32, STEP_GOAL = 64 };
+
+// One env-step. On return frame16 is the newest row of the env's observation stack (or, if the env
+// auto-reset, the reset frame, with tframe16 holding the terminal step's newest row).
+template <typename R>
+F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const MassSet* msets, const double* snapshot,
+                        const double* snapshot_props, const float* act, uint64_t seed, uint64_t env_id, int auto_reset,
+                        float* frame16, float* tframe16, float* reward_out, float* ep_ret_out, int32_t* ep_len_out) {
+  // action -> fcs/*-cmd-norm (jsbsim_gym.py:216-222): float32 -> double widening, no clipping
+  Cmd<R> cmd = {(R)act[0], (R)act[1], (R)act[2], (R)act[3]};
+  es.step += 1;
+  // 4 FDM frames (jsbsim_gym.py:225-232); tanks stay at 1000 lb and gear at 0 by construction
+  FrameObs<R> fo;
+  FrameCfg cfg = {kDt, 0.0, MS_FLIGHT};
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 4; ++k) fdm_frame<R, false>(s, T, msets, cfg, cmd, es.step == 1 && k == 0, fo);
+
+  // observation frame, reward, termination - all on the float32 frame (jsbsim_gym.py:237-261)
+  float o[12];
+  frame_from_fdm<R>(s, fo, o);
+  float reward = 0.0f;
+  bool terminated = false, truncated = false;
+  int flags = STEP_ACTIVE;
+  const float alt = o[2];
+  if (alt < 10.0f) { reward = -10.0f; terminated = true; flags |= STEP_CRASH; }
+  {
+    float ex = fsub_rn(o[0], es.gx), ey = fsub_rn(o[1], es.gy);
+    float d2 = fadd_rn(fmul_rn(ex, ex), fmul_rn(ey, ey));
+    if (!terminated && fsqrt_rn(d2) < 100.0f && fabsf(fsub_rn(alt, es.gz)) < 100.0f) { reward = 10.0f; terminated = true; flags |= STEP_GOAL; }
+  }
+  if (!terminated && es.step >= 1200) truncated = true;
+  // PositionReward.step (jsbsim_gym.py:487-509): reward += 1e-2 * (last_distance - distance), float32
+  const float d = goal_distance(o, es.gx, es.gy, es.gz);
+  reward = fadd_rn(reward, fmul_rn(0.01f, fsub_rn(es.last_d, d)));
+  es.last_d = d;
+  es.ep_ret += reward;
+  es.ep_len += 1;
+  *reward_out = reward;
+  for (int i = 0; i < 12; ++i) frame16[i] = o[i];
+  frame16[12] = es.gx; frame16[13] = es.gy; frame16[14] = es.gz; frame16[15] = 0.0f;
+  if (truncated) flags |= STEP_TRUNCATED;
+  if (terminated || truncated) {
+    flags |= STEP_DONE;
+    *ep_ret_out = es.ep_ret;
+    *ep_len_out = es.ep_len;
+    if (auto_reset) {
+      for (int i = 0; i < 16; ++i) tframe16[i] = frame16[i];
+      flags |= STEP_RESET | STEP_TERMINAL;
+      es.episodes += 1;
+      float g[3];
+      sample_goal(seed, env_id, es.episodes, g);
+      env_reset_one<R>(s, es, snapshot, snapshot_props, g, frame16);
+    }
+  }
+  return flags;
+}
+
+}  // namespace f16

@@ -1,0 +1,110 @@
+/* f16_b200.h - C ABI of the B200-native batched F-16 environment (libf16b200.so).
+ *
+ * This is the drop-in boundary for the reference's env-step path. The reference reaches its
+ * flight-dynamics code through the Python binding of JSBSim, one FGFDMExec per environment
+ * (jsbsim_gym/jsbsim_gym.py:151-155 construct/load_model/run_ic, :168-170 ic properties,
+ * :219-232 command + tank/gear properties + 4 x run(), :181-182 twelve property reads,
+ * :305-306 run_ic + propulsion/set-running). One f16_step() call replaces, for N environments at
+ * once, everything JSBSimEnv.step + PositionReward.step do (jsbsim_gym.py:199-287, 487-509):
+ * action mapping, 4 FDM frames, observation frame, 10-frame stack, reward, termination, truncation,
+ * and - with auto_reset - the DummyVecEnv reset-on-done convention
+ * (stable_baselines3/common/vec_env/dummy_vec_env.py:56-73).
+ *
+ * Conventions: opaque handle; device buffers are owned by the caller (PyTorch in this repo) and
+ * bound once; every launch goes to the caller-supplied cudaStream_t (passed as void*); no hidden
+ * synchronisation except in the *_host entry points and get/set_state; int status returns
+ * (0 = ok, negative = error) with f16_last_error() giving the message for the calling thread.
+ * There is no CPU fallback: every entry point needs a CUDA device.
+ */
+#ifndef F16_B200_H
+#define F16_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "f16_state_fields.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct f16_ctx* f16_handle;
+
+enum { F16_MODE_FP64 = 0, /* parity mode: all model math in double            */
+       F16_MODE_FP32 = 1  /* throughput mode: float math, double kinematics    */ };
+
+enum { F16_OBS_FRAMES = 10, F16_OBS_FEATURES = 15, F16_ACTION_DIM = 4, F16_NUM_STATS = 8 };
+
+/* Replaces jsbsim.FGFDMExec(root, None) + load_model('f16') + the constructor's run_ic()
+ * (jsbsim_gym.py:151-155) for n_envs environments on CUDA device `device`. Computes the canonical
+ * post-reset snapshot on the device (fresh construct -> run_ic -> reset's run_ic + set-running). */
+int f16_create(f16_handle* out, int64_t n_envs, int device, int mode);
+int f16_destroy(f16_handle h);
+
+/* Bytes of device memory the caller must provide for the structure-of-arrays state. */
+size_t f16_state_bytes(f16_handle h);
+
+/* Bind caller-owned device buffers. state: f16_state_bytes() bytes, 256-byte aligned.
+ * obs: N x 10 x 15 float (row 0 oldest, row 9 newest; jsbsim_gym.py:150,235,263).
+ * reward: N float. done/truncated: N uint8. terminal_obs: N x 10 x 15 float or NULL.
+ * ep_return / ep_len: N float / N int32, written when an episode ends (Monitor's info["episode"],
+ * stable_baselines3/common/monitor.py:96-109), or NULL. */
+int f16_bind(f16_handle h, void* state, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
+             float* terminal_obs, float* ep_return, int32_t* ep_len);
+
+/* JSBSimEnv.reset + PositionReward.reset (jsbsim_gym.py:289-331, 511-519) for every env whose mask
+ * byte is non-zero (mask == NULL: all). goals: N x 3 float device pointer holding the goal of
+ * every env (entries of unmasked envs are ignored), or NULL to sample distance~U[1000,10000) m,
+ * bearing~U[0,2pi), altitude~U[1000,4000) m (jsbsim_gym.py:315-317) from Philox4x32-10 keyed by
+ * (seed, global env id, episode counter). */
+int f16_reset(f16_handle h, const uint8_t* mask, const float* goals, uint64_t seed, void* stream);
+
+/* One env-step for all N envs. actions: N x 4 float device pointer
+ * [roll, pitch, yaw, throttle] -> fcs/{aileron,elevator,rudder,throttle}-cmd-norm, un-clipped
+ * (jsbsim_gym.py:216-222); NULL samples action_space.sample()-like uniform actions in-kernel
+ * (Philox, keyed by seed/env/step). auto_reset != 0: an env that finishes is reset in the same
+ * launch (new Philox goal), its stacked terminal observation goes to terminal_obs, and obs holds
+ * the reset observation, as DummyVecEnv does. */
+int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream);
+
+/* Same step through HOST buffers (the reference-facing call: NumPy in, NumPy out). Copies
+ * actions host->device, steps, copies obs/reward/done/truncated device->host and synchronises.
+ * Pinned host memory makes the copies asynchronous DMA; pageable memory works but is slower.
+ * Any output pointer may be NULL to skip that copy. */
+int f16_step_host(f16_handle h, const float* actions_host, int auto_reset, float* obs_host,
+                  float* reward_host, uint8_t* done_host, uint8_t* truncated_host, void* stream);
+
+/* Offset the global env ids used for Philox keys (multi-GPU: rank r owns ids [base, base+N)). */
+int f16_set_env_id_base(f16_handle h, int64_t base);
+
+/* Packed double state of one env (field order: f16_state_fields.h), for parity tests and teacher
+ * forcing. n must be F16_NUM_STATE_FIELDS. Synchronises. */
+int f16_get_state(f16_handle h, int64_t env, double* out, int n);
+int f16_set_state(f16_handle h, int64_t env, const double* in, int n);
+/* Batch variants on device memory: packed is N x F16_NUM_STATE_FIELDS doubles (device pointer). */
+int f16_pack_states(f16_handle h, double* packed_dev, void* stream);
+int f16_unpack_states(f16_handle h, const double* packed_dev, void* stream);
+/* Env-layer bookkeeping of one env: current_step (jsbsim_gym.py:215) for teacher forcing. */
+int f16_set_env_step(f16_handle h, int64_t env, int32_t current_step);
+
+/* The canonical post-reset state (packed, F16_NUM_STATE_FIELDS doubles) followed by the twelve
+ * STATE_FORMAT properties (jsbsim_gym.py:12-25) read right after reset, as doubles. */
+int f16_get_snapshot(f16_handle h, double* state_out, double* props12_out);
+
+/* Rollout statistics accumulated on the device since the last call with reset != 0:
+ * [0] episodes finished, [1] sum of episode returns, [2] sum of episode lengths, [3] crashes,
+ * [4] goals reached, [5] truncations, [6] env-steps, [7] reserved. Synchronises `stream`. */
+int f16_get_stats(f16_handle h, double* out8, int reset, void* stream);
+/* Device pointer to those 8 doubles (for an NCCL all-reduce by the caller). */
+int f16_stats_device_ptr(f16_handle h, double** out);
+
+/* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
+int64_t f16_launch_count(void);
+
+const char* f16_last_error(void);
+const char* f16_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F16_B200_H */

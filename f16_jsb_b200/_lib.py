@@ -1,0 +1,69 @@
+"""ctypes binding of libf16b200.so (include/f16_b200.h). No CPU fallback: errors are loud."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_lib = None
+
+
+class F16Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library, building it in-tree first if the sources are newer."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if _build.needs_build():
+        try:
+            _build.build_library()
+        except Exception as e:  # pragma: no cover - depends on toolchain
+            if not os.path.exists(path):
+                raise F16Error("libf16b200.so is missing and could not be built (%s); "
+                               "there is no CPU fallback for the F-16 env" % e) from e
+    L = C.CDLL(path)
+    vp, i64, u64, i32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int
+    L.f16_create.argtypes = [C.POINTER(vp), i64, i32, i32]
+    L.f16_destroy.argtypes = [vp]
+    L.f16_state_bytes.argtypes = [vp]
+    L.f16_state_bytes.restype = C.c_size_t
+    L.f16_bind.argtypes = [vp] + [vp] * 8
+    L.f16_reset.argtypes = [vp, vp, vp, u64, vp]
+    L.f16_step.argtypes = [vp, vp, i32, vp]
+    L.f16_step_host.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
+    L.f16_set_env_id_base.argtypes = [vp, i64]
+    L.f16_get_state.argtypes = [vp, i64, vp, i32]
+    L.f16_set_state.argtypes = [vp, i64, vp, i32]
+    L.f16_pack_states.argtypes = [vp, vp, vp]
+    L.f16_unpack_states.argtypes = [vp, vp, vp]
+    L.f16_set_env_step.argtypes = [vp, i64, C.c_int32]
+    L.f16_get_snapshot.argtypes = [vp, vp, vp]
+    L.f16_get_stats.argtypes = [vp, vp, i32, vp]
+    L.f16_stats_device_ptr.argtypes = [vp, C.POINTER(vp)]
+    L.f16_launch_count.restype = i64
+    L.f16_num_state_fields.restype = i32
+    L.f16_last_error.restype = C.c_char_p
+    L.f16_version.restype = C.c_char_p
+    for name in ("f16_create", "f16_destroy", "f16_bind", "f16_reset", "f16_step", "f16_step_host",
+                 "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states",
+                 "f16_unpack_states", "f16_set_env_step", "f16_get_snapshot", "f16_get_stats",
+                 "f16_stats_device_ptr"):
+        getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().f16_last_error().decode(errors="replace")
+        raise F16Error("%s failed: %s" % (what or "f16 call", msg))
+
+
+EXPORTED_SYMBOLS = (
+    "f16_create", "f16_destroy", "f16_state_bytes", "f16_bind", "f16_reset", "f16_step", "f16_step_host",
+    "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states", "f16_unpack_states",
+    "f16_set_env_step", "f16_get_snapshot", "f16_get_stats", "f16_stats_device_ptr", "f16_launch_count", "f16_num_state_fields",
+    "f16_last_error", "f16_version")

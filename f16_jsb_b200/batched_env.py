@@ -1,0 +1,159 @@
+"""F16BatchedEnv - N F-16 environments resident on one B200, stepped by libf16b200.so.
+
+PyTorch only owns the device memory and the stream; every numeric operation is in the CUDA library
+(f16_jsb_b200/csrc). The torch-tensor API (`reset`, `step`) never leaves the device; `step_host` is
+the NumPy-in / NumPy-out call with the host<->device copies inside (what SB3's stock loops use).
+"""
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .constants import NUM_FEATURES, NUM_STACKED_FRAMES
+
+MODE_FP64, MODE_FP32 = 0, 1
+NUM_STATS = 8
+STAT_NAMES = ("episodes", "return_sum", "length_sum", "crashes", "goals", "truncations", "env_steps", "reserved")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class F16BatchedEnv:
+    """Batched replacement of JSBSimEnv+PositionReward (jsbsim_gym/jsbsim_gym.py:95-533).
+
+    mode: "fp64" (parity: all model math in double) or "fp32" (throughput: float math, double
+    kinematic state). Observations are (N, 10, 15) float32, row 0 oldest, row 9 newest.
+    """
+
+    def __init__(self, num_envs: int, device=None, mode: str = "fp32", seed: int = 0,
+                 with_terminal_obs: bool = True, env_id_base: int = 0):
+        if not torch.cuda.is_available():
+            raise _lib.F16Error("F16BatchedEnv needs a CUDA device: the F-16 env has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.F16Error("F16BatchedEnv only runs on CUDA devices (got %s)" % self.device)
+        self.num_envs = int(num_envs)
+        self.mode = {"fp64": MODE_FP64, "fp32": MODE_FP32}[mode]
+        self.mode_name = mode
+        self.seed = int(seed)
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        h = C.c_void_p()
+        _lib.check(self.lib.f16_create(C.byref(h), self.num_envs, dev_index, self.mode), "f16_create")
+        self._h = h
+        n = self.num_envs
+        with torch.cuda.device(self.device):
+            self.state = torch.zeros(self.lib.f16_state_bytes(h), dtype=torch.uint8, device=self.device)
+            self.obs = torch.zeros((n, NUM_STACKED_FRAMES, NUM_FEATURES), dtype=torch.float32, device=self.device)
+            self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.done = torch.zeros(n, dtype=torch.uint8, device=self.device)
+            self.truncated = torch.zeros(n, dtype=torch.uint8, device=self.device)
+            self.terminal_obs = torch.zeros_like(self.obs) if with_terminal_obs else None
+            self.ep_return = torch.zeros(n, dtype=torch.float32, device=self.device)
+            self.ep_len = torch.zeros(n, dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.f16_bind(h, _ptr(self.state), _ptr(self.obs), _ptr(self.reward), _ptr(self.done),
+                                     _ptr(self.truncated), _ptr(self.terminal_obs), _ptr(self.ep_return),
+                                     _ptr(self.ep_len)), "f16_bind")
+        if env_id_base:
+            _lib.check(self.lib.f16_set_env_id_base(h, int(env_id_base)), "f16_set_env_id_base")
+        sp = C.c_void_p()
+        _lib.check(self.lib.f16_stats_device_ptr(h, C.byref(sp)), "f16_stats_device_ptr")
+        self._stats_ptr = sp.value
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.f16_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ device-resident API
+    def reset(self, mask: Optional[torch.Tensor] = None, goals: Optional[torch.Tensor] = None,
+              seed: Optional[int] = None) -> torch.Tensor:
+        """Reset masked envs (all if mask is None). goals: (N,3) float32 cuda tensor or None (Philox)."""
+        if seed is not None:
+            self.seed = int(seed)
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        if goals is not None:
+            goals = goals.to(device=self.device, dtype=torch.float32).contiguous()
+            assert goals.shape == (self.num_envs, 3)
+        _lib.check(self.lib.f16_reset(self._h, _ptr(mask), _ptr(goals), self.seed, self._stream()), "f16_reset")
+        return self.obs
+
+    def step(self, actions: Optional[torch.Tensor], auto_reset: bool = True):
+        """One env-step on the current CUDA stream; returns views of the bound device tensors
+        (obs, reward, done, truncated). actions: (N,4) float32 cuda tensor, or None for in-kernel
+        uniform random actions."""
+        if actions is not None:
+            if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
+                actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
+            assert actions.shape == (self.num_envs, 4)
+        _lib.check(self.lib.f16_step(self._h, _ptr(actions), int(auto_reset), self._stream()), "f16_step")
+        return self.obs, self.reward, self.done, self.truncated
+
+    # ------------------------------------------------------------------ host-buffer API
+    def step_host(self, actions: np.ndarray, obs_out: Optional[np.ndarray], reward_out: Optional[np.ndarray],
+                  done_out: Optional[np.ndarray], truncated_out: Optional[np.ndarray], auto_reset: bool = True):
+        """NumPy in / NumPy out; host->device and device->host copies and a stream sync inside."""
+        assert actions.dtype == np.float32 and actions.flags.c_contiguous and actions.shape == (self.num_envs, 4)
+
+        def p(a):
+            return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+        _lib.check(self.lib.f16_step_host(self._h, p(actions), int(auto_reset), p(obs_out), p(reward_out), p(done_out),
+                                          p(truncated_out), self._stream()), "f16_step_host")
+
+    # ------------------------------------------------------------------ parity / debugging
+    @property
+    def num_state_fields(self) -> int:
+        return int(self.lib.f16_num_state_fields())
+
+    def get_state(self, env: int) -> np.ndarray:
+        out = np.zeros(self.num_state_fields, dtype=np.float64)
+        _lib.check(self.lib.f16_get_state(self._h, int(env), C.c_void_p(out.ctypes.data), out.size), "f16_get_state")
+        return out
+
+    def set_state(self, env: int, packed: np.ndarray, current_step: Optional[int] = None) -> None:
+        a = np.ascontiguousarray(packed, dtype=np.float64)
+        _lib.check(self.lib.f16_set_state(self._h, int(env), C.c_void_p(a.ctypes.data), a.size), "f16_set_state")
+        if current_step is not None:
+            _lib.check(self.lib.f16_set_env_step(self._h, int(env), int(current_step)), "f16_set_env_step")
+
+    def pack_states(self) -> torch.Tensor:
+        out = torch.empty((self.num_envs, self.num_state_fields), dtype=torch.float64, device=self.device)
+        _lib.check(self.lib.f16_pack_states(self._h, _ptr(out), self._stream()), "f16_pack_states")
+        return out
+
+    def unpack_states(self, packed: torch.Tensor) -> None:
+        packed = packed.to(device=self.device, dtype=torch.float64).contiguous()
+        assert packed.shape == (self.num_envs, self.num_state_fields)
+        _lib.check(self.lib.f16_unpack_states(self._h, _ptr(packed), self._stream()), "f16_unpack_states")
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def snapshot(self):
+        st = np.zeros(self.num_state_fields, dtype=np.float64)
+        props = np.zeros(12, dtype=np.float64)
+        _lib.check(self.lib.f16_get_snapshot(self._h, C.c_void_p(st.ctypes.data), C.c_void_p(props.ctypes.data)), "f16_get_snapshot")
+        return st, props
+
+    # ------------------------------------------------------------------ statistics
+    def stats(self, reset: bool = False) -> dict:
+        out = np.zeros(NUM_STATS, dtype=np.float64)
+        _lib.check(self.lib.f16_get_stats(self._h, C.c_void_p(out.ctypes.data), int(reset), self._stream()), "f16_get_stats")
+        return dict(zip(STAT_NAMES, out.tolist()))
+
+    def launch_count(self) -> int:
+        return int(self.lib.f16_launch_count())

@@ -1,0 +1,38 @@
+"""Builds libf16b200.so (the CUDA library behind include/f16_b200.h) in-tree with nvcc for sm_100a."""
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libf16b200.so")
+SOURCES = [os.path.join(_HERE, "csrc", "f16_b200.cu")]
+DEPS = [os.path.join(_HERE, "csrc", f) for f in
+        ("f16_b200.cu", "f16_model.cuh", "f16_env.cuh", "f16_host_setup.h", "f16_model_data.h")] + [
+    os.path.join(os.path.dirname(_HERE), "include", f) for f in ("f16_b200.h", "f16_state_fields.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found: the F-16 env has no CPU fallback and needs the CUDA toolkit to build")
+    return p
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if force or needs_build():
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

@@ -373,6 +373,7 @@ extern "C" {
 const char* f16_last_error(void) { return g_err.c_str(); }
 const char* f16_version(void) { return "f16_b200 0.1 (sm_100a)"; }
 int64_t f16_launch_count(void) { return g_launches; }
+int f16_num_state_fields(void) { return F16_NUM_STATE_FIELDS; }
 
 int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
   if (!out) return fail("f16_create: out is NULL");

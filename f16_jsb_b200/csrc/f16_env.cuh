@@ -100,10 +100,15 @@ F16_HD void frame_from_fdm(const Veh<R>& s, const FrameObs<R>& fo, float* o) {
   o[0] = fmul_rn(o[0], 6.3781e6f);
   o[1] = fmul_rn(o[1], 6.3781e6f);
 }
-// PositionReward distance (jsbsim_gym.py:499-500): float32 3-D norm, no fused multiply-add
+// PositionReward distance (jsbsim_gym.py:499-500): np.linalg.norm of a float32 3-vector = sqrt(x.dot(x)).
+// NumPy's float32 dot is BLAS sdot, whose scalar tail adds the float32-rounded products in a double
+// accumulator and rounds the sum to float32 once; reproduced here so rewards match bit for bit.
 F16_HD float goal_distance(const float* o, float gx, float gy, float gz) {
   float dx = fsub_rn(gx, o[0]), dy = fsub_rn(gy, o[1]), dz = fsub_rn(gz, o[2]);
-  return fsqrt_rn(fadd_rn(fadd_rn(fmul_rn(dx, dx), fmul_rn(dy, dy)), fmul_rn(dz, dz)));
+  double dot = (double)fmul_rn(dx, dx);
+  dot += (double)fmul_rn(dy, dy);
+  dot += (double)fmul_rn(dz, dz);
+  return fsqrt_rn((float)dot);
 }
 // goal ~ (d cos b, d sin b, alt), d~U[1000,10000), b~U[0,2pi), alt~U[1000,4000) (jsbsim_gym.py:315-323)
 F16_HD void sample_goal(uint64_t seed, uint64_t env_id, uint32_t episode, float* g) {

@@ -1,0 +1,170 @@
+"""F16VecEnv - Stable-Baselines3 VecEnv over the batched CUDA env.
+
+Drop-in for what `PPO('MlpPolicy', gym.make("JSBSim-v0"))` builds internally in the reference
+(Monitor + DummyVecEnv around JSBSimEnv/PositionReward/TimeLimit; train.py:34,113,
+stable_baselines3/common/base_class.py:204-224): pass an instance to PPO/SAC and SB3 uses it as is
+(`isinstance(env, VecEnv)` short-circuits the wrapping). Conventions reproduced from
+stable_baselines3/common/vec_env/dummy_vec_env.py:56-73 and common/monitor.py:85-111:
+done = terminated or truncated; info["TimeLimit.truncated"] = truncated and not terminated;
+on done info["terminal_observation"] holds the last stacked observation, the env is reset in the
+same step and the returned observation is the reset one; info["episode"] = {"r", "l", "t"}.
+"""
+import time
+from collections.abc import Sequence
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from ._compat import VecEnvBase, spaces
+from .batched_env import F16BatchedEnv
+from .constants import (ACTION_HIGH, ACTION_LOW, NUM_FEATURES, NUM_STACKED_FRAMES, SINGLE_OBS_HIGH, SINGLE_OBS_LOW,
+                        sample_goal_numpy)
+
+_EMPTY_INFO_KEYS = ("TimeLimit.truncated",)
+
+
+class _LazyInfos(Sequence):
+    """list[dict]-like view: envs that did not finish share one read-only dict, finished envs get
+    their own dict. Keeps SB3's per-step O(N) Python loops cheap for thousands of envs."""
+
+    def __init__(self, n: int, done_infos: dict):
+        self._n = n
+        self._done = done_infos
+        self._shared = {"TimeLimit.truncated": False}
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if not 0 <= i < self._n:
+            raise IndexError(i)
+        return self._done.get(i, self._shared)
+
+
+def make_spaces():
+    obs_space = spaces.Box(low=np.tile(SINGLE_OBS_LOW, (NUM_STACKED_FRAMES, 1)),
+                           high=np.tile(SINGLE_OBS_HIGH, (NUM_STACKED_FRAMES, 1)),
+                           shape=(NUM_STACKED_FRAMES, NUM_FEATURES), dtype=np.float32)
+    act_space = spaces.Box(low=ACTION_LOW.copy(), high=ACTION_HIGH.copy(), shape=(4,), dtype=np.float32)
+    return obs_space, act_space
+
+
+class F16VecEnv(VecEnvBase):
+    """num_envs F-16 goal-reaching envs on one GPU behind the SB3 VecEnv interface.
+
+    host_ring: number of pinned host buffers the returned NumPy observations rotate through
+    (>= 2 so that SB3's `_last_obs` stays valid across the next step; use copy_obs=True for
+    DummyVecEnv's fresh-array-per-step behaviour).
+    """
+
+    metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 30}   # jsbsim_gym.py:120
+
+    def __init__(self, num_envs: int, device=None, mode: str = "fp32", seed: int = 0, host_ring: int = 2,
+                 copy_obs: bool = False, lazy_infos: Optional[bool] = None, env_id_base: int = 0):
+        obs_space, act_space = make_spaces()
+        self.env = F16BatchedEnv(num_envs, device=device, mode=mode, seed=seed, env_id_base=env_id_base)
+        self.render_mode = None
+        try:
+            super().__init__(num_envs, obs_space, act_space)
+        except Exception:  # SB3's ctor calls get_attr("render_mode"); keep going with plain attributes
+            self.num_envs, self.observation_space, self.action_space = num_envs, obs_space, act_space
+            self.reset_infos = [{} for _ in range(num_envs)]
+            self._seeds = [None for _ in range(num_envs)]
+            self._options = [{} for _ in range(num_envs)]
+        self.copy_obs = copy_obs
+        self.lazy_infos = (num_envs > 64) if lazy_infos is None else lazy_infos
+        ring = max(2, int(host_ring))
+        n = num_envs
+        self._h_obs = [torch.empty((n, NUM_STACKED_FRAMES, NUM_FEATURES), dtype=torch.float32, pin_memory=True) for _ in range(ring)]
+        self._h_rew = [torch.empty(n, dtype=torch.float32, pin_memory=True) for _ in range(ring)]
+        self._h_done = [torch.empty(n, dtype=torch.uint8, pin_memory=True) for _ in range(ring)]
+        self._h_trunc = [torch.empty(n, dtype=torch.uint8, pin_memory=True) for _ in range(ring)]
+        self._h_act = torch.empty((n, 4), dtype=torch.float32, pin_memory=True)
+        self._slot = 0
+        self._actions = None
+        self._t_start = time.time()
+        # attributes of the single env that get_attr serves (jsbsim_gym.py:131,157-163)
+        self.num_stacked_frames = NUM_STACKED_FRAMES
+        self.down_sample = 4
+        self.max_episode_steps = 1200
+        self.dg = 100.0
+
+    # ------------------------------------------------------------------ VecEnv API
+    def reset(self) -> np.ndarray:
+        goals = None
+        if any(s is not None for s in self._seeds):
+            # reference semantics: goal drawn from np.random.default_rng(seed) per env (jsbsim_gym.py:312-323)
+            g = np.stack([sample_goal_numpy(s) for s in self._seeds])
+            goals = torch.from_numpy(g).to(self.env.device)
+        obs = self.env.reset(goals=goals)
+        host = self._h_obs[self._slot]
+        host.copy_(obs, non_blocking=True)
+        torch.cuda.current_stream(self.env.device).synchronize()
+        self._reset_seeds()
+        self._reset_options()
+        self.reset_infos = [{} for _ in range(self.num_envs)]
+        out = host.numpy()
+        return out.copy() if self.copy_obs else out
+
+    def step_async(self, actions: np.ndarray) -> None:
+        a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 4)
+        self._h_act.numpy()[...] = a
+        self._actions = self._h_act.numpy()
+
+    def step_wait(self):
+        self._slot = (self._slot + 1) % len(self._h_obs)
+        k = self._slot
+        obs, rew, done, trunc = self._h_obs[k].numpy(), self._h_rew[k].numpy(), self._h_done[k].numpy(), self._h_trunc[k].numpy()
+        self.env.step_host(self._actions, obs, rew, done, trunc, auto_reset=True)
+        dones = done.astype(bool)
+        done_infos: dict = {}
+        idx = np.flatnonzero(dones)
+        if idx.size:
+            sel = torch.from_numpy(idx).to(self.env.device)
+            term_obs = self.env.terminal_obs.index_select(0, sel).cpu().numpy()
+            ep_r = self.env.ep_return.index_select(0, sel).cpu().numpy()
+            ep_l = self.env.ep_len.index_select(0, sel).cpu().numpy()
+            t = round(time.time() - self._t_start, 6)
+            for j, i in enumerate(idx.tolist()):
+                done_infos[i] = {"TimeLimit.truncated": bool(trunc[i]), "terminal_observation": term_obs[j],
+                                 "episode": {"r": float(ep_r[j]), "l": int(ep_l[j]), "t": t}}
+        if self.lazy_infos:
+            infos: Any = _LazyInfos(self.num_envs, done_infos)
+        else:
+            infos = [done_infos.get(i, {"TimeLimit.truncated": False}) for i in range(self.num_envs)]
+        if self.copy_obs:
+            return obs.copy(), rew.copy(), dones, infos
+        return obs, rew.copy(), dones, infos
+
+    def close(self) -> None:
+        self.env.close()
+
+    def has_attr(self, attr_name: str) -> bool:
+        return hasattr(self, attr_name)
+
+    def get_attr(self, attr_name: str, indices=None):
+        n = len(list(self._get_indices(indices)))
+        return [getattr(self, attr_name, None) for _ in range(n)]
+
+    def set_attr(self, attr_name: str, value, indices=None) -> None:
+        setattr(self, attr_name, value)
+
+    def env_method(self, method_name: str, *method_args, indices=None, **method_kwargs):
+        raise NotImplementedError("F16VecEnv has no per-env Python objects to call %r on" % method_name)
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        n = len(list(self._get_indices(indices)))
+        return [False for _ in range(n)]
+
+    # ------------------------------------------------------------------ device-tensor fast path
+    def reset_torch(self, goals: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.env.reset(goals=goals)
+
+    def step_torch(self, actions: Optional[torch.Tensor]):
+        """Zero-copy path: cuda actions in, (obs, reward, done, truncated) device tensors out."""
+        return self.env.step(actions, auto_reset=True)

@@ -101,6 +101,9 @@ int f16_stats_device_ptr(f16_handle h, double** out);
 /* Number of kernels this library has launched so far in this process (bench.py's gpu_launches). */
 int64_t f16_launch_count(void);
 
+/* Number of doubles in a packed state (= F16_NUM_STATE_FIELDS of f16_state_fields.h). */
+int f16_num_state_fields(void);
+
 const char* f16_last_error(void);
 const char* f16_version(void);
 

@@ -1163,9 +1163,15 @@ struct Env {
     o[1] *= 6.3781e6f;
     for (int i = 0; i < 3; i++) o[12 + i] = goal[i];
   }
-  static float dist3(const float* o) {   // PositionReward: np.linalg.norm(goal - pos) in float32
+  // PositionReward: np.linalg.norm(goal - pos) on float32 (jsbsim_gym.py:499-500) = sqrt(x.dot(x)); NumPy's
+  // float32 dot goes to BLAS sdot, whose scalar tail (n < 32) adds the float32 products in a double
+  // accumulator and rounds the sum to float32 once (OpenBLAS kernel/x86_64/sdot.c).
+  static float dist3(const float* o) {
     float dx = o[12] - o[0], dy = o[13] - o[1], dz = o[14] - o[2];
-    return std::sqrt(dx * dx + dy * dy + dz * dz);
+    float xx = dx * dx, yy = dy * dy, zz = dz * dz;
+    double dot = 0.0;
+    dot += xx; dot += yy; dot += zz;
+    return std::sqrt((float)dot);
   }
   void reset(const float g[3]) {   // jsbsim_gym.py:289-331 + PositionReward.reset :511-519
     current_step = 0;
@@ -1288,6 +1294,43 @@ long long f16o_rollout(int n_envs, int n_steps, uint64_t seed, int n_threads, do
   for (int t = 0; t < n_threads; t++) { cs += sums[t]; n += counts[t]; }
   if (checksum_out) *checksum_out = cs;
   return n;
+}
+
+// ---- batch trajectories for the parity tests: n_envs envs, each reset with goals[e] and driven by
+// actions[k][e][:] for k < n_steps with no auto-reset; stepping of an env stops after its first done
+// (later rows repeat the done flags with zero reward). frames: [n_steps][n_envs][15] newest frame,
+// rewards: [n_steps][n_envs], flags: [n_steps][n_envs] (bit0 terminated, bit1 truncated, bit7 = env
+// was already finished). final_states: [n_envs][F16_NUM_STATE_FIELDS] or NULL.
+void f16o_batch_trajectory(int n_envs, int n_steps, const float* goals, const float* actions, float* frames,
+                           float* rewards, uint8_t* flags, double* final_states, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  std::vector<std::thread> th;
+  auto work = [&](int t) {
+    int lo = (int)((long long)n_envs * t / n_threads), hi = (int)((long long)n_envs * (t + 1) / n_threads);
+    for (int e = lo; e < hi; e++) {
+      Env env;
+      env.reset(goals + 3 * e);
+      bool finished = false;
+      int last = 0;
+      for (int k = 0; k < n_steps; k++) {
+        size_t idx = (size_t)k * n_envs + e;
+        if (!finished) {
+          float r;
+          int fl = env.step(actions + idx * 4, &r);
+          rewards[idx] = r;
+          flags[idx] = (uint8_t)fl;
+          if (fl) { finished = true; last = fl; }
+        } else {
+          rewards[idx] = 0.0f;
+          flags[idx] = (uint8_t)(last | 0x80);
+        }
+        std::memcpy(frames + idx * 15, env.frames[9], 15 * sizeof(float));
+      }
+      if (final_states) pack_state(env.sim, final_states + (size_t)e * F16_NUM_STATE_FIELDS);
+    }
+  };
+  for (int t = 0; t < n_threads; t++) th.emplace_back(work, t);
+  for (auto& x : th) x.join();
 }
 
 }  // extern "C"

@@ -47,6 +47,7 @@ def lib():
         L.f16o_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         L.f16o_rollout.restype = C.c_longlong
         L.f16o_rollout.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+        L.f16o_batch_trajectory.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int]
         _lib = L
     return _lib
 
@@ -137,3 +138,22 @@ def rollout(n_envs: int, n_steps: int, seed: int = 0, n_threads: int = 1):
     cs = C.c_double()
     n = lib().f16o_rollout(int(n_envs), int(n_steps), int(seed), int(n_threads), C.byref(cs))
     return int(n), cs.value
+
+
+def batch_trajectory(goals: np.ndarray, actions: np.ndarray, n_threads: int = 0, want_states: bool = False):
+    """goals (N,3) f32, actions (T,N,4) f32 -> frames (T,N,15) f32, rewards (T,N) f32, flags (T,N) u8
+    [, final packed states (N,NF) f64]; no auto-reset, stepping of an env stops at its first done."""
+    goals = np.ascontiguousarray(goals, dtype=np.float32)
+    actions = np.ascontiguousarray(actions, dtype=np.float32)
+    T, N = actions.shape[0], actions.shape[1]
+    assert goals.shape == (N, 3) and actions.shape == (T, N, 4)
+    frames = np.zeros((T, N, 15), dtype=np.float32)
+    rewards = np.zeros((T, N), dtype=np.float32)
+    flags = np.zeros((T, N), dtype=np.uint8)
+    nf = lib().f16o_num_state_fields()
+    states = np.zeros((N, nf), dtype=np.float64) if want_states else None
+    if n_threads <= 0:
+        n_threads = min(os.cpu_count() or 1, max(1, N))
+    lib().f16o_batch_trajectory(N, T, goals.ctypes.data, actions.ctypes.data, frames.ctypes.data, rewards.ctypes.data,
+                                flags.ctypes.data, states.ctypes.data if want_states else None, int(n_threads))
+    return (frames, rewards, flags, states) if want_states else (frames, rewards, flags)

@@ -1,0 +1,207 @@
+"""Known-answer tests that pin the oracle: no reference test exists for this path, so
+the pins are analytic - US Standard Atmosphere 1976 values, table lookups at and between breakpoints
+against the parsed XML, mass properties, the IC flight condition, integrator and component laws."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def fdm(oracle):
+    f = oracle.OracleFDM()
+    f["propulsion/set-running"] = -1
+    f["ic/u-fps"] = 900.0
+    f["ic/h-sl-ft"] = 5000.0
+    f.run_ic()
+    return f
+
+
+@pytest.fixture(scope="module")
+def model():
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "f16_model.json")))
+
+
+def test_isa1976_at_5000ft(fdm):
+    # US Standard Atmosphere 1976 at 5000 ft geometric: T = 500.843 R, P = 1760.88 psf,
+    # rho = 2.04819e-3 slug/ft3, a = 1097.09 ft/s (SURVEY.md A.4 KAT)
+    assert fdm["position/h-sl-ft"] == pytest.approx(5000.0, abs=1e-6)
+    assert fdm["atmosphere/T-R"] == pytest.approx(500.843474, rel=1e-8)
+    assert fdm["atmosphere/P-psf"] == pytest.approx(1760.881378, rel=1e-8)
+    assert fdm["atmosphere/rho-slugs_ft3"] == pytest.approx(2.04818798e-3, rel=1e-7)
+    assert fdm["atmosphere/a-fps"] == pytest.approx(1097.094814, rel=1e-8)
+    # standard day: density altitude equals geometric altitude
+    assert fdm["atmosphere/density-altitude"] == pytest.approx(5000.0, abs=1e-6)
+
+
+@pytest.mark.parametrize("h_ft,T,P", [(0.0, 518.67, 2116.228), (36089.2388 * 20855531.5 / (20855531.5 - 36089.2388), 389.97, 472.6792),
+                                      (50000.0, 389.97, 243.61)])
+def test_isa1976_layers(oracle, h_ft, T, P):
+    f = oracle.OracleFDM()
+    f["ic/u-fps"] = 500.0
+    f["ic/h-sl-ft"] = h_ft
+    f.run_ic()
+    assert f["atmosphere/T-R"] == pytest.approx(T, rel=2e-5)
+    assert f["atmosphere/P-psf"] == pytest.approx(P, rel=2e-4)
+    assert f["atmosphere/rho-slugs_ft3"] == pytest.approx(f["atmosphere/P-psf"] / (1716.557158 * f["atmosphere/T-R"]), rel=1e-9)
+
+
+def test_ic_flight_condition(fdm):
+    # Mach 0.82035, qbar 829.516 psf, CAS 500.97 kt at u = 900 ft/s, 5000 ft
+    assert fdm["velocities/mach"] == pytest.approx(0.82035, abs=1e-5)
+    assert fdm["aero/qbar-psf"] == pytest.approx(829.516, abs=1e-3)
+    assert fdm["velocities/vc-kts"] == pytest.approx(500.97, abs=1e-2)
+    assert fdm["aero/alpha-rad"] == 0.0 and fdm["aero/beta-rad"] == 0.0
+    assert fdm["velocities/u-fps"] == pytest.approx(900.0, rel=1e-12)
+    assert fdm["position/lat-gc-rad"] == 0.0 and fdm["position/long-gc-rad"] == 0.0
+    assert fdm["attitude/psi-rad"] == pytest.approx(0.0, abs=1e-12)
+    # J2 gravity at the equator, 5000 ft
+    assert fdm["accelerations/gravity-ft_sec2"] == pytest.approx(32.1834, abs=2e-3)
+
+
+def test_mass_properties_ic_and_flight(oracle, fdm):
+    # run_ic frames: both internal tanks at their initial 1500 lb (f16.xml:264-281)
+    assert fdm["inertia/weight-lbs"] == pytest.approx(17400 + 230 + 3000)
+    # flight frames: env holds the tanks at 1000 lb each (jsbsim_gym.py:227-228): W = 19630 lb,
+    # CG = (-192.7828, 0, -4.0112) in
+    f = oracle.OracleFDM()
+    f["ic/u-fps"] = 900.0
+    f["ic/h-sl-ft"] = 5000.0
+    f.run_ic()
+    for _ in range(2):
+        f["propulsion/tank/contents-lbs"] = 1000.0
+        f["propulsion/tank[1]/contents-lbs"] = 1000.0
+        f.run()
+    assert f["inertia/weight-lbs"] == pytest.approx(19630.0)
+    assert f["inertia/mass-slugs"] == pytest.approx(19630.0 / 32.174049, rel=1e-12)
+    assert f["inertia/cg-x-in"] == pytest.approx(-192.782781, abs=1e-5)
+    assert f["inertia/cg-y-in"] == pytest.approx(0.0, abs=1e-12)
+    assert f["inertia/cg-z-in"] == pytest.approx(-4.011207, abs=1e-5)
+    # negated_crossproduct_inertia="true" with ixz = -982 gives the physical Ixz = +982 (plus point masses)
+    assert f["inertia/ixz-slugs_ft2"] > 900.0
+    # parallel axis theorem by hand for Iyy
+    cg = np.array([f["inertia/cg-x-in"], 0.0, f["inertia/cg-z-in"]])
+    iyy = 55814.0
+    for w, loc in ((17400, (-193, 0, -5.1)), (230, (-336.2, 0, 0)), (1000, (-174.4, 65, 5)), (1000, (-174.4, -65, 5))):
+        d = (np.array(loc) - cg) / 12.0
+        iyy += w / 32.174049 * (d[0] ** 2 + d[2] ** 2)
+    assert f["inertia/iyy-slugs_ft2"] == pytest.approx(iyy, rel=1e-9)
+
+
+def _interp1(x, y, k):
+    return float(np.interp(k, x, y))
+
+
+def test_aero_tables_against_parsed_xml(oracle, model):
+    """Every aero <function> value the oracle reports equals the product of its factors evaluated
+    independently from the parsed XML (numpy interpolation), at a perturbed flight condition."""
+    f = oracle.OracleFDM()
+    f["ic/u-fps"] = 700.0
+    f["ic/h-sl-ft"] = 12000.0
+    f.run_ic()
+    for k in range(40):   # fly a little with controls deflected so every factor is non-trivial
+        for name, val in (("fcs/aileron-cmd-norm", 0.3), ("fcs/elevator-cmd-norm", -0.4), ("fcs/rudder-cmd-norm", 0.2),
+                          ("fcs/throttle-cmd-norm", 0.9), ("gear/gear-cmd-norm", 0.0), ("gear/gear-pos-norm", 0.0)):
+            f[name] = val
+        f.run()
+
+    def prop(p):
+        return {"metrics/Sw-sqft": 300.0, "metrics/bw-ft": 30.0, "metrics/cbarw-ft": 11.32}.get(p) or f[p]
+
+    def table(t):
+        if t["kind"] == "1d":
+            return _interp1(t["rows"], t["data"], prop(t["row_prop"]))
+        rk, ck = prop(t["row_prop"]), prop(t["col_prop"])
+        rows, cols, d = np.array(t["rows"]), np.array(t["cols"]), np.array(t["data"])
+        col_vals = [np.interp(rk, rows, d[:, j]) for j in range(len(cols))]
+        return float(np.interp(ck, cols, col_vals))
+
+    n = 0
+    for ax in model["aero"]["axes"]:
+        for fn in ax["functions"]:
+            want = 1.0
+            for fac in fn["factors"]:
+                want *= prop(fac["prop"]) if fac["kind"] == "property" else (fac["value"] if fac["kind"] == "value" else table(fac["table"]))
+            got = f[fn["name"]]
+            assert got == pytest.approx(want, rel=1e-9, abs=1e-9), fn["name"]
+            n += 1
+    assert n == 40
+    assert abs(f["aero/alpha-rad"]) > 1e-3   # the condition really was off-nominal
+
+
+def test_table_clamping_and_breakpoints(oracle, model):
+    # engine table at and outside its corners through the trim thrust: M = 0.82, h_d = 5000 ft (inside),
+    # then the clamped lookup: kCLge is 1.0 far above the ground
+    f = oracle.OracleFDM()
+    f["ic/u-fps"] = 900.0
+    f["ic/h-sl-ft"] = 5000.0
+    f.run_ic()
+    assert f["aero/function/kCLge"] == 1.0
+    t = model["engine"]["tables"]["IdleThrust"]
+    rows, cols, d = np.array(t["rows"]), np.array(t["cols"]), np.array(t["data"])
+    m, hd = f["velocities/mach"], f["atmosphere/density-altitude"]
+    idle = float(np.interp(hd, cols, [np.interp(m, rows, d[:, j]) for j in range(len(cols))]))
+    # zero throttle, zero-dt frame: thrust = MilThrust * idle * (1 - bleed)  (FGTurbine::Trim)
+    assert f["propulsion/engine/thrust-lbs"] == pytest.approx(17800.0 * idle * 0.97, rel=1e-9)
+
+
+def test_quaternion_stays_normalised_and_truncation_bookkeeping(oracle):
+    env = oracle.OracleEnv()
+    env.reset(oracle.sample_goal(3))
+    rng = np.random.default_rng(3)
+    for k in range(200):
+        env.step(rng.uniform([-1, -1, -1, 0], [1, 1, 1, 1]).astype(np.float32))
+        s = env.fdm.pack_state()
+        assert abs(np.linalg.norm(s[0:4]) - 1.0) < 2e-10
+    assert env.fdm["simulation/epa-rad"] == pytest.approx(7.292115e-5 * 800 / 120.0, rel=1e-9)
+
+
+def test_engine_spool_and_afterburner(oracle):
+    env = oracle.OracleEnv()
+    env.reset(oracle.sample_goal(0))
+    assert env.fdm["propulsion/engine/n2"] == 100.0          # InitRunning leaves the spool at 100 %
+    for _ in range(60):
+        env.step(np.array([0, -0.1, 0, 0.25], np.float32))   # ThrottlePos = 0.5 -> N2 target 80 %
+    assert env.fdm["propulsion/engine/n2"] == pytest.approx(80.0, abs=1e-9)
+    assert env.fdm["propulsion/engine/augmentation"] == 0.0
+    dry = env.fdm["propulsion/engine/thrust-lbs"]
+    for _ in range(90):
+        env.step(np.array([0, -0.1, 0, 1.0], np.float32))    # ThrottlePos = 2 -> full afterburner
+    assert env.fdm["propulsion/engine/n2"] == pytest.approx(100.0, abs=1e-9)
+    assert env.fdm["propulsion/engine/augmentation"] == 1.0
+    assert env.fdm["propulsion/engine/thrust-lbs"] > 2.0 * dry
+
+
+def test_fcs_actuator_rate_limits(oracle):
+    # elevator kinematic: +-1 in 0.3 s -> at most 2/0.3/120 per frame (f16.xml:630-643)
+    env = oracle.OracleEnv()
+    env.reset(oracle.sample_goal(0))
+    prev = env.fdm["fcs/elevator-pos-norm"]
+    for k in range(4):
+        env.fdm["fcs/elevator-cmd-norm"] = -1.0
+        env.fdm["propulsion/tank/contents-lbs"] = 1000.0
+        env.fdm["propulsion/tank[1]/contents-lbs"] = 1000.0
+        env.fdm["gear/gear-cmd-norm"] = 0.0
+        env.fdm["gear/gear-pos-norm"] = 0.0
+        env.fdm.run()
+        cur = env.fdm["fcs/elevator-pos-norm"]
+        assert abs(cur - prev) <= 2.0 / 0.3 / 120.0 + 1e-12
+        prev = cur
+    # PID integrators are frozen above the trigger speeds: the g-load integral keeps its IC value
+    assert env.fdm["fcs/elevator-pid-trigger"] == 1.0
+
+
+def test_reset_frame_layout(oracle):
+    env = oracle.OracleEnv()
+    g = oracle.sample_goal(7)
+    obs = env.reset(g)
+    assert obs.shape == (10, 15) and obs.dtype == np.float32
+    assert np.all(obs == obs[0])                       # ten copies of the reset frame (jsbsim_gym.py:328-329)
+    assert np.array_equal(obs[0, 12:], g)
+    assert obs[0, 2] == np.float32(1524.0)             # 5000 ft in metres
+    assert obs[0, 0] == 0.0 and obs[0, 1] == 0.0
+    assert math.isclose(float(obs[0, 3]), 0.82034844, rel_tol=1e-6)

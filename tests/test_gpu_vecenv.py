@@ -1,0 +1,69 @@
+"""SB3 VecEnv / Gymnasium surface on the GPU: return types, shapes, auto-reset infos, seeding."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vecenv_api_contract(golden):
+    from f16_jsb_b200 import F16VecEnv
+    n = 8
+    env = F16VecEnv(n, mode="fp64", lazy_infos=False)
+    assert env.num_envs == n and env.observation_space.shape == (10, 15) and env.action_space.shape == (4,)
+    assert env.get_attr("render_mode") == [None] * n and env.env_is_wrapped(object) == [False] * n
+    env.seed(0)
+    obs = env.reset()
+    assert obs.shape == (n, 10, 15) and obs.dtype == np.float32
+    # seed(s) -> env i is reset with seed s+i, goal = default_rng(s+i) draw (jsbsim_gym.py:312-323)
+    assert np.array_equal(obs[0, 0, 12:], golden["random0"]["goal"]) and np.array_equal(obs[1, 0, 12:], golden["random1"]["goal"])
+    t = golden["random0"]
+    a = np.tile(t["actions"][0], (n, 1))
+    obs2, rew, dones, infos = env.step(a)
+    assert obs2.shape == (n, 10, 15) and rew.shape == (n,) and rew.dtype == np.float32 and dones.dtype == bool
+    assert len(infos) == n and infos[0]["TimeLimit.truncated"] is False
+    assert np.allclose(obs2[0, -1], t["frames"][0], rtol=1e-6, atol=1e-6) and abs(rew[0] - t["rewards"][0]) < 2e-5
+    assert obs is not obs2 and np.array_equal(obs[0, 1:], obs2[0, :-1])      # ring of host buffers keeps `_last_obs` valid
+    env.close()
+
+
+def test_vecenv_done_infos_match_dummy_vec_env_conventions(golden):
+    from f16_jsb_b200 import F16VecEnv
+    t = golden["gentle1"]
+    n = 70
+    env = F16VecEnv(n, mode="fp64", seed=5)
+    env.seed(11)         # env 0 gets the golden goal of seed 11 (trace gentle1)
+    env.reset()
+    for k in range(len(t["actions"])):
+        obs, rew, dones, infos = env.step(np.tile(t["actions"][k], (n, 1)))
+    assert dones[0] and infos[0]["TimeLimit.truncated"] is False
+    assert infos[0]["terminal_observation"].shape == (10, 15)
+    assert np.allclose(infos[0]["terminal_observation"][-1][:12], t["frames"][-1][:12], rtol=1e-5, atol=1e-4)
+    assert infos[0]["episode"]["l"] == len(t["actions"]) and abs(infos[0]["episode"]["r"] - float(t["rewards"].sum())) < 1e-2
+    assert np.all(obs[0] == obs[0, 0])                       # returned obs is the reset observation
+    assert sum(1 for i in infos if i.get("episode")) == int(dones.sum())
+    env.close()
+
+
+def test_single_env_gymnasium_adapter_matches_golden(golden):
+    from f16_jsb_b200 import wrap_jsbsim
+    t = golden["random3"]
+    env = wrap_jsbsim()
+    obs, info = env.reset(seed=3)
+    assert info == {} and np.allclose(obs, t["reset_obs"], atol=1e-9)
+    assert np.array_equal(env.env.goal, t["goal"])
+    for k in range(60):
+        obs, r, term, trunc, info = env.step(t["actions"][k])
+        assert np.allclose(obs[-1], t["frames"][k], rtol=1e-6, atol=1e-6)
+        assert abs(float(r) - float(t["rewards"][k])) < 2e-5 and not term and not trunc
+    env.close()
+
+
+def test_torch_fast_path_is_device_resident():
+    from f16_jsb_b200 import F16VecEnv
+    env = F16VecEnv(256, mode="fp32")
+    obs = env.reset_torch()
+    a = torch.rand((256, 4), device="cuda") * 2 - 1
+    o, r, d, tr = env.step_torch(a)
+    assert o.is_cuda and r.is_cuda and d.is_cuda and o.data_ptr() == obs.data_ptr()
+    env.close()

@@ -52,7 +52,7 @@ def test_teacher_forced_step_parity(hostsim, golden, state_fields, mode, tol, na
     assert worst > 0.0
 
 
-def check_free_run(step_fn, t, early_steps=300, early_tol=1e-5, late_tol=2e-2):
+def check_free_run(step_fn, t, early_steps=300, early_tol=1e-5, late_tol=1e-1):
     """Free-running comparison against a golden trace. The airframe is open-loop unstable once the
     actuators saturate, so round-off level differences (summation order, FMA, libm) are amplified
     late in aggressive episodes: frames must agree to `early_tol` (relative, floor 1e-2) for the

@@ -16,8 +16,8 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if _build.needs_build():
+    path = os.environ.get("F16_B200_LIB") or _build.LIB_PATH   # override: tuning variants built side by side
+    if path == _build.LIB_PATH and _build.needs_build():
         try:
             _build.build_library()
         except Exception as e:  # pragma: no cover - depends on toolchain

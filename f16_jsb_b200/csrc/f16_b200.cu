@@ -98,12 +98,22 @@ __device__ __forceinline__ void store_env(const EnvScalars& es, const StatePtrs<
 }
 
 // ------------------------------------------------------------------------------------ constant memory
-__constant__ MassSet c_msets[MS_COUNT];
+__constant__ MassSetT<double> c_msets[MS_COUNT];
+__constant__ MassSetT<float> c_msets_f[MS_COUNT];
+template <typename R> __device__ __forceinline__ const MassSetT<R>* msets_for();
+template <> __device__ __forceinline__ const MassSetT<double>* msets_for<double>() { return c_msets; }
+template <> __device__ __forceinline__ const MassSetT<float>* msets_for<float>() { return c_msets_f; }
 __constant__ double c_snapshot[F16_NUM_STATE_FIELDS];   // canonical post-reset FDM state
 __constant__ double c_snapshot_props[12];               // the 12 STATE_FORMAT properties after reset
 
 // ------------------------------------------------------------------------------------ kernels
-constexpr int BLOCK = 128;
+#ifndef F16_BLOCK
+#define F16_BLOCK 128
+#endif
+#ifndef F16_MIN_BLOCKS_F32
+#define F16_MIN_BLOCKS_F32 4   // CTAs per SM the float step kernel is compiled for: 128 registers (measured best of 2..5)
+#endif
+constexpr int BLOCK = F16_BLOCK;
 constexpr int WARPS = BLOCK / 32;
 
 template <typename R>
@@ -154,56 +164,67 @@ __global__ void f16_init_snapshot_kernel(const Tables<double>* __restrict__ gT, 
   compute_snapshot(T, c_msets, ic_state, out);
 }
 
-// warp-cooperative write of 32 envs' observation stacks. `frame_s[l]` holds env l's newest frame,
+// Warp-cooperative write of 32 envs' observation stacks: one contiguous span of 32 x 150 floats in
+// the obs tensor. Per env (warp-uniform control flow) the warp moves the nine surviving rows down by
+// one row in place - four full 128-byte transactions plus a 22-lane tail, all loads before all stores -
+// and appends the newest frame from shared memory. Two envs are in flight per iteration (10 loads).
 // flags: bit0 = env exists, bit1 = fill all ten rows with the frame (reset), bit2 = also emit the
 // shifted stack to terminal_obs with `tframe_s[l]` as its newest row.
 __device__ __forceinline__ void warp_write_obs(float* __restrict__ obs, float* __restrict__ term_obs, int64_t env0,
                                                const float (*frame_s)[16], const float (*tframe_s)[16],
                                                const uint8_t* flags_s) {
   const int lane = threadIdx.x & 31;
-  constexpr int PER_ENV = F16_OBS_FRAMES * F16_OBS_FEATURES;   // 150
+  constexpr int PER_ENV = F16_OBS_FRAMES * F16_OBS_FEATURES;   // 150 floats
   constexpr int SHIFT = F16_OBS_FEATURES;                      // 15
-  constexpr int TOTAL = 32 * PER_ENV;                          // 4800 floats = 150 warp-wide transactions
-  constexpr int U = 10;                                        // transactions in flight per batch
-  float* base = obs + env0 * PER_ENV;
-  float* tbase = term_obs ? term_obs + env0 * PER_ENV : nullptr;
-  for (int it0 = 0; it0 < TOTAL / 32; it0 += U) {
-    float v[U];
-    int el[U], jj[U];
+  constexpr int KEEP = PER_ENV - SHIFT;                        // 135 floats survive a step
+  const uint8_t my = flags_s[lane];
+  const unsigned m_active = __ballot_sync(0xffffffffu, my & 1);
+  const unsigned m_reset = __ballot_sync(0xffffffffu, my & 2);
+  const unsigned m_term = term_obs ? __ballot_sync(0xffffffffu, my & 4) : 0u;
+  const int j4 = 128 + lane;                                   // tail chunk index (valid while < 150)
+  int col[5];                                                  // column of element (c*32 + lane) within its row
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      int i = (it0 + u) * 32 + lane;
-      int l = i / PER_ENV;
-      int j = i - l * PER_ENV;
-      el[u] = l; jj[u] = j;
-      uint8_t fl = flags_s[l];
-      float x = 0.0f;
-      if ((fl & 1) && !(fl & 2) ) {
-        x = (j < PER_ENV - SHIFT) ? base[i + SHIFT] : frame_s[l][j - (PER_ENV - SHIFT)];
-      } else if (fl & 1) {
-        // reset: ten copies of the reset frame; the old stack is still needed for terminal_obs
-        x = (j < PER_ENV - SHIFT) ? base[i + SHIFT] : 0.0f;
+  for (int c = 0; c < 5; ++c) col[c] = (c * 32 + lane) % SHIFT;
+  float* const base = obs + env0 * PER_ENV;
+#pragma unroll 1
+  for (int l0 = 0; l0 < 32; l0 += 2) {
+    float v[2][5];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int l = l0 + u;
+      if (!((m_active >> l) & 1)) continue;
+      const float* eb = base + l * PER_ENV + SHIFT;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[u][c] = eb[c * 32 + lane];
+      v[u][4] = (j4 < KEEP) ? eb[j4] : 0.0f;
+    }
+    __syncwarp();   // every lane's loads precede any lane's stores of the same env (in-place shift)
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int l = l0 + u;
+      if (!((m_active >> l) & 1)) continue;
+      float* eb = base + l * PER_ENV;
+      if ((m_term >> l) & 1) {
+        float* tb = term_obs + (env0 + l) * PER_ENV;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tb[c * 32 + lane] = v[u][c];
+        if (j4 < PER_ENV) tb[j4] = (j4 < KEEP) ? v[u][4] : tframe_s[l][j4 - KEEP];
       }
-      v[u] = x;
-    }
-    __syncwarp();   // every lane's loads of this batch precede any lane's stores (in-place shift)
+      if ((m_reset >> l) & 1) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      int i = (it0 + u) * 32 + lane;
-      int l = el[u], j = jj[u];
-      uint8_t fl = flags_s[l];
-      if (!(fl & 1)) continue;
-      if ((fl & 4) && tbase) tbase[i] = (j < PER_ENV - SHIFT) ? v[u] : tframe_s[l][j - (PER_ENV - SHIFT)];
-      float x = v[u];
-      if (fl & 2) { int c = j % SHIFT; x = frame_s[l][c]; }
-      base[i] = x;
+        for (int c = 0; c < 4; ++c) eb[c * 32 + lane] = frame_s[l][col[c]];
+        if (j4 < PER_ENV) eb[j4] = frame_s[l][col[4]];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) eb[c * 32 + lane] = v[u][c];
+        if (j4 < PER_ENV) eb[j4] = (j4 < KEEP) ? v[u][4] : frame_s[l][j4 - KEEP];
+      }
     }
-    __syncwarp();
   }
 }
 
 template <typename R>
-__global__ void __launch_bounds__(BLOCK) f16_step_kernel(const StepArgs a) {
+__global__ void __launch_bounds__(BLOCK, sizeof(R) == 4 ? F16_MIN_BLOCKS_F32 : 1) f16_step_kernel(const StepArgs a) {
   __shared__ __align__(16) Tables<R> T;
   __shared__ __align__(16) float frame_s[WARPS][32][16];
   __shared__ __align__(16) float tframe_s[WARPS][32][16];
@@ -229,7 +250,7 @@ __global__ void __launch_bounds__(BLOCK) f16_step_kernel(const StepArgs a) {
     }
     float reward, ep_ret = 0.0f;
     int32_t ep_len = 0;
-    flags = env_step_one<R>(s, es, T, c_msets, c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
+    flags = env_step_one<R>(s, es, T, msets_for<R>(), c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
                             frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len);
     a.reward[e] = reward;
     a.done[e] = (flags & STEP_DONE) ? 1 : 0;
@@ -392,9 +413,12 @@ int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
   c->mode = mode;
   c->L = make_layout(n_envs, mode);
   // constants shared by every context on this device
-  MassSet ms[MS_COUNT];
+  MassSetT<double> ms[MS_COUNT];
+  MassSetT<float> msf[MS_COUNT];
   host::build_mass_sets(ms);
+  for (int i = 0; i < MS_COUNT; ++i) host::convert_mass_set(ms[i], &msf[i]);
   CUDA_OK(cudaMemcpyToSymbol(c_msets, ms, sizeof(ms)));
+  CUDA_OK(cudaMemcpyToSymbol(c_msets_f, msf, sizeof(msf)));
   int rc = mode == F16_MODE_FP64 ? upload_tables<double>(c) : upload_tables<float>(c);
   if (rc) { delete c; return rc; }
   CUDA_OK(cudaMalloc(&c->stats_dev, F16_NUM_STATS * sizeof(double)));

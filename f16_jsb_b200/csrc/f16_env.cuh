@@ -85,8 +85,8 @@ template <typename R>
 F16_HD void frame_from_fdm(const Veh<R>& s, const FrameObs<R>& fo, float* o) {
   R phi, tht, psi;
   euler_from_tl2b<R>(fo, phi, tht, psi);
-  o[0] = (float)fo.lat;
-  o[1] = (float)fo.lon;
+  o[0] = (float)Mx<R>::atan2_(fo.ze, fo.rxy);   // position/lat-gc-rad
+  o[1] = (float)Mx<R>::atan2_(fo.ye, fo.xe);    // position/long-gc-rad
   o[2] = (float)(fo.h_ft * kFtToM);
   o[3] = (float)s.mach;
   o[4] = (float)s.alpha;
@@ -137,7 +137,7 @@ F16_HD void sample_action(uint64_t seed, uint64_t env_id, uint32_t step_counter,
 // augmentation off). Gear is still down and both internal tanks still hold their initial 1500 lb
 // during these frames; the FCS components tick with dt = 1/120. `out` receives the packed state
 // followed by the twelve STATE_FORMAT properties (jsbsim_gym.py:12-25) as doubles.
-F16_HD void compute_snapshot(const Tables<double>& T, const MassSet* msets, const double* ic_state, double* out) {
+F16_HD void compute_snapshot(const Tables<double>& T, const MassSetT<double>* msets, const double* ic_state, double* out) {
   Veh<double> s;
   veh_from_packed(s, ic_state);   // kinematic IC, everything else zero (fresh FDM)
   Cmd<double> cmd = {0.0, 0.0, 0.0, 0.0};
@@ -158,7 +158,7 @@ F16_HD void compute_snapshot(const Tables<double>& T, const MassSet* msets, cons
   double phi, tht, psi;
   euler_from_tl2b<double>(fo, phi, tht, psi);
   double* p = out + F16_NUM_STATE_FIELDS;
-  p[0] = fo.lat; p[1] = fo.lon; p[2] = fo.h_ft * kFtToM; p[3] = s.mach; p[4] = s.alpha; p[5] = fo.beta;
+  p[0] = atan2(fo.ze, fo.rxy); p[1] = atan2(fo.ye, fo.xe); p[2] = fo.h_ft * kFtToM; p[3] = s.mach; p[4] = s.alpha; p[5] = fo.beta;
   p[6] = fo.pqr[0]; p[7] = fo.pqr[1]; p[8] = fo.pqr[2]; p[9] = phi; p[10] = tht; p[11] = psi;
 }
 
@@ -185,7 +185,7 @@ enum { STEP_ACTIVE = 1, STEP_RESET = 2, STEP_TERMINAL = 4, STEP_DONE = 8, STEP_T
 // One env-step. On return frame16 is the newest row of the env's observation stack (or, if the env
 // auto-reset, the reset frame, with tframe16 holding the terminal step's newest row).
 template <typename R>
-F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const MassSet* msets, const double* snapshot,
+F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const MassSetT<R>* msets, const double* snapshot,
                         const double* snapshot_props, const float* act, uint64_t seed, uint64_t env_id, int auto_reset,
                         float* frame16, float* tframe16, float* reward_out, float* ep_ret_out, int32_t* ep_len_out) {
   // action -> fcs/*-cmd-norm (jsbsim_gym.py:216-222): float32 -> double widening, no clipping

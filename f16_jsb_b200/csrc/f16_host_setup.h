@@ -43,6 +43,7 @@ V3h compute_mass_set(const double contents[4], const V3h& cg_prev, MassSet* ms) 
   }
   double weight = emptywt + tw + pilot_w;
   ms->mass = lbtoslug * weight;
+  ms->inv_mass = 1.0 / ms->mass;
   V3h cg = {(emptywt * base_cg[0] + pilot_w * pilot_loc[0] + tm.x) / weight,
             (emptywt * base_cg[1] + pilot_w * pilot_loc[1] + tm.y) / weight,
             (emptywt * base_cg[2] + pilot_w * pilot_loc[2] + tm.z) / weight};
@@ -73,6 +74,11 @@ V3h compute_mass_set(const double contents[4], const V3h& cg_prev, MassSet* ms) 
   ms->r_thr[0] = th.x; ms->r_thr[1] = th.y; ms->r_thr[2] = th.z;
   return cg;
 }
+inline void convert_mass_set(const MassSetT<double>& a, MassSetT<float>* b) {
+  b->mass = (float)a.mass; b->inv_mass = (float)a.inv_mass;
+  for (int i = 0; i < 9; ++i) { b->J[i] = (float)a.J[i]; b->Jinv[i] = (float)a.Jinv[i]; }
+  for (int i = 0; i < 3; ++i) { b->r_rp[i] = (float)a.r_rp[i]; b->r_eye[i] = (float)a.r_eye[i]; b->r_thr[i] = (float)a.r_thr[i]; }
+}
 void build_mass_sets(MassSet out[MS_COUNT]) {
   double ic[4], fl[4];
   for (int i = 0; i < 4; ++i) { ic[i] = f16data::tank_contents0[i]; fl[i] = ic[i]; }
@@ -100,7 +106,6 @@ void build_tables(Tables<R>* T) {
   constexpr int NA = f16::NA, NDE = f16::NDE, NB7 = f16::NB7, NB13 = f16::NB13;
   memset(T, 0, sizeof(*T));
   for (int i = 0; i < NA; ++i) {
-    T->alpha_bp[i] = (R)alpha_bp[i];
     for (int k = 0; k < A1_N; ++k) T->A1[i][k] = (R)A1[i][k];
     for (int j = 0; j < NDE; ++j)
       for (int k = 0; k < 4; ++k) T->AE[i][j][k] = (R)AE[i][j][k];
@@ -109,9 +114,13 @@ void build_tables(Tables<R>* T) {
     for (int j = 0; j < NB13; ++j)
       for (int k = 0; k < 2; ++k) T->AB13[i][j][k] = (R)AB13[i][j][k];
   }
-  for (int j = 0; j < NDE; ++j) T->de_bp[j] = (R)de_bp[j];
-  for (int j = 0; j < NB7; ++j) T->b7_bp[j] = (R)b7_bp[j];
-  for (int j = 0; j < NB13; ++j) T->b13_bp[j] = (R)b13_bp[j];
+  auto fill_seg = [](R (*seg)[2], const double* x, int n) {
+    for (int r = 1; r < n; ++r) { seg[r][0] = (R)x[r - 1]; seg[r][1] = (R)(1.0 / (x[r] - x[r - 1])); }
+  };
+  fill_seg(T->seg_alpha, alpha_bp, NA);
+  fill_seg(T->seg_de, de_bp, NDE);
+  fill_seg(T->seg_b7, b7_bp, NB7);
+  fill_seg(T->seg_b13, b13_bp, NB13);
   // union of the Mach breakpoints of the nine Mach tables; every table is piecewise linear with
   // clamped ends, so resampling it on the union grid reproduces it exactly
   std::vector<double> grid;
@@ -125,10 +134,13 @@ void build_tables(Tables<R>* T) {
   add(x_CDmach, n_CDmach); add(x_CYb_M, n_CYb_M); add(x_Clb_M, n_Clb_M); add(x_Clda_M, n_Clda_M); add(x_Cldr_M, n_Cldr_M);
   add(x_Cma_M, n_Cma_M); add(x_Cnb_M, n_Cnb_M); add(x_Cnda_M, n_Cnda_M); add(x_Cndr_M, n_Cndr_M);
   std::sort(grid.begin(), grid.end());
+  const double gen_grid[NMACH] = F16_MACH_BP;   // the generator's copy (compared as immediates in the kernel)
   if ((int)grid.size() != NMACH) { fprintf(stderr, "f16: Mach union grid has %d points, expected %d\n", (int)grid.size(), NMACH); abort(); }
+  for (int i = 0; i < NMACH; ++i)
+    if (grid[i] != gen_grid[i]) { fprintf(stderr, "f16: Mach union grid mismatch at %d\n", i); abort(); }
+  fill_seg(T->seg_mach, gen_grid, NMACH);
   for (int i = 0; i < NMACH; ++i) {
     double m = grid[i];
-    T->mach_bp[i] = (R)m;
     T->MT[i][MT_CDmach] = (R)interp1(x_CDmach, y_CDmach, n_CDmach, m);
     T->MT[i][MT_CYb_M] = (R)interp1(x_CYb_M, y_CYb_M, n_CYb_M, m);
     T->MT[i][MT_Clb_M] = (R)interp1(x_Clb_M, y_Clb_M, n_Clb_M, m);

@@ -15,11 +15,13 @@ struct Consts {
   Tables<double> Td;
   Tables<float> Tf;
   MassSet ms[MS_COUNT];
+  MassSetT<float> msf[MS_COUNT];
   double snap[F16_NUM_STATE_FIELDS + 12];
   Consts() {
     host::build_tables<double>(&Td);
     host::build_tables<float>(&Tf);
     host::build_mass_sets(ms);
+    for (int i = 0; i < MS_COUNT; ++i) host::convert_mass_set(ms[i], &msf[i]);
     double ic[F16_NUM_STATE_FIELDS];
     host::initial_condition(900.0, 5000.0, ic);
     compute_snapshot(Td, ms, ic, snap);
@@ -68,7 +70,7 @@ int hs_env_step(void* h, const float* action, int auto_reset, uint64_t seed, uin
   if (e->mode == 0)
     flags = env_step_one<double>(e->sd, e->es, c.Td, c.ms, c.snap, c.snap + F16_NUM_STATE_FIELDS, action, seed, env_id, auto_reset, fr, tfr, reward, &ep_ret, &ep_len);
   else
-    flags = env_step_one<float>(e->sf, e->es, c.Tf, c.ms, c.snap, c.snap + F16_NUM_STATE_FIELDS, action, seed, env_id, auto_reset, fr, tfr, reward, &ep_ret, &ep_len);
+    flags = env_step_one<float>(e->sf, e->es, c.Tf, c.msf, c.snap, c.snap + F16_NUM_STATE_FIELDS, action, seed, env_id, auto_reset, fr, tfr, reward, &ep_ret, &ep_len);
   // same stack update as warp_write_obs
   if (flags & STEP_TERMINAL) {
     std::memcpy(e->tobs[0], e->obs[1], 9 * 15 * sizeof(float));

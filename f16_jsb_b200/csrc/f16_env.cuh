@@ -85,8 +85,8 @@ template <typename R>
 F16_HD void frame_from_fdm(const Veh<R>& s, const FrameObs<R>& fo, float* o) {
   R phi, tht, psi;
   euler_from_tl2b<R>(fo, phi, tht, psi);
-  o[0] = (float)Mx<R>::atan2_(fo.ze, fo.rxy);   // position/lat-gc-rad
-  o[1] = (float)Mx<R>::atan2_(fo.ye, fo.xe);    // position/long-gc-rad
+  o[0] = (float)Mx<R>::fatan2_(fo.ze, fo.rxy);   // position/lat-gc-rad
+  o[1] = (float)Mx<R>::fatan2_(fo.ye, fo.xe);    // position/long-gc-rad
   o[2] = (float)(fo.h_ft * kFtToM);
   o[3] = (float)s.mach;
   o[4] = (float)s.alpha;

@@ -227,68 +227,106 @@ __device__ __forceinline__ void warp_write_obs(float* __restrict__ obs, float* _
   }
 }
 
+// ---- TMA (bulk async copy) staging of the table image: one elected thread issues a single
+// cp.async.bulk global -> shared::cta that completes on an mbarrier; nobody spends registers or issue
+// slots on the copy and the first tile's state loads overlap with it.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+
+#ifndef F16_PERSISTENT
+#define F16_PERSISTENT 0
+#endif
+// Persistent step kernel: the grid is sized to the machine (SMs x resident CTAs); the table image is
+// staged once per CTA and every warp then walks its own sequence of 32-env tiles (tile = warp id,
+// += total warps). Warps never synchronise with each other after the staging barrier, so their
+// load / compute / store phases drift apart and overlap on each SM.
 template <typename R>
 __global__ void __launch_bounds__(BLOCK, sizeof(R) == 4 ? F16_MIN_BLOCKS_F32 : 1) f16_step_kernel(const StepArgs a) {
-  __shared__ __align__(16) Tables<R> T;
+  __shared__ __align__(128) Tables<R> T;
   __shared__ __align__(16) float frame_s[WARPS][32][16];
   __shared__ __align__(16) float tframe_s[WARPS][32][16];
   __shared__ uint8_t flags_s[WARPS][32];
-  stage_tables(&T, reinterpret_cast<const Tables<R>*>(a.tables));
+  __shared__ __align__(8) uint64_t tbar;
+  static_assert(sizeof(Tables<R>) % 16 == 0, "bulk copy size must be a multiple of 16 bytes");
+  if (threadIdx.x == 0) mbar_init(&tbar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) tma_load_1d(&T, a.tables, (uint32_t)sizeof(Tables<R>), &tbar);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-#ifndef F16_NO_PREFETCH_OBS
-  {
-    // the nine surviving rows are only needed after the four frames: pull the warp's 19 200-byte span
-    // towards L2 now so that the shift at the end does not wait on HBM
-    const int64_t env0p = (int64_t)blockIdx.x * BLOCK + warp * 32;
-    const char* span = reinterpret_cast<const char*>(a.obs + env0p * (F16_OBS_FRAMES * F16_OBS_FEATURES));
-    const int64_t remaining = (a.n - env0p) * (int64_t)(F16_OBS_FRAMES * F16_OBS_FEATURES * 4);
-    const int64_t bytes = remaining < 19200 ? remaining : 19200;
-    for (int off = lane * 128; off < bytes; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(span + off));
-  }
+  const int64_t n_tiles = (a.n + 31) >> 5;
+  const int64_t warps_total = (int64_t)gridDim.x * WARPS;
+  bool tables_ready = false;
+  const StatePtrs<R> sp = state_ptrs<R>(a.state, a.r_off, a.e_off, a.np);
+#if F16_PERSISTENT
+#pragma unroll 1
+  for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += warps_total) {
+#else
+  (void)warps_total;
+  const int64_t tile = (int64_t)blockIdx.x * WARPS + warp;
+  if (tile < n_tiles) {
 #endif
-  int flags = 0;
-  if (e < a.n) {
-    StatePtrs<R> sp = state_ptrs<R>(a.state, a.r_off, a.e_off, a.np);
-    Veh<R> s;
-    EnvScalars es;
-    load_veh(s, sp, e);
-    load_env(es, sp, e);
-    const uint64_t gid = (uint64_t)(a.env_id_base + e);
-    float act[4];
-    if (a.actions) {
-      float4 v = reinterpret_cast<const float4*>(a.actions)[e];
-      act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
-    } else {
-      sample_action(a.seed, gid, a.step_counter, act);
-    }
-    float reward, ep_ret = 0.0f;
-    int32_t ep_len = 0;
-    flags = env_step_one<R>(s, es, T, msets_for<R>(), c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
-                            frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len);
-    a.reward[e] = reward;
-    a.done[e] = (flags & STEP_DONE) ? 1 : 0;
-    a.truncated[e] = (flags & STEP_TRUNCATED) ? 1 : 0;
-    if (flags & STEP_DONE) {
-      if (a.ep_return) a.ep_return[e] = ep_ret;
-      if (a.ep_len) a.ep_len[e] = ep_len;
-      if (a.stats) {
-        atomicAdd(a.stats + 0, 1.0);
-        atomicAdd(a.stats + 1, (double)ep_ret);
-        atomicAdd(a.stats + 2, (double)ep_len);
-        if (flags & STEP_CRASH) atomicAdd(a.stats + 3, 1.0);
-        if (flags & STEP_GOAL) atomicAdd(a.stats + 4, 1.0);
-        if (flags & STEP_TRUNCATED) atomicAdd(a.stats + 5, 1.0);
+    const int64_t env0 = tile << 5;
+    const int64_t e = env0 + lane;
+    int flags = 0;
+    if (e < a.n) {
+      Veh<R> s;
+      EnvScalars es;
+      load_veh(s, sp, e);
+      load_env(es, sp, e);
+      const uint64_t gid = (uint64_t)(a.env_id_base + e);
+      float act[4];
+      if (a.actions) {
+        float4 v = reinterpret_cast<const float4*>(a.actions)[e];
+        act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
+      } else {
+        sample_action(a.seed, gid, a.step_counter, act);
       }
+      if (!tables_ready) { mbar_wait(&tbar, 0); tables_ready = true; }
+      float reward, ep_ret = 0.0f;
+      int32_t ep_len = 0;
+      flags = env_step_one<R>(s, es, T, msets_for<R>(), c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
+                              frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len);
+      a.reward[e] = reward;
+      a.done[e] = (flags & STEP_DONE) ? 1 : 0;
+      a.truncated[e] = (flags & STEP_TRUNCATED) ? 1 : 0;
+      if (flags & STEP_DONE) {
+        if (a.ep_return) a.ep_return[e] = ep_ret;
+        if (a.ep_len) a.ep_len[e] = ep_len;
+        if (a.stats) {
+          atomicAdd(a.stats + 0, 1.0);
+          atomicAdd(a.stats + 1, (double)ep_ret);
+          atomicAdd(a.stats + 2, (double)ep_len);
+          if (flags & STEP_CRASH) atomicAdd(a.stats + 3, 1.0);
+          if (flags & STEP_GOAL) atomicAdd(a.stats + 4, 1.0);
+          if (flags & STEP_TRUNCATED) atomicAdd(a.stats + 5, 1.0);
+        }
+      }
+      store_veh(s, sp, e);
+      store_env(es, sp, e);
     }
-    store_veh(s, sp, e);
-    store_env(es, sp, e);
+    flags_s[warp][lane] = (uint8_t)(flags & (STEP_ACTIVE | STEP_RESET | STEP_TERMINAL));
+    __syncwarp();
+    warp_write_obs(a.obs, a.terminal_obs, env0, frame_s[warp], tframe_s[warp], flags_s[warp]);
+    __syncwarp();   // the frame / flag staging of this warp is reused by its next tile
   }
-  flags_s[warp][lane] = (uint8_t)(flags & (STEP_ACTIVE | STEP_RESET | STEP_TERMINAL));
-  __syncwarp();
-  const int64_t env0 = (int64_t)blockIdx.x * BLOCK + warp * 32;
-  if (env0 < a.n) warp_write_obs(a.obs, a.terminal_obs, env0, frame_s[warp], tframe_s[warp], flags_s[warp]);
 }
 
 struct ResetArgs {
@@ -390,6 +428,7 @@ struct f16_ctx {
   uint64_t seed = 0;
   uint32_t step_counter = 0;
   double env_steps = 0.0;            // host-side count for stats[6]
+  int num_sms = 1, ctas_per_sm = 1;  // persistent grid of the step kernel
 };
 
 template <typename R>
@@ -463,6 +502,10 @@ int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
     CUDA_OK(cudaMemcpyToSymbol(c_snapshot_props, c->snapshot + F16_NUM_STATE_FIELDS, 12 * sizeof(double)));
   }
   CUDA_OK(cudaMalloc(&c->actions_stage, (size_t)n_envs * F16_ACTION_DIM * sizeof(float)));
+  CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+  if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double>, BLOCK, 0));
+  else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float>, BLOCK, 0));
+  if (c->ctas_per_sm < 1) c->ctas_per_sm = 1;
   *out = c;
   return 0;
 }
@@ -524,7 +567,11 @@ int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream) {
   a.done = h->done; a.truncated = h->truncated; a.terminal_obs = h->terminal_obs; a.ep_return = h->ep_return;
   a.ep_len = h->ep_len; a.stats = h->stats_dev; a.n = h->L.n; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
   a.seed = h->seed; a.env_id_base = h->env_id_base; a.step_counter = h->step_counter++; a.auto_reset = auto_reset;
-  unsigned grid = (unsigned)((h->L.n + BLOCK - 1) / BLOCK);
+  // persistent grid: SMs x resident CTAs (capped by the number of 32-env tiles)
+  const int64_t tiles = (h->L.n + 31) / 32;
+  int64_t want = (int64_t)h->num_sms * h->ctas_per_sm;
+  const int64_t need = (tiles + WARPS - 1) / WARPS;
+  unsigned grid = (unsigned)((F16_PERSISTENT && want < need) ? want : need);
   if (h->mode == F16_MODE_FP64) f16_step_kernel<double><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
   else f16_step_kernel<float><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
   g_launches++;

@@ -187,7 +187,7 @@ __device__ __forceinline__ void warp_write_obs(float* __restrict__ obs, float* _
   for (int c = 0; c < 5; ++c) col[c] = (c * 32 + lane) % SHIFT;
   float* const base = obs + env0 * PER_ENV;
 #ifndef F16_OBS_INFLIGHT
-#define F16_OBS_INFLIGHT 4     // envs whose rows are in flight per iteration (5 loads each)
+#define F16_OBS_INFLIGHT 8     // envs whose rows are in flight per iteration (5 loads each); 8 measured best
 #endif
   constexpr int NU = F16_OBS_INFLIGHT;
 #pragma unroll 1
@@ -254,6 +254,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifndef F16_PERSISTENT
 #define F16_PERSISTENT 0
 #endif
+#ifndef F16_PREFETCH_OBS
+#define F16_PREFETCH_OBS 1
+#endif
 // Persistent step kernel: the grid is sized to the machine (SMs x resident CTAs); the table image is
 // staged once per CTA and every warp then walks its own sequence of 32-env tiles (tile = warp id,
 // += total warps). Warps never synchronise with each other after the staging barrier, so their
@@ -302,8 +305,15 @@ __global__ void __launch_bounds__(BLOCK, sizeof(R) == 4 ? F16_MIN_BLOCKS_F32 : 1
       if (!tables_ready) { mbar_wait(&tbar, 0); tables_ready = true; }
       float reward, ep_ret = 0.0f;
       int32_t ep_len = 0;
+      // each lane prefetches lines lane, lane+32, ... of the warp's 150-line observation span (F16_PREFETCH_OBS)
+      PrefetchHint pf = {nullptr, 0, 0};
+#if F16_PREFETCH_OBS
+      pf.ptr = reinterpret_cast<const char*>(a.obs + env0 * (F16_OBS_FRAMES * F16_OBS_FEATURES)) + lane * 128;
+      pf.count = lane < 22 ? 5 : 4;       // 150 lines of 128 bytes
+      pf.stride = 32 * 128;
+#endif
       flags = env_step_one<R>(s, es, T, msets_for<R>(), c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
-                              frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len);
+                              frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len, pf);
       a.reward[e] = reward;
       a.done[e] = (flags & STEP_DONE) ? 1 : 0;
       a.truncated[e] = (flags & STEP_TRUNCATED) ? 1 : 0;

@@ -184,10 +184,15 @@ enum { STEP_ACTIVE = 1, STEP_RESET = 2, STEP_TERMINAL = 4, STEP_DONE = 8, STEP_T
 
 // One env-step. On return frame16 is the newest row of the env's observation stack (or, if the env
 // auto-reset, the reset frame, with tframe16 holding the terminal step's newest row).
+// Optional L2 prefetch issued by each lane just before the last FDM frame: the caller's observation
+// rows are needed right after that frame, and one frame of compute covers the HBM latency.
+struct PrefetchHint { const char* ptr; int count; int stride; };
+
 template <typename R>
 F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const MassSetT<R>* msets, const double* snapshot,
                         const double* snapshot_props, const float* act, uint64_t seed, uint64_t env_id, int auto_reset,
-                        float* frame16, float* tframe16, float* reward_out, float* ep_ret_out, int32_t* ep_len_out) {
+                        float* frame16, float* tframe16, float* reward_out, float* ep_ret_out, int32_t* ep_len_out,
+                        PrefetchHint pf = PrefetchHint{nullptr, 0, 0}) {
   // action -> fcs/*-cmd-norm (jsbsim_gym.py:216-222): float32 -> double widening, no clipping
   Cmd<R> cmd = {(R)act[0], (R)act[1], (R)act[2], (R)act[3]};
   es.step += 1;
@@ -197,7 +202,16 @@ F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const Mas
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
-  for (int k = 0; k < 4; ++k) fdm_frame<R, false>(s, T, msets, cfg, cmd, es.step == 1 && k == 0, fo);
+  for (int k = 0; k < 4; ++k) {
+#ifdef __CUDA_ARCH__
+#ifndef F16_PREFETCH_AT_FRAME
+#define F16_PREFETCH_AT_FRAME 3
+#endif
+    if (k == F16_PREFETCH_AT_FRAME)
+      for (int i = 0; i < pf.count; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf.ptr + (size_t)i * pf.stride));
+#endif
+    fdm_frame<R, false>(s, T, msets, cfg, cmd, es.step == 1 && k == 0, fo);
+  }
 
   // observation frame, reward, termination - all on the float32 frame (jsbsim_gym.py:237-261)
   float o[12];

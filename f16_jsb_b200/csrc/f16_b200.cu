@@ -52,25 +52,37 @@ struct StatePtrs {
   int64_t np;
 };
 
+// state and observations are touched exactly once per step: streaming (evict-first) accesses keep them
+// from displacing the prefetched observation rows in L2 (F16_STREAMING)
+#ifndef F16_STREAMING
+#define F16_STREAMING 0   // measured slower on B200 (extra register pressure), kept as an option
+#endif
+#if F16_STREAMING
+#define F16_LD(ptr) __ldcs(ptr)
+#define F16_ST(ptr, v) __stcs(ptr, v)
+#else
+#define F16_LD(ptr) (*(ptr))
+#define F16_ST(ptr, v) (*(ptr) = (v))
+#endif
 template <typename R>
 __device__ __forceinline__ void load_veh(Veh<R>& s, const StatePtrs<R>& p, int64_t e) {
   int f = 0;
-#define X(m) s.m = p.k[(size_t)(f++) * p.np + e];
+#define X(m) s.m = F16_LD(&p.k[(size_t)(f++) * p.np + e]);
   F16_KFIELDS(X)
 #undef X
   f = 0;
-#define X(m) s.m = p.r[(size_t)(f++) * p.np + e];
+#define X(m) s.m = F16_LD(&p.r[(size_t)(f++) * p.np + e]);
   F16_RFIELDS(X)
 #undef X
 }
 template <typename R>
 __device__ __forceinline__ void store_veh(const Veh<R>& s, const StatePtrs<R>& p, int64_t e) {
   int f = 0;
-#define X(m) p.k[(size_t)(f++) * p.np + e] = s.m;
+#define X(m) F16_ST(&p.k[(size_t)(f++) * p.np + e], s.m);
   F16_KFIELDS(X)
 #undef X
   f = 0;
-#define X(m) p.r[(size_t)(f++) * p.np + e] = s.m;
+#define X(m) F16_ST(&p.r[(size_t)(f++) * p.np + e], s.m);
   F16_RFIELDS(X)
 #undef X
 }
@@ -108,10 +120,10 @@ __constant__ double c_snapshot_props[12];               // the 12 STATE_FORMAT p
 
 // ------------------------------------------------------------------------------------ kernels
 #ifndef F16_BLOCK
-#define F16_BLOCK 256            // measured on B200: 256 x 2 CTAs/SM beats 128 x 4 and 64 x 8 by 2-5 %
+#define F16_BLOCK 128            // measured on B200 (1M envs): 128 x 3 CTAs/SM best; 64x6 -1 %, 96x4 -2 %, 256x2 -10 %
 #endif
 #ifndef F16_MIN_BLOCKS_F32
-#define F16_MIN_BLOCKS_F32 2   // CTAs per SM of the float step kernel: 2 x 256 threads -> 128 registers (measured best)
+#define F16_MIN_BLOCKS_F32 3   // CTAs per SM of the float step kernel: 3 x 128 threads -> 168 registers, 72 B of spills
 #endif
 constexpr int BLOCK = F16_BLOCK;
 constexpr int WARPS = BLOCK / 32;
@@ -185,43 +197,64 @@ __device__ __forceinline__ void warp_write_obs(float* __restrict__ obs, float* _
   int col[5];                                                  // column of element (c*32 + lane) within its row
 #pragma unroll
   for (int c = 0; c < 5; ++c) col[c] = (c * 32 + lane) % SHIFT;
-  float* const base = obs + env0 * PER_ENV;
 #ifndef F16_OBS_INFLIGHT
 #define F16_OBS_INFLIGHT 8     // envs whose rows are in flight per iteration (5 loads each); 8 measured best
 #endif
   constexpr int NU = F16_OBS_INFLIGHT;
+  constexpr unsigned GROUP = (NU == 32) ? 0xffffffffu : ((1u << NU) - 1u);
+  float* const base = obs + env0 * PER_ENV;
 #pragma unroll 1
   for (int l0 = 0; l0 < 32; l0 += NU) {
+    float* const gb = base + l0 * PER_ENV + lane;              // this lane's first element of the group's first env
+    const unsigned act = (m_active >> l0) & GROUP, special = ((m_reset | m_term) >> l0) & GROUP;
     float v[NU][5];
+    if (act == GROUP && special == 0u) {
+      // common case, straight-line: every env of the group exists and just shifts by one row
 #pragma unroll
-    for (int u = 0; u < NU; ++u) {
-      const int l = l0 + u;
-      if (!((m_active >> l) & 1)) continue;
-      const float* eb = base + l * PER_ENV + SHIFT;
+      for (int u = 0; u < NU; ++u) {
+        const float* eb = gb + u * PER_ENV + SHIFT;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) v[u][c] = eb[c * 32 + lane];
-      v[u][4] = (j4 < KEEP) ? eb[j4] : 0.0f;
+        for (int c = 0; c < 4; ++c) v[u][c] = F16_LD(&eb[c * 32]);
+        v[u][4] = (j4 < KEEP) ? F16_LD(&eb[128]) : frame_s[l0 + u][(j4 - KEEP) & 15];
+      }
+      __syncwarp();   // every lane's loads precede any lane's stores of the same env (in-place shift)
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        float* eb = gb + u * PER_ENV;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) F16_ST(&eb[c * 32], v[u][c]);
+        if (j4 < PER_ENV) F16_ST(&eb[128], v[u][4]);
+      }
+      continue;
     }
-    __syncwarp();   // every lane's loads precede any lane's stores of the same env (in-place shift)
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      if (!((act >> u) & 1)) continue;
+      const float* eb = gb + u * PER_ENV + SHIFT;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[u][c] = F16_LD(&eb[c * 32]);
+      v[u][4] = (j4 < KEEP) ? F16_LD(&eb[128]) : 0.0f;
+    }
+    __syncwarp();
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       const int l = l0 + u;
-      if (!((m_active >> l) & 1)) continue;
-      float* eb = base + l * PER_ENV;
+      if (!((act >> u) & 1)) continue;
+      float* eb = gb + u * PER_ENV;
       if ((m_term >> l) & 1) {
-        float* tb = term_obs + (env0 + l) * PER_ENV;
+        float* tb = term_obs + (env0 + l) * PER_ENV + lane;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tb[c * 32 + lane] = v[u][c];
-        if (j4 < PER_ENV) tb[j4] = (j4 < KEEP) ? v[u][4] : tframe_s[l][j4 - KEEP];
+        for (int c = 0; c < 4; ++c) tb[c * 32] = v[u][c];
+        if (j4 < PER_ENV) tb[128] = (j4 < KEEP) ? v[u][4] : tframe_s[l][j4 - KEEP];
       }
       if ((m_reset >> l) & 1) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) eb[c * 32 + lane] = frame_s[l][col[c]];
-        if (j4 < PER_ENV) eb[j4] = frame_s[l][col[4]];
+        for (int c = 0; c < 4; ++c) eb[c * 32] = frame_s[l][col[c]];
+        if (j4 < PER_ENV) eb[128] = frame_s[l][col[4]];
       } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) eb[c * 32 + lane] = v[u][c];
-        if (j4 < PER_ENV) eb[j4] = (j4 < KEEP) ? v[u][4] : frame_s[l][j4 - KEEP];
+        for (int c = 0; c < 4; ++c) eb[c * 32] = v[u][c];
+        if (j4 < PER_ENV) eb[128] = (j4 < KEEP) ? v[u][4] : frame_s[l][j4 - KEEP];
       }
     }
   }
@@ -307,10 +340,18 @@ __global__ void __launch_bounds__(BLOCK, sizeof(R) == 4 ? F16_MIN_BLOCKS_F32 : 1
       int32_t ep_len = 0;
       // each lane prefetches lines lane, lane+32, ... of the warp's 150-line observation span (F16_PREFETCH_OBS)
       PrefetchHint pf = {nullptr, 0, 0};
-#if F16_PREFETCH_OBS
+#if F16_PREFETCH_OBS == 1
       pf.ptr = reinterpret_cast<const char*>(a.obs + env0 * (F16_OBS_FRAMES * F16_OBS_FEATURES)) + lane * 128;
       pf.count = lane < 22 ? 5 : 4;       // 150 lines of 128 bytes
       pf.stride = 32 * 128;
+#elif F16_PREFETCH_OBS == 2
+      // one TMA bulk prefetch of the warp's whole 19 200-byte span, issued by lane 0
+      if (lane == 0) {
+        const int64_t left = (a.n - env0) * (int64_t)(F16_OBS_FRAMES * F16_OBS_FEATURES * 4);
+        pf.ptr = reinterpret_cast<const char*>(a.obs + env0 * (F16_OBS_FRAMES * F16_OBS_FEATURES));
+        pf.count = -1;
+        pf.stride = (int)(left < 19200 ? (left & ~15) : 19200);
+      }
 #endif
       flags = env_step_one<R>(s, es, T, msets_for<R>(), c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
                               frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len, pf);

@@ -186,7 +186,7 @@ enum { STEP_ACTIVE = 1, STEP_RESET = 2, STEP_TERMINAL = 4, STEP_DONE = 8, STEP_T
 // auto-reset, the reset frame, with tframe16 holding the terminal step's newest row).
 // Optional L2 prefetch issued by each lane just before the last FDM frame: the caller's observation
 // rows are needed right after that frame, and one frame of compute covers the HBM latency.
-struct PrefetchHint { const char* ptr; int count; int stride; };
+struct PrefetchHint { const char* ptr; int count; int stride; };   // count < 0: one bulk (TMA) prefetch of `stride` bytes
 
 template <typename R>
 F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const MassSetT<R>* msets, const double* snapshot,
@@ -207,8 +207,10 @@ F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const Mas
 #ifndef F16_PREFETCH_AT_FRAME
 #define F16_PREFETCH_AT_FRAME 3
 #endif
-    if (k == F16_PREFETCH_AT_FRAME)
+    if (k == F16_PREFETCH_AT_FRAME) {
+      if (pf.count < 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.ptr), "r"(pf.stride) : "memory");
       for (int i = 0; i < pf.count; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf.ptr + (size_t)i * pf.stride));
+    }
 #endif
     fdm_frame<R, false>(s, T, msets, cfg, cmd, es.step == 1 && k == 0, fo);
   }

@@ -43,6 +43,11 @@ def load():
     L.f16_get_snapshot.argtypes = [vp, vp, vp]
     L.f16_get_stats.argtypes = [vp, vp, i32, vp]
     L.f16_stats_device_ptr.argtypes = [vp, C.POINTER(vp)]
+    L.f16_rollout_add.argtypes = [i64, i64, i64] + [vp] * 15
+    L.f16_rollout_gae.argtypes = [i64, i64, C.c_float, C.c_float] + [vp] * 8
+    L.f16_rollout_gather.argtypes = [i64, i64, i64] + [vp] * 15
+    for name in ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather"):
+        getattr(L, name).restype = i32
     L.f16_launch_count.restype = i64
     L.f16_num_state_fields.restype = i32
     L.f16_last_error.restype = C.c_char_p
@@ -67,3 +72,4 @@ EXPORTED_SYMBOLS = (
     "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states", "f16_unpack_states",
     "f16_set_env_step", "f16_get_snapshot", "f16_get_stats", "f16_stats_device_ptr", "f16_launch_count", "f16_num_state_fields",
     "f16_last_error", "f16_version")
+ROLLOUT_SYMBOLS = ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather")

@@ -294,8 +294,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // staged once per CTA and every warp then walks its own sequence of 32-env tiles (tile = warp id,
 // += total warps). Warps never synchronise with each other after the staging barrier, so their
 // load / compute / store phases drift apart and overlap on each SM.
-template <typename R>
-__global__ void __launch_bounds__(BLOCK, sizeof(R) == 4 ? F16_MIN_BLOCKS_F32 : 1) f16_step_kernel(const StepArgs a) {
+template <typename R, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a) {
   __shared__ __align__(128) Tables<R> T;
   __shared__ __align__(16) float frame_s[WARPS][32][16];
   __shared__ __align__(16) float tframe_s[WARPS][32][16];
@@ -496,6 +496,10 @@ static int upload_tables(f16_ctx* c) {
 
 extern "C" {
 
+// shared with f16_rollout.cu
+int f16_internal_fail(const char* msg) { return fail("%s", msg); }
+void f16_internal_count_launch(void) { g_launches++; }
+
 const char* f16_last_error(void) { return g_err.c_str(); }
 const char* f16_version(void) { return "f16_b200 0.1 (sm_100a)"; }
 int64_t f16_launch_count(void) { return g_launches; }
@@ -554,8 +558,8 @@ int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
   }
   CUDA_OK(cudaMalloc(&c->actions_stage, (size_t)n_envs * F16_ACTION_DIM * sizeof(float)));
   CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
-  if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double>, BLOCK, 0));
-  else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float>, BLOCK, 0));
+  if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, 1>, BLOCK, 0));
+  else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float, F16_MIN_BLOCKS_F32>, BLOCK, 0));
   if (c->ctas_per_sm < 1) c->ctas_per_sm = 1;
   *out = c;
   return 0;
@@ -623,8 +627,18 @@ int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream) {
   int64_t want = (int64_t)h->num_sms * h->ctas_per_sm;
   const int64_t need = (tiles + WARPS - 1) / WARPS;
   unsigned grid = (unsigned)((F16_PERSISTENT && want < need) ? want : need);
-  if (h->mode == F16_MODE_FP64) f16_step_kernel<double><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
-  else f16_step_kernel<float><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+  if (h->mode == F16_MODE_FP64) {
+    f16_step_kernel<double, 1><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    // Two register budgets of the float kernel: F16_MIN_BLOCKS_F32 CTAs/SM (167 registers, fastest per
+    // env when the grid is many waves deep) and one more CTA per SM (128 registers), which wins when the
+    // extra resident CTAs save a whole wave (e.g. 65 536 envs = 512 CTAs: 2 waves at 3/SM, 1 at 4/SM).
+    const int64_t slots_a = (int64_t)h->num_sms * F16_MIN_BLOCKS_F32, slots_b = (int64_t)h->num_sms * (F16_MIN_BLOCKS_F32 + 1);
+    const double cost_a = (double)((need + slots_a - 1) / slots_a);
+    const double cost_b = (double)((need + slots_b - 1) / slots_b) * 1.45;   // measured per-wave cost ratio
+    if (cost_b < cost_a) f16_step_kernel<float, F16_MIN_BLOCKS_F32 + 1><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+    else f16_step_kernel<float, F16_MIN_BLOCKS_F32><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+  }
   g_launches++;
   h->env_steps += (double)h->L.n;
   CUDA_OK(cudaGetLastError());

@@ -1,0 +1,60 @@
+"""GPU rollout store vs the SB3 RolloutBuffer restatement: a real rollout of the CUDA env with
+auto-resets, bit-exact observations (rebuilt stacks), GAE, and minibatch gather."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rollout_store_matches_sb3_buffer_bit_for_bit():
+    from f16_jsb_b200 import F16BatchedEnv
+    from f16_jsb_b200.rollout import GpuRolloutBuffer
+    from oracle.rollout_oracle import RolloutBufferOracle
+
+    N, T, gamma, lam = 300, 96, 0.99, 0.95
+    env = F16BatchedEnv(N, mode="fp32", seed=5)
+    obs = env.reset().clone()
+    # make resets frequent: put a third of the envs 40 m above the ground... (not exposed) -> instead use
+    # long episodes plus forced mid-rollout resets through the masked reset call
+    gbuf = GpuRolloutBuffer(T, N, device=env.device, gae_lambda=lam, gamma=gamma)
+    obuf = RolloutBufferOracle(T, N, gae_lambda=lam, gamma=gamma)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    episode_starts = torch.ones(N, dtype=torch.bool, device="cuda")
+    for rollout in range(2):          # second rollout starts mid-episode: history depth carried over
+        gbuf.reset()
+        obuf.reset()
+        for t in range(T):
+            actions = torch.rand((N, 4), device="cuda", generator=g) * torch.tensor([2, 2, 2, 1.0], device="cuda") - torch.tensor([1, 1, 1, 0.0], device="cuda")
+            values = torch.randn(N, device="cuda", generator=g)
+            log_probs = torch.randn(N, device="cuda", generator=g)
+            last_obs = obs.clone()
+            o, rew, done, trunc = env.step(actions, auto_reset=True)
+            rew = rew.clone()
+            done_b = done.bool().clone()
+            if t % 17 == 5:           # force resets of a few envs so stacks with 0..9 valid frames occur
+                mask = torch.zeros(N, dtype=torch.uint8, device="cuda")
+                mask[(t * 7) % N::11] = 1
+                env.reset(mask=mask)
+                done_b |= mask.bool()
+            gbuf.add(last_obs, actions, rew, episode_starts, values, log_probs)
+            obuf.add(last_obs.cpu().numpy(), actions.cpu().numpy(), rew.cpu().numpy(), episode_starts.cpu().numpy(), values.cpu().numpy(), log_probs.cpu().numpy())
+            obs = env.obs.clone()
+            episode_starts = done_b
+        last_values = torch.randn(N, device="cuda", generator=g)
+        gbuf.compute_returns_and_advantage(last_values, episode_starts)
+        obuf.compute_returns_and_advantage(last_values.cpu().numpy(), episode_starts.cpu().numpy())
+        assert np.array_equal(gbuf.advantages.cpu().numpy(), obuf.advantages)
+        assert np.array_equal(gbuf.returns.cpu().numpy(), obuf.returns)
+        idx = torch.randperm(T * N, device="cuda", generator=g)
+        for start in range(0, T * N, 4096):
+            bi = idx[start:start + 4096]
+            s = gbuf.gather(bi)
+            want = obuf.get_samples(bi.cpu().numpy())
+            assert np.array_equal(s.observations.cpu().numpy(), want[0]), "rebuilt observation stacks differ"
+            assert np.array_equal(s.actions.cpu().numpy(), want[1])
+            for a, b in zip((s.old_values, s.old_log_prob, s.advantages, s.returns), want[2:]):
+                assert np.array_equal(a.cpu().numpy(), b)
+        assert int((gbuf.age == 0).sum()) > 0 and int((gbuf.age == 9).sum()) > 0
+    n = sum(1 for _ in gbuf.get(batch_size=8192))
+    assert n == -(-T * N // 8192)

@@ -46,6 +46,8 @@ def load():
     L.f16_rollout_add.argtypes = [i64, i64, i64] + [vp] * 15
     L.f16_rollout_gae.argtypes = [i64, i64, C.c_float, C.c_float] + [vp] * 8
     L.f16_rollout_gather.argtypes = [i64, i64, i64] + [vp] * 15
+    L.f16_features17.argtypes = [i64, vp, vp, vp]
+    L.f16_features17.restype = i32
     for name in ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather"):
         getattr(L, name).restype = i32
     L.f16_launch_count.restype = i64
@@ -72,4 +74,4 @@ EXPORTED_SYMBOLS = (
     "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states", "f16_unpack_states",
     "f16_set_env_step", "f16_get_snapshot", "f16_get_stats", "f16_stats_device_ptr", "f16_launch_count", "f16_num_state_fields",
     "f16_last_error", "f16_version")
-ROLLOUT_SYMBOLS = ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather")
+ROLLOUT_SYMBOLS = ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather", "f16_features17")

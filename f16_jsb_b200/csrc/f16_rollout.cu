@@ -51,14 +51,26 @@ __global__ void rollout_gae_kernel(int64_t n, int64_t T, float gamma, float gamm
   float last_gae_lam = 0.0f;
   float next_values = last_values[e];
   float next_non_terminal = __fsub_rn(1.0f, dones[e] ? 1.0f : 0.0f);
-  for (int64_t step = T - 1; step >= 0; --step) {
-    const float v = values[step * n + e];
-    const float delta = __fsub_rn(__fadd_rn(rewards[step * n + e], __fmul_rn(__fmul_rn(gamma, next_values), next_non_terminal)), v);
-    last_gae_lam = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lambda, next_non_terminal), last_gae_lam));
-    advantages[step * n + e] = last_gae_lam;
-    returns[step * n + e] = __fadd_rn(last_gae_lam, v);
-    next_values = v;
-    next_non_terminal = __fsub_rn(1.0f, episode_starts[step * n + e]);
+  // the recurrence is sequential in time, the loads are not: fetch CH steps ahead of the dependent chain
+  constexpr int CH = 8;
+  for (int64_t hi = T; hi > 0; hi -= CH) {
+    float r[CH], v[CH], es[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int64_t step = hi - 1 - k;
+      if (step >= 0) { r[k] = rewards[step * n + e]; v[k] = values[step * n + e]; es[k] = episode_starts[step * n + e]; }
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int64_t step = hi - 1 - k;
+      if (step < 0) break;
+      const float delta = __fsub_rn(__fadd_rn(r[k], __fmul_rn(__fmul_rn(gamma, next_values), next_non_terminal)), v[k]);
+      last_gae_lam = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_lambda, next_non_terminal), last_gae_lam));
+      advantages[step * n + e] = last_gae_lam;
+      returns[step * n + e] = __fadd_rn(last_gae_lam, v[k]);
+      next_values = v[k];
+      next_non_terminal = __fsub_rn(1.0f, es[k]);
+    }
   }
 }
 

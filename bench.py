@@ -41,6 +41,17 @@ BYTES_PER_ENV_STEP_FP32 = 576 + 16 + 540 + 600 + 6
 BYTES_PER_ENV_STEP_FP64 = 2 * (11 * 8 + 42 * 8 + 8 * 4) + 16 + 540 + 600 + 6
 
 
+def ncu_traffic(kernel, envs):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
+        if t and int(t["envs"]) == int(envs):
+            return float(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -240,7 +251,9 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total_envs * 16, "d2h_bytes_per_step": total_envs * (600 + 4 + 1 + 1),
                 "steps": e2e_steps, "api": "F16VecEnv.step(numpy actions) -> numpy obs, rewards, dones, infos (pinned host ring)"},
         "gpu_launches": int(launches) * world,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic("f16_step_kernel<%s>" % ("float" if mode == "fp32" else "double"), hi - lo),
+                     "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/)", "algorithmic_bytes_per_launch": (hi - lo) * bpe,
                      "peak_source": peak_src, "kernel": "f16_step_kernel<%s>" % ("float" if mode == "fp32" else "double"),
                      "algorithmic_bytes_per_env_step": bpe, "per": "GPU"},
     }

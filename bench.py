@@ -236,7 +236,7 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     bpe = BYTES_PER_ENV_STEP_FP32 if mode == "fp32" else BYTES_PER_ENV_STEP_FP64
     achieved = (hi - lo) * bpe / (ms_step * 1e-3) / 1e9          # per GPU: one launch processes one rank's envs
-    cpu = cpu_baseline(seconds=args.cpu_seconds) if not args.no_cpu_baseline else None
+    cpu = cpu_baseline(seconds=args.cpu_seconds) if (not args.no_cpu_baseline and world == 1) else None   # rank 0, N=1 only
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -9,10 +9,23 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    txt = open(os.path.join(ROOT, "include", "f16_b200.h")).read()
+def declared_symbols(header="f16_b200.h"):
+    txt = open(os.path.join(ROOT, "include", header)).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     return sorted(set(re.findall(r"\b(f16_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_every_header_in_include_is_exported():
+    from f16_jsb_b200 import _lib
+    L = _lib.load()
+    n = 0
+    for header in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if not header.endswith(".h"):
+            continue
+        for s in declared_symbols(header):
+            assert hasattr(L, s), "%s declares %s but libf16b200.so does not export it" % (header, s)
+            n += 1
+    assert n >= 24
 
 
 def test_header_symbols_are_exported():

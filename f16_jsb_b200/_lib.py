@@ -31,6 +31,8 @@ def load():
     L.f16_state_bytes.argtypes = [vp]
     L.f16_state_bytes.restype = C.c_size_t
     L.f16_bind.argtypes = [vp] + [vp] * 8
+    L.f16_bind_ring.argtypes = [vp] + [vp] * 8
+    L.f16_obs_window.argtypes = [vp, C.POINTER(i32)]
     L.f16_reset.argtypes = [vp, vp, vp, u64, vp]
     L.f16_step.argtypes = [vp, vp, i32, vp]
     L.f16_step_host.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
@@ -54,7 +56,7 @@ def load():
     L.f16_num_state_fields.restype = i32
     L.f16_last_error.restype = C.c_char_p
     L.f16_version.restype = C.c_char_p
-    for name in ("f16_create", "f16_destroy", "f16_bind", "f16_reset", "f16_step", "f16_step_host",
+    for name in ("f16_create", "f16_destroy", "f16_bind", "f16_bind_ring", "f16_obs_window", "f16_reset", "f16_step", "f16_step_host",
                  "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states",
                  "f16_unpack_states", "f16_set_env_step", "f16_get_snapshot", "f16_get_stats",
                  "f16_stats_device_ptr"):
@@ -70,7 +72,7 @@ def check(rc: int, what: str = "") -> None:
 
 
 EXPORTED_SYMBOLS = (
-    "f16_create", "f16_destroy", "f16_state_bytes", "f16_bind", "f16_reset", "f16_step", "f16_step_host",
+    "f16_create", "f16_destroy", "f16_state_bytes", "f16_bind", "f16_bind_ring", "f16_obs_window", "f16_reset", "f16_step", "f16_step_host",
     "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states", "f16_unpack_states",
     "f16_set_env_step", "f16_get_snapshot", "f16_get_stats", "f16_stats_device_ptr", "f16_launch_count", "f16_num_state_fields",
     "f16_last_error", "f16_version")

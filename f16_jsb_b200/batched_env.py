@@ -27,10 +27,15 @@ class F16BatchedEnv:
 
     mode: "fp64" (parity: all model math in double) or "fp32" (throughput: float math, double
     kinematic state). Observations are (N, 10, 15) float32, row 0 oldest, row 9 newest.
+
+    obs_layout: "stacked" (default) keeps a contiguous (N, 10, 15) tensor that the step kernel shifts in
+    place, exactly the reference's array. "ring" keeps (N, 20, 15) and writes each new frame twice, so
+    `obs` is a zero-copy strided view (N, 10, 15) of the current window - same values, 2.4x less HBM
+    traffic per step; each env's 150 floats stay contiguous (obs.view(N, 150) is a valid strided matrix).
     """
 
     def __init__(self, num_envs: int, device=None, mode: str = "fp32", seed: int = 0,
-                 with_terminal_obs: bool = True, env_id_base: int = 0):
+                 with_terminal_obs: bool = True, env_id_base: int = 0, obs_layout: str = "stacked"):
         if not torch.cuda.is_available():
             raise _lib.F16Error("F16BatchedEnv needs a CUDA device: the F-16 env has no CPU fallback")
         self.lib = _lib.load()
@@ -48,21 +53,37 @@ class F16BatchedEnv:
         n = self.num_envs
         with torch.cuda.device(self.device):
             self.state = torch.zeros(self.lib.f16_state_bytes(h), dtype=torch.uint8, device=self.device)
-            self.obs = torch.zeros((n, NUM_STACKED_FRAMES, NUM_FEATURES), dtype=torch.float32, device=self.device)
+            if obs_layout not in ("stacked", "ring"):
+                raise ValueError("obs_layout must be 'stacked' or 'ring'")
+            self.obs_layout = obs_layout
+            rows = NUM_STACKED_FRAMES * (2 if obs_layout == "ring" else 1)
+            self._obs_buf = torch.zeros((n, rows, NUM_FEATURES), dtype=torch.float32, device=self.device)
             self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
             self.done = torch.zeros(n, dtype=torch.uint8, device=self.device)
             self.truncated = torch.zeros(n, dtype=torch.uint8, device=self.device)
-            self.terminal_obs = torch.zeros_like(self.obs) if with_terminal_obs else None
+            self.terminal_obs = (torch.zeros((n, NUM_STACKED_FRAMES, NUM_FEATURES), dtype=torch.float32, device=self.device)
+                                 if with_terminal_obs else None)
             self.ep_return = torch.zeros(n, dtype=torch.float32, device=self.device)
             self.ep_len = torch.zeros(n, dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.f16_bind(h, _ptr(self.state), _ptr(self.obs), _ptr(self.reward), _ptr(self.done),
-                                     _ptr(self.truncated), _ptr(self.terminal_obs), _ptr(self.ep_return),
-                                     _ptr(self.ep_len)), "f16_bind")
+        bind = self.lib.f16_bind_ring if obs_layout == "ring" else self.lib.f16_bind
+        _lib.check(bind(h, _ptr(self.state), _ptr(self._obs_buf), _ptr(self.reward), _ptr(self.done),
+                        _ptr(self.truncated), _ptr(self.terminal_obs), _ptr(self.ep_return),
+                        _ptr(self.ep_len)), "f16_bind")
         if env_id_base:
             _lib.check(self.lib.f16_set_env_id_base(h, int(env_id_base)), "f16_set_env_id_base")
         sp = C.c_void_p()
         _lib.check(self.lib.f16_stats_device_ptr(h, C.byref(sp)), "f16_stats_device_ptr")
         self._stats_ptr = sp.value
+
+    @property
+    def obs(self) -> torch.Tensor:
+        """Current stacked observations (N, 10, 15): the bound tensor itself (stacked layout) or the
+        window view of the ring (ring layout; a new view after every step)."""
+        if self.obs_layout == "stacked":
+            return self._obs_buf
+        first = C.c_int()
+        _lib.check(self.lib.f16_obs_window(self._h, C.byref(first)), "f16_obs_window")
+        return self._obs_buf[:, first.value:first.value + NUM_STACKED_FRAMES, :]
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):

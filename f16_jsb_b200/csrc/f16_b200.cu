@@ -155,6 +155,7 @@ struct StepArgs {
   int64_t env_id_base;
   uint32_t step_counter;
   int auto_reset;
+  int ring_slot;     // ring layout only: slot (0..9) this step writes; the window is rows slot+1 .. slot+10
 };
 
 template <typename R>
@@ -260,6 +261,55 @@ __device__ __forceinline__ void warp_write_obs(float* __restrict__ obs, float* _
   }
 }
 
+// Ring layout of the observations (opt-in, f16_bind_ring): per env 20 rows of 15 floats; each step writes
+// the newest frame into row `slot` and its mirror `slot + 10`, so the chronological stack is always the
+// contiguous window of rows slot+1 .. slot+10 and nothing is ever shifted: 120 B written per env-step
+// instead of 540 B read + 600 B written. A reset fills all 20 rows with the reset frame. The warp writes
+// cooperatively: lanes run over the 32 x 15 floats of one row set, so a store touches ~2 envs' 60-byte rows.
+__device__ __forceinline__ void warp_write_ring(float* __restrict__ ring, float* __restrict__ term_obs, int64_t env0, int slot,
+                                                const float (*frame_s)[16], const float (*tframe_s)[16],
+                                                const uint8_t* flags_s) {
+  const int lane = threadIdx.x & 31;
+  constexpr int ROW = F16_OBS_FEATURES, RING_ROWS = 2 * F16_OBS_FRAMES, PER_ENV = RING_ROWS * ROW;   // 15, 20, 300
+  const uint8_t my = flags_s[lane];
+  const unsigned m_active = __ballot_sync(0xffffffffu, my & 1);
+  const unsigned m_reset = __ballot_sync(0xffffffffu, my & 2);
+  const unsigned m_term = term_obs ? __ballot_sync(0xffffffffu, my & 4) : 0u;
+  float* const base = ring + env0 * PER_ENV;
+  // terminal stacks first (they need the window as it was before this step's frame): rare
+  if (m_term) {
+    for (int l = 0; l < 32; ++l) {
+      if (!((m_term >> l) & 1)) continue;
+      const float* eb = base + l * PER_ENV + (slot + 1) * ROW;       // rows slot+1 .. slot+9 = the nine older frames
+      float* tb = term_obs + (env0 + l) * (F16_OBS_FRAMES * ROW);
+      for (int j = lane; j < F16_OBS_FRAMES * ROW; j += 32) tb[j] = (j < 9 * ROW) ? eb[j] : tframe_s[l][j - 9 * ROW];
+    }
+    __syncwarp();
+  }
+  // newest frame into rows slot and slot+10 of every env of the warp
+  int l = 0, c = lane;                                    // element i = it*32 + lane -> (env l, column c)
+  while (c >= ROW) { c -= ROW; ++l; }
+#pragma unroll 1
+  for (int it = 0; it < ROW; ++it) {
+    if (l < 32 && ((m_active >> l) & 1) && !((m_reset >> l) & 1)) {
+      const float v = frame_s[l][c];
+      float* eb = base + l * PER_ENV + c;
+      eb[slot * ROW] = v;
+      eb[(slot + F16_OBS_FRAMES) * ROW] = v;
+    }
+    c += 2; l += 2;                                       // 32 = 2 * 15 + 2
+    if (c >= ROW) { c -= ROW; ++l; }
+  }
+  // reset envs: all 20 rows = reset frame
+  if (m_reset) {
+    for (int lr = 0; lr < 32; ++lr) {
+      if (!((m_reset >> lr) & 1) || !((m_active >> lr) & 1)) continue;
+      float* eb = base + lr * PER_ENV;
+      for (int j = lane; j < PER_ENV; j += 32) eb[j] = frame_s[lr][j % ROW];
+    }
+  }
+}
+
 // ---- TMA (bulk async copy) staging of the table image: one elected thread issues a single
 // cp.async.bulk global -> shared::cta that completes on an mbarrier; nobody spends registers or issue
 // slots on the copy and the first tile's state loads overlap with it.
@@ -294,7 +344,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // staged once per CTA and every warp then walks its own sequence of 32-env tiles (tile = warp id,
 // += total warps). Warps never synchronise with each other after the staging barrier, so their
 // load / compute / store phases drift apart and overlap on each SM.
-template <typename R, int MINB>
+template <typename R, int MINB, bool RING>
 __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a) {
   __shared__ __align__(128) Tables<R> T;
   __shared__ __align__(16) float frame_s[WARPS][32][16];
@@ -341,9 +391,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
       // each lane prefetches lines lane, lane+32, ... of the warp's 150-line observation span (F16_PREFETCH_OBS)
       PrefetchHint pf = {nullptr, 0, 0};
 #if F16_PREFETCH_OBS == 1
-      pf.ptr = reinterpret_cast<const char*>(a.obs + env0 * (F16_OBS_FRAMES * F16_OBS_FEATURES)) + lane * 128;
-      pf.count = lane < 22 ? 5 : 4;       // 150 lines of 128 bytes
-      pf.stride = 32 * 128;
+      if (!RING) {
+        pf.ptr = reinterpret_cast<const char*>(a.obs + env0 * (F16_OBS_FRAMES * F16_OBS_FEATURES)) + lane * 128;
+        pf.count = lane < 22 ? 5 : 4;       // 150 lines of 128 bytes
+        pf.stride = 32 * 128;
+      }
 #elif F16_PREFETCH_OBS == 2
       // one TMA bulk prefetch of the warp's whole 19 200-byte span, issued by lane 0
       if (lane == 0) {
@@ -375,7 +427,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
     }
     flags_s[warp][lane] = (uint8_t)(flags & (STEP_ACTIVE | STEP_RESET | STEP_TERMINAL));
     __syncwarp();
-    warp_write_obs(a.obs, a.terminal_obs, env0, frame_s[warp], tframe_s[warp], flags_s[warp]);
+    if (RING) warp_write_ring(a.obs, a.terminal_obs, env0, a.ring_slot, frame_s[warp], tframe_s[warp], flags_s[warp]);
+    else warp_write_obs(a.obs, a.terminal_obs, env0, frame_s[warp], tframe_s[warp], flags_s[warp]);
     __syncwarp();   // the frame / flag staging of this warp is reused by its next tile
   }
 }
@@ -389,6 +442,7 @@ struct ResetArgs {
   size_t r_off, e_off;
   uint64_t seed;
   int64_t env_id_base;
+  int obs_rows;      // 10 (stacked layout) or 20 (ring layout)
 };
 
 template <typename R>
@@ -408,8 +462,8 @@ __global__ void __launch_bounds__(BLOCK) f16_reset_kernel(const ResetArgs a) {
   env_reset_one<R>(s, es, c_snapshot, c_snapshot_props, g, fr);
   store_veh(s, sp, e);
   store_env(es, sp, e);
-  float* ob = a.obs + e * (F16_OBS_FRAMES * F16_OBS_FEATURES);
-  for (int r = 0; r < F16_OBS_FRAMES; ++r)
+  float* ob = a.obs + e * (a.obs_rows * F16_OBS_FEATURES);
+  for (int r = 0; r < a.obs_rows; ++r)
     for (int c = 0; c < F16_OBS_FEATURES; ++c) ob[r * F16_OBS_FEATURES + c] = fr[c];
 }
 
@@ -480,6 +534,7 @@ struct f16_ctx {
   uint32_t step_counter = 0;
   double env_steps = 0.0;            // host-side count for stats[6]
   int num_sms = 1, ctas_per_sm = 1;  // persistent grid of the step kernel
+  int ring = 0, ring_head = 0;       // ring observation layout: next slot to write
 };
 
 template <typename R>
@@ -558,8 +613,8 @@ int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
   }
   CUDA_OK(cudaMalloc(&c->actions_stage, (size_t)n_envs * F16_ACTION_DIM * sizeof(float)));
   CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
-  if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, 1>, BLOCK, 0));
-  else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float, F16_MIN_BLOCKS_F32>, BLOCK, 0));
+  if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, 1, false>, BLOCK, 0));
+  else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float, F16_MIN_BLOCKS_F32, false>, BLOCK, 0));
   if (c->ctas_per_sm < 1) c->ctas_per_sm = 1;
   *out = c;
   return 0;
@@ -586,7 +641,24 @@ int f16_bind(f16_handle h, void* state, float* obs, float* reward, uint8_t* done
   CUDA_OK(cudaSetDevice(h->device));
   h->state = state; h->obs = obs; h->reward = reward; h->done = done; h->truncated = truncated;
   h->terminal_obs = terminal_obs; h->ep_return = ep_return; h->ep_len = ep_len;
+  h->ring = 0; h->ring_head = 0;
   CUDA_OK(cudaMemset(state, 0, h->L.total));
+  return 0;
+}
+
+int f16_bind_ring(f16_handle h, void* state, float* obs_ring, float* reward, uint8_t* done, uint8_t* truncated, float* terminal_obs,
+                  float* ep_return, int32_t* ep_len) {
+  int rc = f16_bind(h, state, obs_ring, reward, done, truncated, terminal_obs, ep_return, ep_len);
+  if (rc) return rc;
+  h->ring = 1;
+  h->ring_head = 0;
+  return 0;
+}
+
+int f16_obs_window(f16_handle h, int* first_row) {
+  if (!h || !first_row) return fail("f16_obs_window: NULL argument");
+  // stacked layout: rows 0..9; ring layout: rows slot+1 .. slot+10 of the slot written by the last step
+  *first_row = h->ring ? ((h->ring_head + F16_OBS_FRAMES - 1) % F16_OBS_FRAMES) + 1 : 0;
   return 0;
 }
 
@@ -605,6 +677,7 @@ int f16_reset(f16_handle h, const uint8_t* mask, const float* goals, uint64_t se
   a.state = h->state; a.mask = mask; a.goals = goals; a.obs = h->obs;
   a.n = h->L.n; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
   a.seed = seed; a.env_id_base = h->env_id_base;
+  a.obs_rows = h->ring ? 2 * F16_OBS_FRAMES : F16_OBS_FRAMES;
   unsigned grid = (unsigned)((h->L.n + BLOCK - 1) / BLOCK);
   if (h->mode == F16_MODE_FP64) f16_reset_kernel<double><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
   else f16_reset_kernel<float><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
@@ -622,13 +695,17 @@ int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream) {
   a.done = h->done; a.truncated = h->truncated; a.terminal_obs = h->terminal_obs; a.ep_return = h->ep_return;
   a.ep_len = h->ep_len; a.stats = h->stats_dev; a.n = h->L.n; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
   a.seed = h->seed; a.env_id_base = h->env_id_base; a.step_counter = h->step_counter++; a.auto_reset = auto_reset;
+  a.ring_slot = h->ring_head;
+  if (h->ring) h->ring_head = (h->ring_head + 1) % F16_OBS_FRAMES;
   // persistent grid: SMs x resident CTAs (capped by the number of 32-env tiles)
   const int64_t tiles = (h->L.n + 31) / 32;
   int64_t want = (int64_t)h->num_sms * h->ctas_per_sm;
   const int64_t need = (tiles + WARPS - 1) / WARPS;
   unsigned grid = (unsigned)((F16_PERSISTENT && want < need) ? want : need);
+  const cudaStream_t st = (cudaStream_t)stream;
   if (h->mode == F16_MODE_FP64) {
-    f16_step_kernel<double, 1><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+    if (h->ring) f16_step_kernel<double, 1, true><<<grid, BLOCK, 0, st>>>(a);
+    else f16_step_kernel<double, 1, false><<<grid, BLOCK, 0, st>>>(a);
   } else {
     // Two register budgets of the float kernel: F16_MIN_BLOCKS_F32 CTAs/SM (167 registers, fastest per
     // env when the grid is many waves deep) and one more CTA per SM (128 registers), which wins when the
@@ -636,8 +713,13 @@ int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream) {
     const int64_t slots_a = (int64_t)h->num_sms * F16_MIN_BLOCKS_F32, slots_b = (int64_t)h->num_sms * (F16_MIN_BLOCKS_F32 + 1);
     const double cost_a = (double)((need + slots_a - 1) / slots_a);
     const double cost_b = (double)((need + slots_b - 1) / slots_b) * 1.45;   // measured per-wave cost ratio
-    if (cost_b < cost_a) f16_step_kernel<float, F16_MIN_BLOCKS_F32 + 1><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
-    else f16_step_kernel<float, F16_MIN_BLOCKS_F32><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+    if (cost_b < cost_a) {
+      if (h->ring) f16_step_kernel<float, F16_MIN_BLOCKS_F32 + 1, true><<<grid, BLOCK, 0, st>>>(a);
+      else f16_step_kernel<float, F16_MIN_BLOCKS_F32 + 1, false><<<grid, BLOCK, 0, st>>>(a);
+    } else {
+      if (h->ring) f16_step_kernel<float, F16_MIN_BLOCKS_F32, true><<<grid, BLOCK, 0, st>>>(a);
+      else f16_step_kernel<float, F16_MIN_BLOCKS_F32, false><<<grid, BLOCK, 0, st>>>(a);
+    }
   }
   g_launches++;
   h->env_steps += (double)h->L.n;
@@ -655,7 +737,18 @@ int f16_step_host(f16_handle h, const float* actions_host, int auto_reset, float
   CUDA_OK(cudaMemcpyAsync(h->actions_stage, actions_host, n * F16_ACTION_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
   int rc = f16_step(h, h->actions_stage, auto_reset, stream);
   if (rc) return rc;
-  if (obs_host) CUDA_OK(cudaMemcpyAsync(obs_host, h->obs, n * F16_OBS_FRAMES * F16_OBS_FEATURES * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (obs_host) {
+    const size_t stack_bytes = F16_OBS_FRAMES * F16_OBS_FEATURES * sizeof(float);
+    if (h->ring) {
+      // strided device->host copy of each env's 600-byte window out of its 1200-byte ring
+      int first = 0;
+      f16_obs_window(h, &first);
+      CUDA_OK(cudaMemcpy2DAsync(obs_host, stack_bytes, h->obs + (size_t)first * F16_OBS_FEATURES, 2 * stack_bytes, stack_bytes, n,
+                                cudaMemcpyDeviceToHost, st));
+    } else {
+      CUDA_OK(cudaMemcpyAsync(obs_host, h->obs, n * stack_bytes, cudaMemcpyDeviceToHost, st));
+    }
+  }
   if (reward_host) CUDA_OK(cudaMemcpyAsync(reward_host, h->reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (done_host) CUDA_OK(cudaMemcpyAsync(done_host, h->done, n, cudaMemcpyDeviceToHost, st));
   if (truncated_host) CUDA_OK(cudaMemcpyAsync(truncated_host, h->truncated, n, cudaMemcpyDeviceToHost, st));

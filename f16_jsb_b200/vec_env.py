@@ -65,9 +65,11 @@ class F16VecEnv(VecEnvBase):
     metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 30}   # jsbsim_gym.py:120
 
     def __init__(self, num_envs: int, device=None, mode: str = "fp32", seed: int = 0, host_ring: int = 2,
-                 copy_obs: bool = False, lazy_infos: Optional[bool] = None, env_id_base: int = 0):
+                 copy_obs: bool = False, lazy_infos: Optional[bool] = None, env_id_base: int = 0,
+                 obs_layout: str = "stacked"):
         obs_space, act_space = make_spaces()
-        self.env = F16BatchedEnv(num_envs, device=device, mode=mode, seed=seed, env_id_base=env_id_base)
+        self.env = F16BatchedEnv(num_envs, device=device, mode=mode, seed=seed, env_id_base=env_id_base,
+                                 obs_layout=obs_layout)
         self.render_mode = None
         try:
             super().__init__(num_envs, obs_space, act_space)

@@ -52,6 +52,16 @@ size_t f16_state_bytes(f16_handle h);
 int f16_bind(f16_handle h, void* state, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
              float* terminal_obs, float* ep_return, int32_t* ep_len);
 
+/* Optional ring layout of the observations. obs_ring: N x 20 x 15 float. Each step writes the newest frame
+ * into row `slot` and row `slot + 10` (slot cycles 0..9); the chronological (10,15) stack of every env is the
+ * contiguous row window first_row .. first_row + 9 reported by f16_obs_window (a strided view, never shifted or
+ * copied): 120 B written per env-step instead of 540 B read + 600 B written. Everything else as f16_bind;
+ * terminal_obs stays a plain N x 10 x 15 tensor; f16_step_host still returns contiguous N x 10 x 15 host arrays. */
+int f16_bind_ring(f16_handle h, void* state, float* obs_ring, float* reward, uint8_t* done, uint8_t* truncated,
+                  float* terminal_obs, float* ep_return, int32_t* ep_len);
+/* First row of the current observation window: 0 for the stacked layout, 1..10 for the ring layout. */
+int f16_obs_window(f16_handle h, int* first_row);
+
 /* JSBSimEnv.reset + PositionReward.reset (jsbsim_gym.py:289-331, 511-519) for every env whose mask
  * byte is non-zero (mask == NULL: all). goals: N x 3 float device pointer holding the goal of
  * every env (entries of unmasked envs are ignored), or NULL to sample distance~U[1000,10000) m,

@@ -229,3 +229,55 @@ def test_random_action_rollout_full_size_properties(F16BatchedEnv):
     s = env.stats()
     assert s["episodes"] == dones and s["env_steps"] == 300 * n
     assert s["crashes"] + s["goals"] + s["truncations"] == s["episodes"]
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp64"])
+def test_ring_layout_is_value_identical_to_stacked(F16BatchedEnv, mode):
+    """obs_layout='ring' (frame written twice, zero-copy window view) must return the stacks, rewards,
+    flags, terminal observations and host copies of the default in-place-shift layout, across
+    auto-resets and masked resets, for a ragged batch. The two layouts are separate instantiations of the
+    step kernel and the compiler contracts a few multiply-adds differently, so values agree to float
+    rounding (1e-5 relative here, over 70 free-running steps), not bit for bit; structure is exact."""
+    def same(x, y, what=""):
+        assert x.shape == y.shape
+        assert torch.allclose(x, y, rtol=2e-5, atol=2e-4), what
+
+    n = 1000 + 37
+    a = F16BatchedEnv(n, mode=mode, seed=9)
+    b = F16BatchedEnv(n, mode=mode, seed=9, obs_layout="ring")
+    g = torch.Generator(device="cuda").manual_seed(1)
+    # goals 150..900 m straight ahead at the start altitude: the envs reach them (+10, terminated) between
+    # steps ~10 and ~100, so auto-resets and terminal observations occur all along the run
+    goals0 = torch.zeros((n, 3), device="cuda")
+    goals0[:, 0] = torch.rand(n, device="cuda", generator=g) * 750 + 150
+    goals0[:, 2] = 1524.0
+    assert torch.equal(a.reset(goals=goals0), b.reset(goals=goals0).contiguous())     # resets are copies of the snapshot: exact
+    host = np.zeros((n, 10, 15), np.float32)
+    for k in range(70):
+        act = (torch.rand((n, 4), device="cuda", generator=g) * 2 - 1) * 0.1
+        act[:, 3] = 0.8
+        if k == 30:
+            oa, ra, da, ta = a.step(act, auto_reset=True)
+            b.step_host(act.cpu().numpy(), host, None, None, None, auto_reset=True)     # strided device->host copy
+            same(torch.from_numpy(host).cuda(), oa, "host copy of the ring window")
+            ob = b.obs
+        else:
+            oa, ra, da, ta = a.step(act, auto_reset=True)
+            ob, rb, db, tb = b.step(act, auto_reset=True)
+            same(ra, rb, "rewards")
+            assert torch.equal(da, db) and torch.equal(ta, tb)
+        assert ob.shape == (n, 10, 15) and ob.stride() == (300, 15, 1)
+        same(oa, ob.contiguous(), "window differs at step %d" % k)
+        same(oa.reshape(n, 150), ob.reshape(n, 150))
+        if bool(da.any()):
+            m = da.bool()
+            same(a.terminal_obs[m], b.terminal_obs[m], "terminal observations")
+        if k == 20:
+            mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+            mask[5::13] = 1
+            gl = torch.rand((n, 3), device="cuda", generator=g) * 3000 + 1000
+            a.reset(mask=mask, goals=gl)
+            b.reset(mask=mask, goals=gl)
+            same(a.obs, b.obs.contiguous())
+    sa, sb = a.stats(), b.stats()
+    assert sa["goals"] > 100 and sa["episodes"] == sb["episodes"] and sa["goals"] == sb["goals"] and sa["length_sum"] == sb["length_sum"]

@@ -11,6 +11,18 @@ class F16Error(RuntimeError):
     pass
 
 
+class DoneRecord(C.Structure):
+    """f16_done_record (include/f16_b200.h): one finished env of a frame-layout step."""
+    _fields_ = [("env", C.c_int32), ("flags", C.c_int32), ("ep_return", C.c_float), ("ep_len", C.c_int32),
+                ("terminal_frame", C.c_float * 16), ("reset_frame", C.c_float * 16)]
+
+
+class HostwinResult(C.Structure):
+    """f16_hostwin_result (include/f16_hostwin.h)."""
+    _fields_ = [("ring", C.c_int32), ("first_slot", C.c_int32), ("n_done", C.c_int64), ("reward", C.c_void_p),
+                ("done", C.c_void_p), ("truncated", C.c_void_p), ("records", C.c_void_p), ("terminal_obs", C.c_void_p)]
+
+
 def load():
     """Load the CUDA library, building it in-tree first if the sources are newer."""
     global _lib
@@ -32,7 +44,18 @@ def load():
     L.f16_state_bytes.restype = C.c_size_t
     L.f16_bind.argtypes = [vp] + [vp] * 8
     L.f16_bind_ring.argtypes = [vp] + [vp] * 8
+    L.f16_bind_frames.argtypes = [vp] + [vp] * 7
+    L.f16_set_done_list.argtypes = [vp, vp, vp]
     L.f16_obs_window.argtypes = [vp, C.POINTER(i32)]
+    L.f16_hostwin_create.argtypes = [C.POINTER(vp), i64, i32, i32]
+    L.f16_hostwin_destroy.argtypes = [vp]
+    L.f16_hostwin_layout.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.f16_hostwin_action_buffer.argtypes = [vp, i32]
+    L.f16_hostwin_action_buffer.restype = vp
+    L.f16_hostwin_reset.argtypes = [vp, vp, vp, C.POINTER(HostwinResult)]
+    L.f16_hostwin_step.argtypes = [vp, vp, vp, i32, vp, C.POINTER(HostwinResult)]
+    L.f16_hostwin_fill.argtypes = [vp, vp, C.POINTER(HostwinResult)]
+    L.f16_hostwin_push.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.POINTER(HostwinResult)]
     L.f16_reset.argtypes = [vp, vp, vp, u64, vp]
     L.f16_step.argtypes = [vp, vp, i32, vp]
     L.f16_step_host.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp]
@@ -56,7 +79,10 @@ def load():
     L.f16_num_state_fields.restype = i32
     L.f16_last_error.restype = C.c_char_p
     L.f16_version.restype = C.c_char_p
-    for name in ("f16_create", "f16_destroy", "f16_bind", "f16_bind_ring", "f16_obs_window", "f16_reset", "f16_step", "f16_step_host",
+    for name in HOSTWIN_SYMBOLS:
+        if name != "f16_hostwin_action_buffer":
+            getattr(L, name).restype = i32
+    for name in ("f16_create", "f16_destroy", "f16_bind", "f16_bind_ring", "f16_bind_frames", "f16_set_done_list", "f16_obs_window", "f16_reset", "f16_step", "f16_step_host",
                  "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states",
                  "f16_unpack_states", "f16_set_env_step", "f16_get_snapshot", "f16_get_stats",
                  "f16_stats_device_ptr"):
@@ -72,8 +98,10 @@ def check(rc: int, what: str = "") -> None:
 
 
 EXPORTED_SYMBOLS = (
-    "f16_create", "f16_destroy", "f16_state_bytes", "f16_bind", "f16_bind_ring", "f16_obs_window", "f16_reset", "f16_step", "f16_step_host",
+    "f16_create", "f16_destroy", "f16_state_bytes", "f16_bind", "f16_bind_ring", "f16_bind_frames", "f16_set_done_list", "f16_obs_window", "f16_reset", "f16_step", "f16_step_host",
     "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states", "f16_unpack_states",
     "f16_set_env_step", "f16_get_snapshot", "f16_get_stats", "f16_stats_device_ptr", "f16_launch_count", "f16_num_state_fields",
     "f16_last_error", "f16_version")
+HOSTWIN_SYMBOLS = ("f16_hostwin_create", "f16_hostwin_destroy", "f16_hostwin_layout", "f16_hostwin_action_buffer", "f16_hostwin_reset",
+                   "f16_hostwin_step", "f16_hostwin_fill", "f16_hostwin_push")
 ROLLOUT_SYMBOLS = ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather", "f16_features17")

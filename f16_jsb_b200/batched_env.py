@@ -28,7 +28,9 @@ class F16BatchedEnv:
     mode: "fp64" (parity: all model math in double) or "fp32" (throughput: float math, double
     kinematic state). Observations are (N, 10, 15) float32, row 0 oldest, row 9 newest.
 
-    obs_layout: "stacked" (default) keeps a contiguous (N, 10, 15) tensor that the step kernel shifts in
+    obs_layout: "frame" keeps no observation history on the device: `obs` is the (N, 15) tensor of newest
+    frames, 60 B written per env-step; the ten-frame windows then live in host memory (host_window.py,
+    F16VecEnv's default) or in the frame-only rollout store (rollout.py). "stacked" (default) keeps a contiguous (N, 10, 15) tensor that the step kernel shifts in
     place, exactly the reference's array. "ring" keeps (N, 20, 15) and writes each new frame twice, so
     `obs` is a zero-copy strided view (N, 10, 15) of the current window - same values, 2.4x less HBM
     traffic per step; each env's 150 floats stay contiguous (obs.view(N, 150) is a valid strided matrix).
@@ -53,11 +55,15 @@ class F16BatchedEnv:
         n = self.num_envs
         with torch.cuda.device(self.device):
             self.state = torch.zeros(self.lib.f16_state_bytes(h), dtype=torch.uint8, device=self.device)
-            if obs_layout not in ("stacked", "ring"):
-                raise ValueError("obs_layout must be 'stacked' or 'ring'")
+            if obs_layout not in ("stacked", "ring", "frame"):
+                raise ValueError("obs_layout must be 'stacked', 'ring' or 'frame'")
             self.obs_layout = obs_layout
-            rows = NUM_STACKED_FRAMES * (2 if obs_layout == "ring" else 1)
-            self._obs_buf = torch.zeros((n, rows, NUM_FEATURES), dtype=torch.float32, device=self.device)
+            if obs_layout == "frame":
+                self._obs_buf = torch.zeros((n, NUM_FEATURES), dtype=torch.float32, device=self.device)
+                with_terminal_obs = False
+            else:
+                rows = NUM_STACKED_FRAMES * (2 if obs_layout == "ring" else 1)
+                self._obs_buf = torch.zeros((n, rows, NUM_FEATURES), dtype=torch.float32, device=self.device)
             self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
             self.done = torch.zeros(n, dtype=torch.uint8, device=self.device)
             self.truncated = torch.zeros(n, dtype=torch.uint8, device=self.device)
@@ -65,10 +71,14 @@ class F16BatchedEnv:
                                  if with_terminal_obs else None)
             self.ep_return = torch.zeros(n, dtype=torch.float32, device=self.device)
             self.ep_len = torch.zeros(n, dtype=torch.int32, device=self.device)
-        bind = self.lib.f16_bind_ring if obs_layout == "ring" else self.lib.f16_bind
-        _lib.check(bind(h, _ptr(self.state), _ptr(self._obs_buf), _ptr(self.reward), _ptr(self.done),
-                        _ptr(self.truncated), _ptr(self.terminal_obs), _ptr(self.ep_return),
-                        _ptr(self.ep_len)), "f16_bind")
+        if obs_layout == "frame":
+            _lib.check(self.lib.f16_bind_frames(h, _ptr(self.state), _ptr(self._obs_buf), _ptr(self.reward), _ptr(self.done),
+                                                _ptr(self.truncated), None, None), "f16_bind_frames")
+        else:
+            bind = self.lib.f16_bind_ring if obs_layout == "ring" else self.lib.f16_bind
+            _lib.check(bind(h, _ptr(self.state), _ptr(self._obs_buf), _ptr(self.reward), _ptr(self.done),
+                            _ptr(self.truncated), _ptr(self.terminal_obs), _ptr(self.ep_return),
+                            _ptr(self.ep_len)), "f16_bind")
         if env_id_base:
             _lib.check(self.lib.f16_set_env_id_base(h, int(env_id_base)), "f16_set_env_id_base")
         sp = C.c_void_p()
@@ -78,8 +88,9 @@ class F16BatchedEnv:
     @property
     def obs(self) -> torch.Tensor:
         """Current stacked observations (N, 10, 15): the bound tensor itself (stacked layout) or the
-        window view of the ring (ring layout; a new view after every step)."""
-        if self.obs_layout == "stacked":
+        window view of the ring (ring layout; a new view after every step). Frame layout: the newest
+        frames (N, 15)."""
+        if self.obs_layout in ("stacked", "frame"):
             return self._obs_buf
         first = C.c_int()
         _lib.check(self.lib.f16_obs_window(self._h, C.byref(first)), "f16_obs_window")

@@ -156,6 +156,8 @@ struct StepArgs {
   uint32_t step_counter;
   int auto_reset;
   int ring_slot;     // ring layout only: slot (0..9) this step writes; the window is rows slot+1 .. slot+10
+  f16_done_record* done_list;   // frame layout only: one record per env that finished this step (may be mapped host memory)
+  int32_t* done_count;          // frame layout only: device counter of appended records
 };
 
 template <typename R>
@@ -310,6 +312,25 @@ __device__ __forceinline__ void warp_write_ring(float* __restrict__ ring, float*
   }
 }
 
+// Frame layout of the observations (opt-in, f16_bind_frames): the device keeps no history at all. Each step
+// writes the newest frame of every env to a compact (N,15) tensor - one contiguous 1 920-byte span per warp,
+// fully coalesced - which is exactly what crosses PCIe into the host-side window ring (f16_hostwin.h); an env
+// that finished appends its terminal and reset frames to the done list instead.
+__device__ __forceinline__ void warp_write_frames(float* __restrict__ frames, int64_t env0, int64_t n, const float (*frame_s)[16]) {
+  const int lane = threadIdx.x & 31;
+  constexpr int ROW = F16_OBS_FEATURES;
+  float* const base = frames + env0 * ROW;
+  const int live = (int)((n - env0) < 32 ? (n - env0) : 32);
+  int l = 0, c = lane;                                    // element i = it*32 + lane -> (env l, column c)
+  while (c >= ROW) { c -= ROW; ++l; }
+#pragma unroll
+  for (int it = 0; it < ROW; ++it) {
+    if (l < live) base[it * 32 + lane] = frame_s[l][c];
+    c += 2; l += 2;                                       // 32 = 2 * 15 + 2
+    if (c >= ROW) { c -= ROW; ++l; }
+  }
+}
+
 // ---- TMA (bulk async copy) staging of the table image: one elected thread issues a single
 // cp.async.bulk global -> shared::cta that completes on an mbarrier; nobody spends registers or issue
 // slots on the copy and the first tile's state loads overlap with it.
@@ -344,7 +365,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // staged once per CTA and every warp then walks its own sequence of 32-env tiles (tile = warp id,
 // += total warps). Warps never synchronise with each other after the staging barrier, so their
 // load / compute / store phases drift apart and overlap on each SM.
-template <typename R, int MINB, bool RING>
+enum { OBS_STACKED = 0, OBS_RING = 1, OBS_FRAME = 2 };
+template <typename R, int MINB, int OBS>
 __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a) {
   __shared__ __align__(128) Tables<R> T;
   __shared__ __align__(16) float frame_s[WARPS][32][16];
@@ -391,7 +413,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
       // each lane prefetches lines lane, lane+32, ... of the warp's 150-line observation span (F16_PREFETCH_OBS)
       PrefetchHint pf = {nullptr, 0, 0};
 #if F16_PREFETCH_OBS == 1
-      if (!RING) {
+      if (OBS == OBS_STACKED) {
         pf.ptr = reinterpret_cast<const char*>(a.obs + env0 * (F16_OBS_FRAMES * F16_OBS_FEATURES)) + lane * 128;
         pf.count = lane < 22 ? 5 : 4;       // 150 lines of 128 bytes
         pf.stride = 32 * 128;
@@ -422,12 +444,28 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
           if (flags & STEP_TRUNCATED) atomicAdd(a.stats + 5, 1.0);
         }
       }
+      if (OBS == OBS_FRAME && (flags & STEP_DONE) && a.done_list) {
+        // done list: terminal frame (the env's newest row when it finished) and the frame the next episode starts from
+        f16_done_record* rec = a.done_list + atomicAdd(a.done_count, 1);
+        const float* fr = frame_s[warp][lane];
+        const float* tf = (flags & STEP_TERMINAL) ? tframe_s[warp][lane] : fr;
+        uint4* w = reinterpret_cast<uint4*>(rec);
+        w[0] = make_uint4((uint32_t)e, (uint32_t)(((flags & STEP_TRUNCATED) ? 1 : 0) | ((flags & STEP_CRASH) ? 2 : 0) | ((flags & STEP_GOAL) ? 4 : 0)),
+                          __float_as_uint(ep_ret), (uint32_t)ep_len);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t4 = *reinterpret_cast<const float4*>(tf + 4 * q), r4 = *reinterpret_cast<const float4*>(fr + 4 * q);
+          w[1 + q] = make_uint4(__float_as_uint(t4.x), __float_as_uint(t4.y), __float_as_uint(t4.z), __float_as_uint(t4.w));
+          w[5 + q] = make_uint4(__float_as_uint(r4.x), __float_as_uint(r4.y), __float_as_uint(r4.z), __float_as_uint(r4.w));
+        }
+      }
       store_veh(s, sp, e);
       store_env(es, sp, e);
     }
     flags_s[warp][lane] = (uint8_t)(flags & (STEP_ACTIVE | STEP_RESET | STEP_TERMINAL));
     __syncwarp();
-    if (RING) warp_write_ring(a.obs, a.terminal_obs, env0, a.ring_slot, frame_s[warp], tframe_s[warp], flags_s[warp]);
+    if (OBS == OBS_FRAME) warp_write_frames(a.obs, env0, a.n, frame_s[warp]);
+    else if (OBS == OBS_RING) warp_write_ring(a.obs, a.terminal_obs, env0, a.ring_slot, frame_s[warp], tframe_s[warp], flags_s[warp]);
     else warp_write_obs(a.obs, a.terminal_obs, env0, frame_s[warp], tframe_s[warp], flags_s[warp]);
     __syncwarp();   // the frame / flag staging of this warp is reused by its next tile
   }
@@ -534,7 +572,9 @@ struct f16_ctx {
   uint32_t step_counter = 0;
   double env_steps = 0.0;            // host-side count for stats[6]
   int num_sms = 1, ctas_per_sm = 1;  // persistent grid of the step kernel
-  int ring = 0, ring_head = 0;       // ring observation layout: next slot to write
+  int ring = 0, ring_head = 0;       // observation layout (OBS_STACKED / OBS_RING / OBS_FRAME); ring layout: next slot to write
+  f16_done_record* done_list = nullptr;   // frame layout: where the step kernel appends finished envs
+  int32_t* done_count = nullptr;
 };
 
 template <typename R>
@@ -554,6 +594,16 @@ extern "C" {
 // shared with f16_rollout.cu
 int f16_internal_fail(const char* msg) { return fail("%s", msg); }
 void f16_internal_count_launch(void) { g_launches++; }
+
+// shared with f16_hostwin.cu: the buffers a frame-layout env is bound to
+int f16_internal_frame_buffers(f16_handle h, int64_t* n, int* device, float** obs_frame, float** reward, uint8_t** done,
+                               uint8_t** truncated, float** actions_stage) {
+  if (!h || !h->state) return fail("the env handle is NULL or not bound");
+  if (h->ring != OBS_FRAME) return fail("the env is not bound in the frame layout (f16_bind_frames)");
+  *n = h->L.n; *device = h->device; *obs_frame = h->obs; *reward = h->reward; *done = h->done; *truncated = h->truncated;
+  *actions_stage = h->actions_stage;
+  return 0;
+}
 
 const char* f16_last_error(void) { return g_err.c_str(); }
 const char* f16_version(void) { return "f16_b200 0.1 (sm_100a)"; }
@@ -613,8 +663,8 @@ int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
   }
   CUDA_OK(cudaMalloc(&c->actions_stage, (size_t)n_envs * F16_ACTION_DIM * sizeof(float)));
   CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
-  if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, 1, false>, BLOCK, 0));
-  else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float, F16_MIN_BLOCKS_F32, false>, BLOCK, 0));
+  if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, 1, OBS_STACKED>, BLOCK, 0));
+  else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float, F16_MIN_BLOCKS_F32, OBS_STACKED>, BLOCK, 0));
   if (c->ctas_per_sm < 1) c->ctas_per_sm = 1;
   *out = c;
   return 0;
@@ -641,7 +691,8 @@ int f16_bind(f16_handle h, void* state, float* obs, float* reward, uint8_t* done
   CUDA_OK(cudaSetDevice(h->device));
   h->state = state; h->obs = obs; h->reward = reward; h->done = done; h->truncated = truncated;
   h->terminal_obs = terminal_obs; h->ep_return = ep_return; h->ep_len = ep_len;
-  h->ring = 0; h->ring_head = 0;
+  h->ring = OBS_STACKED; h->ring_head = 0;
+  h->done_list = nullptr; h->done_count = nullptr;
   CUDA_OK(cudaMemset(state, 0, h->L.total));
   return 0;
 }
@@ -650,15 +701,35 @@ int f16_bind_ring(f16_handle h, void* state, float* obs_ring, float* reward, uin
                   float* ep_return, int32_t* ep_len) {
   int rc = f16_bind(h, state, obs_ring, reward, done, truncated, terminal_obs, ep_return, ep_len);
   if (rc) return rc;
-  h->ring = 1;
+  h->ring = OBS_RING;
   h->ring_head = 0;
+  return 0;
+}
+
+int f16_bind_frames(f16_handle h, void* state, float* obs_frame, float* reward, uint8_t* done, uint8_t* truncated,
+                    f16_done_record* done_list, int32_t* done_count) {
+  if ((done_list == nullptr) != (done_count == nullptr)) return fail("f16_bind_frames: done_list and done_count go together");
+  int rc = f16_bind(h, state, obs_frame, reward, done, truncated, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  h->ring = OBS_FRAME;
+  h->done_list = done_list;
+  h->done_count = done_count;
+  return 0;
+}
+
+int f16_set_done_list(f16_handle h, f16_done_record* done_list, int32_t* done_count) {
+  if (!h) return fail("f16_set_done_list: NULL handle");
+  if (h->ring != OBS_FRAME) return fail("f16_set_done_list: the env is not bound in the frame layout (f16_bind_frames)");
+  if ((done_list == nullptr) != (done_count == nullptr)) return fail("f16_set_done_list: done_list and done_count go together");
+  h->done_list = done_list;
+  h->done_count = done_count;
   return 0;
 }
 
 int f16_obs_window(f16_handle h, int* first_row) {
   if (!h || !first_row) return fail("f16_obs_window: NULL argument");
   // stacked layout: rows 0..9; ring layout: rows slot+1 .. slot+10 of the slot written by the last step
-  *first_row = h->ring ? ((h->ring_head + F16_OBS_FRAMES - 1) % F16_OBS_FRAMES) + 1 : 0;
+  *first_row = h->ring == OBS_RING ? ((h->ring_head + F16_OBS_FRAMES - 1) % F16_OBS_FRAMES) + 1 : 0;
   return 0;
 }
 
@@ -677,7 +748,7 @@ int f16_reset(f16_handle h, const uint8_t* mask, const float* goals, uint64_t se
   a.state = h->state; a.mask = mask; a.goals = goals; a.obs = h->obs;
   a.n = h->L.n; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
   a.seed = seed; a.env_id_base = h->env_id_base;
-  a.obs_rows = h->ring ? 2 * F16_OBS_FRAMES : F16_OBS_FRAMES;
+  a.obs_rows = h->ring == OBS_RING ? 2 * F16_OBS_FRAMES : h->ring == OBS_FRAME ? 1 : F16_OBS_FRAMES;
   unsigned grid = (unsigned)((h->L.n + BLOCK - 1) / BLOCK);
   if (h->mode == F16_MODE_FP64) f16_reset_kernel<double><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
   else f16_reset_kernel<float><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
@@ -696,16 +767,23 @@ int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream) {
   a.ep_len = h->ep_len; a.stats = h->stats_dev; a.n = h->L.n; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
   a.seed = h->seed; a.env_id_base = h->env_id_base; a.step_counter = h->step_counter++; a.auto_reset = auto_reset;
   a.ring_slot = h->ring_head;
-  if (h->ring) h->ring_head = (h->ring_head + 1) % F16_OBS_FRAMES;
+  a.done_list = h->done_list; a.done_count = h->done_count;
+  if (h->ring == OBS_FRAME && h->done_count) CUDA_OK(cudaMemsetAsync(h->done_count, 0, sizeof(int32_t), (cudaStream_t)stream));
+  if (h->ring == OBS_RING) h->ring_head = (h->ring_head + 1) % F16_OBS_FRAMES;
   // persistent grid: SMs x resident CTAs (capped by the number of 32-env tiles)
   const int64_t tiles = (h->L.n + 31) / 32;
   int64_t want = (int64_t)h->num_sms * h->ctas_per_sm;
   const int64_t need = (tiles + WARPS - 1) / WARPS;
   unsigned grid = (unsigned)((F16_PERSISTENT && want < need) ? want : need);
   const cudaStream_t st = (cudaStream_t)stream;
+#define F16_LAUNCH_STEP(R, MINB)                                                                           \
+  do {                                                                                                    \
+    if (h->ring == OBS_FRAME) f16_step_kernel<R, MINB, OBS_FRAME><<<grid, BLOCK, 0, st>>>(a);             \
+    else if (h->ring == OBS_RING) f16_step_kernel<R, MINB, OBS_RING><<<grid, BLOCK, 0, st>>>(a);          \
+    else f16_step_kernel<R, MINB, OBS_STACKED><<<grid, BLOCK, 0, st>>>(a);                                \
+  } while (0)
   if (h->mode == F16_MODE_FP64) {
-    if (h->ring) f16_step_kernel<double, 1, true><<<grid, BLOCK, 0, st>>>(a);
-    else f16_step_kernel<double, 1, false><<<grid, BLOCK, 0, st>>>(a);
+    F16_LAUNCH_STEP(double, 1);
   } else {
     // Two register budgets of the float kernel: F16_MIN_BLOCKS_F32 CTAs/SM (167 registers, fastest per
     // env when the grid is many waves deep) and one more CTA per SM (128 registers), which wins when the
@@ -713,14 +791,10 @@ int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream) {
     const int64_t slots_a = (int64_t)h->num_sms * F16_MIN_BLOCKS_F32, slots_b = (int64_t)h->num_sms * (F16_MIN_BLOCKS_F32 + 1);
     const double cost_a = (double)((need + slots_a - 1) / slots_a);
     const double cost_b = (double)((need + slots_b - 1) / slots_b) * 1.45;   // measured per-wave cost ratio
-    if (cost_b < cost_a) {
-      if (h->ring) f16_step_kernel<float, F16_MIN_BLOCKS_F32 + 1, true><<<grid, BLOCK, 0, st>>>(a);
-      else f16_step_kernel<float, F16_MIN_BLOCKS_F32 + 1, false><<<grid, BLOCK, 0, st>>>(a);
-    } else {
-      if (h->ring) f16_step_kernel<float, F16_MIN_BLOCKS_F32, true><<<grid, BLOCK, 0, st>>>(a);
-      else f16_step_kernel<float, F16_MIN_BLOCKS_F32, false><<<grid, BLOCK, 0, st>>>(a);
-    }
+    if (cost_b < cost_a) F16_LAUNCH_STEP(float, F16_MIN_BLOCKS_F32 + 1);
+    else F16_LAUNCH_STEP(float, F16_MIN_BLOCKS_F32);
   }
+#undef F16_LAUNCH_STEP
   g_launches++;
   h->env_steps += (double)h->L.n;
   CUDA_OK(cudaGetLastError());
@@ -737,9 +811,10 @@ int f16_step_host(f16_handle h, const float* actions_host, int auto_reset, float
   CUDA_OK(cudaMemcpyAsync(h->actions_stage, actions_host, n * F16_ACTION_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
   int rc = f16_step(h, h->actions_stage, auto_reset, stream);
   if (rc) return rc;
+  if (obs_host && h->ring == OBS_FRAME) return fail("f16_step_host: the frame layout keeps no stacked observations on the device; use f16_hostwin_step");
   if (obs_host) {
     const size_t stack_bytes = F16_OBS_FRAMES * F16_OBS_FEATURES * sizeof(float);
-    if (h->ring) {
+    if (h->ring == OBS_RING) {
       // strided device->host copy of each env's 600-byte window out of its 1200-byte ring
       int first = 0;
       f16_obs_window(h, &first);

@@ -1,0 +1,422 @@
+// f16_hostwin.cu - host-resident observation windows (include/f16_hostwin.h).
+//
+// Host code only (CUDA runtime calls for pinning and DMA, no kernels): the step kernel in its frame layout
+// (f16_b200.cu, OBS_FRAME) emits 60 B per env-step; this file lands those frames in a slot-major ring of pinned
+// host memory whose pages are mapped twice back to back, so that the reference's (N,10,15) stacked observation
+// (jsbsim_gym/jsbsim_gym.py:150,235,263) is a strided view of the ring and never has to be assembled.
+#include <cuda_runtime.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "../../include/f16_hostwin.h"
+
+extern "C" int f16_internal_fail(const char* msg);
+extern "C" int f16_internal_frame_buffers(f16_handle h, int64_t* n, int* device, float** obs_frame, float** reward, uint8_t** done,
+                                          uint8_t** truncated, float** actions_stage);
+
+namespace {
+
+constexpr int SLOTS = F16_HOSTWIN_SLOTS;               // 11: the ten rows of a window + the slot being written
+constexpr int ROWS = F16_OBS_FRAMES;                   // 10
+constexpr int FEAT = F16_OBS_FEATURES;                 // 15
+constexpr size_t ROW_BYTES = FEAT * sizeof(float);     // 60
+constexpr size_t PAGE = 4096;
+
+int failf(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  return f16_internal_fail(buf);
+}
+
+struct Ring {
+  char* base = nullptr;      // 2 * bytes of address space
+  size_t pitch = 0, bytes = 0;
+  bool aliased = false;      // second half maps the same pages (else: a mirror that every write repeats)
+  bool registered = false;   // cudaHostRegister-ed (aliased) / cudaHostAlloc-ed (mirror)
+  bool pinned_alloc = false;
+  int fd = -1;
+};
+
+struct Fix {
+  int32_t env;
+  float frame[FEAT];
+};
+
+// run f(begin, end) over [0, n) on up to 16 host threads when there is enough work to pay for them
+template <class F>
+void parallel_for(int64_t n, int64_t grain, F f) {
+  unsigned hw = std::thread::hardware_concurrency();
+  int64_t t = std::min<int64_t>(std::min<int64_t>(hw ? hw : 1, 16), n / std::max<int64_t>(grain, 1));
+  if (t <= 1) { f((int64_t)0, n); return; }
+  std::vector<std::thread> th;
+  th.reserve((size_t)t - 1);
+  const int64_t chunk = (n + t - 1) / t;
+  for (int64_t i = 1; i < t; ++i) {
+    const int64_t b = i * chunk, e = std::min(n, b + chunk);
+    if (b < e) th.emplace_back([=] { f(b, e); });
+  }
+  f((int64_t)0, std::min(n, chunk));
+  for (auto& x : th) x.join();
+}
+
+}  // namespace
+
+struct f16_hostwin {
+  int64_t n = 0;
+  int n_rings = 1, flags = 0;
+  bool pin = false;
+  Ring ring[2];
+  int head = SLOTS - 1;          // slot holding the newest frame
+  int64_t t = 0;                 // steps since the last reset (selects the ring and the scalar buffers)
+  float* reward[2] = {nullptr, nullptr};
+  uint8_t* done[2] = {nullptr, nullptr};
+  uint8_t* trunc[2] = {nullptr, nullptr};
+  float* actions[2] = {nullptr, nullptr};
+  f16_done_record* records = nullptr;    // mapped pinned memory the step kernel appends to (PIN only)
+  int32_t* count_dev = nullptr;
+  int32_t* count_host = nullptr;
+  cudaEvent_t ev = nullptr;
+  std::vector<float> term[2];
+  std::vector<Fix> pending;              // finished envs of the previous step, still to be applied to the other ring
+  int device = -1;
+
+  float* row(int r, int slot, int64_t env) const { return (float*)(ring[r].base + (size_t)slot * ring[r].pitch + (size_t)env * ROW_BYTES); }
+  void write_row(int r, int slot, int64_t env, const float* f) const {
+    memcpy(row(r, slot, env), f, ROW_BYTES);
+    if (!ring[r].aliased) memcpy(row(r, slot + SLOTS, env), f, ROW_BYTES);
+  }
+};
+
+namespace {
+
+void free_ring(Ring& g) {
+  if (!g.base) return;
+  if (g.pinned_alloc) cudaFreeHost(g.base);
+  else if (g.fd >= 0 || g.aliased) {
+    if (g.registered) cudaHostUnregister(g.base);
+    munmap(g.base, 2 * g.bytes);
+  } else free(g.base);
+  if (g.fd >= 0) close(g.fd);
+  g = Ring();
+}
+
+// The ring's pages mapped twice back to back: [base, base+bytes) and [base+bytes, base+2*bytes).
+bool make_aliased(Ring& g, bool pin) {
+  int fd = (int)syscall(SYS_memfd_create, "f16_hostwin", 0u);
+  if (fd < 0) return false;
+  if (ftruncate(fd, (off_t)g.bytes) != 0) { close(fd); return false; }
+  void* span = mmap(nullptr, 2 * g.bytes, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (span == MAP_FAILED) { close(fd); return false; }
+  void* a = mmap(span, g.bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED | MAP_POPULATE, fd, 0);
+  void* b = mmap((char*)span + g.bytes, g.bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, fd, 0);
+  if (a == MAP_FAILED || b == MAP_FAILED) { munmap(span, 2 * g.bytes); close(fd); return false; }
+  if (pin) {
+    // DMA only ever targets the first mapping; the second is read by the CPU alone
+    if (cudaHostRegister(span, g.bytes, cudaHostRegisterPortable) != cudaSuccess) {
+      cudaGetLastError();
+      munmap(span, 2 * g.bytes);
+      close(fd);
+      return false;
+    }
+    g.registered = true;
+  }
+  g.base = (char*)span;
+  g.fd = fd;
+  g.aliased = true;
+  return true;
+}
+
+int make_ring(Ring& g, int64_t n, bool pin, bool allow_alias) {
+  g.pitch = ((size_t)n * ROW_BYTES + PAGE - 1) / PAGE * PAGE;
+  g.bytes = g.pitch * SLOTS;
+  if (allow_alias && make_aliased(g, pin)) return 0;
+  // mirror fallback: 22 real slots
+  if (pin) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, 2 * g.bytes, cudaHostAllocPortable) != cudaSuccess) return failf("f16_hostwin: cudaHostAlloc of %zu bytes failed", 2 * g.bytes);
+    g.base = (char*)p;
+    g.pinned_alloc = true;
+  } else {
+    void* p = nullptr;
+    if (posix_memalign(&p, PAGE, 2 * g.bytes) != 0) return failf("f16_hostwin: out of host memory (%zu bytes)", 2 * g.bytes);
+    g.base = (char*)p;
+  }
+  memset(g.base, 0, 2 * g.bytes);
+  g.aliased = false;
+  return 0;
+}
+
+template <class T>
+int host_array(T** out, size_t count, bool pin, unsigned pin_flags = cudaHostAllocPortable) {
+  void* p = nullptr;
+  if (pin) {
+    if (cudaHostAlloc(&p, count * sizeof(T), pin_flags) != cudaSuccess) return failf("f16_hostwin: cudaHostAlloc of %zu bytes failed", count * sizeof(T));
+  } else {
+    p = calloc(count, sizeof(T));
+    if (!p) return failf("f16_hostwin: out of host memory");
+  }
+  *out = (T*)p;
+  return 0;
+}
+template <class T>
+void host_free(T* p, bool pin) {
+  if (!p) return;
+  if (pin) cudaFreeHost(p);
+  else free(p);
+}
+
+inline int first_slot_of(int head) { return (head + 2) % SLOTS; }            // = head - 9 (mod 11)
+inline int slot_back(int head, int k) { return (head - k + 2 * SLOTS) % SLOTS; }  // the slot written k steps ago
+
+// Everything a step does on the host once the done records are known; the newest slot (`head`) of every ring
+// may still be receiving its DMA - only the older slots are touched here.
+void post_step(f16_hostwin* w, int ring_now, const f16_done_record* recs, int64_t n_done, float* term) {
+  const int head = w->head;
+  // (1) finished envs of the previous step, for the ring that was not returned then: its window now is
+  //     slots head-9 .. head; slot head-1 already holds their reset frame, head-9 .. head-2 still hold history
+  if (!w->pending.empty()) {
+    const Fix* P = w->pending.data();
+    parallel_for((int64_t)w->pending.size(), 512, [=](int64_t b, int64_t e) {
+      for (int64_t i = b; i < e; ++i)
+        for (int k = 2; k <= ROWS - 1; ++k) w->write_row(ring_now, slot_back(head, k), P[i].env, P[i].frame);
+    });
+    w->pending.clear();
+  }
+  // (2) envs that finished in this step: terminal stack = the nine previous rows + the terminal frame
+  //     (dummy_vec_env.py:68), then those nine rows become copies of the reset frame (jsbsim_gym.py:325-329)
+  if (n_done > 0) {
+    parallel_for(n_done, 512, [=](int64_t b, int64_t e) {
+      for (int64_t j = b; j < e; ++j) {
+        const f16_done_record& rc = recs[j];
+        float* tj = term + (size_t)j * ROWS * FEAT;
+        if (j + 2 < e)   // the nine rows of an env are a slot pitch apart: one TLB and one cache miss each
+          for (int k = 1; k <= ROWS - 1; ++k) __builtin_prefetch(w->row(ring_now, slot_back(head, k), recs[j + 2].env), 1);
+        for (int k = ROWS - 1; k >= 1; --k) {
+          const int slot = slot_back(head, k);
+          memcpy(tj + (size_t)(ROWS - 1 - k) * FEAT, w->row(ring_now, slot, rc.env), ROW_BYTES);
+          w->write_row(ring_now, slot, rc.env, rc.reset_frame);
+        }
+        memcpy(tj + (size_t)(ROWS - 1) * FEAT, rc.terminal_frame, ROW_BYTES);
+      }
+    });
+    if (w->n_rings == 2) {
+      w->pending.resize((size_t)n_done);
+      for (int64_t j = 0; j < n_done; ++j) {
+        w->pending[(size_t)j].env = recs[j].env;
+        memcpy(w->pending[(size_t)j].frame, recs[j].reset_frame, ROW_BYTES);
+      }
+    }
+  }
+}
+
+void fill_result(f16_hostwin* w, int ring_now, int cur, int64_t n_done, const f16_done_record* recs, f16_hostwin_result* out) {
+  if (!out) return;
+  out->ring = ring_now;
+  out->first_slot = first_slot_of(w->head);
+  out->n_done = n_done;
+  out->reward = w->reward[cur];
+  out->done = w->done[cur];
+  out->truncated = w->trunc[cur];
+  out->records = recs;
+  out->terminal_obs = w->term[cur].data();
+}
+
+}  // namespace
+
+extern "C" {
+
+int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int flags) {
+  if (!out) return failf("f16_hostwin_create: out is NULL");
+  *out = nullptr;
+  if (n_envs <= 0) return failf("f16_hostwin_create: n_envs must be positive (got %lld)", (long long)n_envs);
+  if (n_rings != 1 && n_rings != 2) return failf("f16_hostwin_create: n_rings must be 1 or 2 (got %d)", n_rings);
+  f16_hostwin* w = new (std::nothrow) f16_hostwin;
+  if (!w) return failf("out of host memory");
+  w->n = n_envs;
+  w->n_rings = n_rings;
+  w->flags = flags;
+  w->pin = (flags & F16_HOSTWIN_PIN) != 0;
+  if (w->pin) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+      cudaGetLastError();
+      delete w;
+      return failf("f16_hostwin_create: F16_HOSTWIN_PIN needs a CUDA device; there is no CPU fallback for the env itself");
+    }
+  }
+  int rc = 0;
+  for (int r = 0; r < n_rings && !rc; ++r) rc = make_ring(w->ring[r], n_envs, w->pin, !(flags & F16_HOSTWIN_NO_ALIAS));
+  for (int b = 0; b < 2 && !rc; ++b) {
+    rc = host_array(&w->reward[b], (size_t)n_envs, w->pin);
+    if (!rc) rc = host_array(&w->done[b], (size_t)n_envs, w->pin);
+    if (!rc) rc = host_array(&w->trunc[b], (size_t)n_envs, w->pin);
+    if (!rc) rc = host_array(&w->actions[b], (size_t)n_envs * F16_ACTION_DIM, w->pin);
+  }
+  if (!rc && w->pin) {
+    rc = host_array(&w->records, (size_t)n_envs, true, cudaHostAllocPortable | cudaHostAllocMapped);
+    if (!rc) rc = host_array(&w->count_host, 1, true);
+    if (!rc && cudaMalloc(&w->count_dev, sizeof(int32_t)) != cudaSuccess) rc = failf("f16_hostwin_create: cudaMalloc failed");
+    if (!rc && cudaEventCreateWithFlags(&w->ev, cudaEventDisableTiming) != cudaSuccess) rc = failf("f16_hostwin_create: cudaEventCreate failed");
+  }
+  if (rc) { f16_hostwin_destroy(w); return rc; }
+  *out = w;
+  return 0;
+}
+
+int f16_hostwin_destroy(f16_hostwin_handle w) {
+  if (!w) return 0;
+  for (int r = 0; r < 2; ++r) free_ring(w->ring[r]);
+  for (int b = 0; b < 2; ++b) {
+    host_free(w->reward[b], w->pin);
+    host_free(w->done[b], w->pin);
+    host_free(w->trunc[b], w->pin);
+    host_free(w->actions[b], w->pin);
+  }
+  host_free(w->records, true && w->pin);
+  host_free(w->count_host, w->pin);
+  if (w->count_dev) cudaFree(w->count_dev);
+  if (w->ev) cudaEventDestroy(w->ev);
+  delete w;
+  return 0;
+}
+
+int f16_hostwin_layout(f16_hostwin_handle w, int ring, float** base, int64_t* slot_pitch_bytes, int32_t* n_slots, int32_t* aliased) {
+  if (!w) return failf("f16_hostwin_layout: NULL handle");
+  if (ring < 0 || ring >= w->n_rings) return failf("f16_hostwin_layout: ring %d out of range", ring);
+  if (base) *base = (float*)w->ring[ring].base;
+  if (slot_pitch_bytes) *slot_pitch_bytes = (int64_t)w->ring[ring].pitch;
+  if (n_slots) *n_slots = 2 * SLOTS;
+  if (aliased) *aliased = w->ring[ring].aliased ? 1 : 0;
+  return 0;
+}
+
+float* f16_hostwin_action_buffer(f16_hostwin_handle w, int which) { return (w && (which == 0 || which == 1)) ? w->actions[which] : nullptr; }
+
+int f16_hostwin_fill(f16_hostwin_handle w, const float* frames, f16_hostwin_result* out) {
+  if (!w || !frames) return failf("f16_hostwin_fill: NULL argument");
+  for (int r = 0; r < w->n_rings; ++r)
+    for (int s = 0; s < (w->ring[r].aliased ? SLOTS : 2 * SLOTS); ++s) memcpy(w->row(r, s, 0), frames, (size_t)w->n * ROW_BYTES);
+  w->head = SLOTS - 1;
+  w->t = 0;
+  w->pending.clear();
+  fill_result(w, 0, 0, 0, nullptr, out);
+  return 0;
+}
+
+int f16_hostwin_push(f16_hostwin_handle w, const float* frames, const float* reward, const uint8_t* done, const uint8_t* truncated,
+                     const f16_done_record* records, int64_t n_done, f16_hostwin_result* out) {
+  if (!w || !frames) return failf("f16_hostwin_push: NULL argument");
+  if (n_done < 0 || n_done > w->n || (n_done && !records)) return failf("f16_hostwin_push: bad done list");
+  for (int64_t j = 0; j < n_done; ++j)
+    if (records[j].env < 0 || records[j].env >= w->n) return failf("f16_hostwin_push: record %lld names env %d", (long long)j, records[j].env);
+  w->t += 1;
+  w->head = (w->head + 1) % SLOTS;
+  const int ring_now = w->n_rings == 2 ? (int)(w->t & 1) : 0, cur = (int)(w->t & 1);
+  for (int r = 0; r < w->n_rings; ++r) {
+    memcpy(w->row(r, w->head, 0), frames, (size_t)w->n * ROW_BYTES);
+    if (!w->ring[r].aliased) memcpy(w->row(r, w->head + SLOTS, 0), frames, (size_t)w->n * ROW_BYTES);
+  }
+  if (reward) memcpy(w->reward[cur], reward, (size_t)w->n * sizeof(float));
+  if (done) memcpy(w->done[cur], done, (size_t)w->n);
+  if (truncated) memcpy(w->trunc[cur], truncated, (size_t)w->n);
+  w->term[cur].resize((size_t)n_done * ROWS * FEAT);
+  post_step(w, ring_now, records, n_done, w->term[cur].data());
+  fill_result(w, ring_now, cur, n_done, records, out);
+  return 0;
+}
+
+#define CUDA_OK(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess) return failf("%s failed: %s", #call, cudaGetErrorString(_e));       \
+  } while (0)
+
+static int env_buffers(f16_hostwin* w, f16_handle env, float** obs_frame, float** reward, uint8_t** done, uint8_t** trunc, float** act_stage) {
+  if (!w) return failf("f16_hostwin: NULL handle");
+  if (!w->pin) return failf("f16_hostwin: this window was created without F16_HOSTWIN_PIN; only the host-only entry points work");
+  int64_t n = 0;
+  int dev = 0;
+  int rc = f16_internal_frame_buffers(env, &n, &dev, obs_frame, reward, done, trunc, act_stage);
+  if (rc) return rc;
+  if (n != w->n) return failf("f16_hostwin: the window holds %lld envs, the env handle %lld", (long long)w->n, (long long)n);
+  CUDA_OK(cudaSetDevice(dev));
+  w->device = dev;
+  return 0;
+}
+
+int f16_hostwin_reset(f16_hostwin_handle w, f16_handle env, void* stream, f16_hostwin_result* out) {
+  float *obs_frame, *reward, *act_stage;
+  uint8_t *done, *trunc;
+  int rc = env_buffers(w, env, &obs_frame, &reward, &done, &trunc, &act_stage);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = (size_t)w->n * ROW_BYTES;
+  for (int r = 0; r < w->n_rings; ++r)
+    for (int s = 0; s < (w->ring[r].aliased ? SLOTS : 2 * SLOTS); ++s)
+      CUDA_OK(cudaMemcpyAsync(w->row(r, s, 0), obs_frame, bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  w->head = SLOTS - 1;
+  w->t = 0;
+  w->pending.clear();
+  fill_result(w, 0, 0, 0, nullptr, out);
+  return 0;
+}
+
+int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_host, int auto_reset, void* stream,
+                     f16_hostwin_result* out) {
+  if (!actions_host) return failf("f16_hostwin_step: actions_host is NULL");
+  float *obs_frame, *reward, *act_stage;
+  uint8_t *done, *trunc;
+  int rc = env_buffers(w, env, &obs_frame, &reward, &done, &trunc, &act_stage);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)w->n;
+  f16_done_record* recs_dev = nullptr;
+  CUDA_OK(cudaHostGetDevicePointer((void**)&recs_dev, w->records, 0));
+  rc = f16_set_done_list(env, recs_dev, w->count_dev);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(act_stage, actions_host, n * F16_ACTION_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = f16_step(env, act_stage, auto_reset, stream);
+  if (rc) return rc;
+  w->t += 1;
+  w->head = (w->head + 1) % SLOTS;
+  const int ring_now = w->n_rings == 2 ? (int)(w->t & 1) : 0, cur = (int)(w->t & 1);
+  // the count first (4 bytes) so the host can start on the finished envs while the frames are still in flight
+  CUDA_OK(cudaMemcpyAsync(w->count_host, w->count_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaEventRecord(w->ev, st));
+  CUDA_OK(cudaMemcpyAsync(w->done[cur], done, n, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(w->trunc[cur], trunc, n, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaMemcpyAsync(w->reward[cur], reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  for (int r = 0; r < w->n_rings; ++r) {
+    // the returned ring first
+    const int rr = (r == 0) ? ring_now : 1 - ring_now;
+    CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head, 0), obs_frame, n * ROW_BYTES, cudaMemcpyDeviceToHost, st));
+    if (!w->ring[rr].aliased) CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head + SLOTS, 0), obs_frame, n * ROW_BYTES, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_OK(cudaEventSynchronize(w->ev));     // kernel finished: the records it wrote to mapped host memory are complete
+  const int64_t n_done = *w->count_host;
+  if (n_done < 0 || n_done > w->n) return failf("f16_hostwin_step: done count %lld out of range", (long long)n_done);
+  // without auto-reset a finished env keeps its history (its newest row is the terminal frame itself)
+  const int64_t n_fix = auto_reset ? n_done : 0;
+  w->term[cur].resize((size_t)n_fix * ROWS * FEAT);
+  post_step(w, ring_now, w->records, n_fix, w->term[cur].data());
+  CUDA_OK(cudaStreamSynchronize(st));
+  fill_result(w, ring_now, cur, n_done, w->records, out);
+  return 0;
+}
+
+}  // extern "C"

@@ -62,6 +62,25 @@ int f16_bind_ring(f16_handle h, void* state, float* obs_ring, float* reward, uin
 /* First row of the current observation window: 0 for the stacked layout, 1..10 for the ring layout. */
 int f16_obs_window(f16_handle h, int* first_row);
 
+/* Optional frame layout of the observations: the device keeps no history. obs_frame: N x 15 float; each step
+ * writes the newest frame of every env (the reset frame for an env that auto-reset in this step), 60 B per
+ * env-step - exactly the bytes that have to cross PCIe when the ten-frame windows live in host memory
+ * (f16_hostwin.h). Every env that finishes appends one f16_done_record to done_list (capacity N records, device
+ * or mapped host memory; order unspecified) and bumps *done_count (device memory, zeroed by f16_step before each
+ * launch); both may be NULL. f16_reset writes each masked env's reset frame to obs_frame. */
+typedef struct f16_done_record {
+  int32_t env;                 /* local env index */
+  int32_t flags;               /* bit 0 truncated (TimeLimit, jsbsim_gym.py:258-261), bit 1 crash, bit 2 goal reached */
+  float ep_return;             /* Monitor's info["episode"]["r"] (stable_baselines3/common/monitor.py:96-109) */
+  int32_t ep_len;              /* info["episode"]["l"] */
+  float terminal_frame[16];    /* newest row of info["terminal_observation"]; [15] is padding */
+  float reset_frame[16];       /* the frame the next episode starts from (all ten rows of the returned obs) */
+} f16_done_record;
+int f16_bind_frames(f16_handle h, void* state, float* obs_frame, float* reward, uint8_t* done, uint8_t* truncated,
+                    f16_done_record* done_list, int32_t* done_count);
+/* Re-point the done list of a frame-layout env (double buffering by the caller). */
+int f16_set_done_list(f16_handle h, f16_done_record* done_list, int32_t* done_count);
+
 /* JSBSimEnv.reset + PositionReward.reset (jsbsim_gym.py:289-331, 511-519) for every env whose mask
  * byte is non-zero (mask == NULL: all). goals: N x 3 float device pointer holding the goal of
  * every env (entries of unmasked envs are ignored), or NULL to sample distance~U[1000,10000) m,

@@ -6,10 +6,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def test_vecenv_api_contract(golden):
+HOST_OBS = [("window", 2), ("window", 1), ("copy", 2)]
+
+
+@pytest.mark.parametrize("host_obs,rings", HOST_OBS)
+def test_vecenv_api_contract(golden, host_obs, rings):
     from f16_jsb_b200 import F16VecEnv
     n = 8
-    env = F16VecEnv(n, mode="fp64", lazy_infos=False)
+    env = F16VecEnv(n, mode="fp64", lazy_infos=False, host_obs=host_obs, host_rings=rings)
     assert env.num_envs == n and env.observation_space.shape == (10, 15) and env.action_space.shape == (4,)
     assert env.get_attr("render_mode") == [None] * n and env.env_is_wrapped(object) == [False] * n
     env.seed(0)
@@ -23,15 +27,18 @@ def test_vecenv_api_contract(golden):
     assert obs2.shape == (n, 10, 15) and rew.shape == (n,) and rew.dtype == np.float32 and dones.dtype == bool
     assert len(infos) == n and infos[0]["TimeLimit.truncated"] is False
     assert np.allclose(obs2[0, -1], t["frames"][0], rtol=1e-6, atol=1e-6) and abs(rew[0] - t["rewards"][0]) < 2e-5
-    assert obs is not obs2 and np.array_equal(obs[0, 1:], obs2[0, :-1])      # ring of host buffers keeps `_last_obs` valid
+    if rings == 2:
+        assert obs is not obs2 and np.array_equal(obs[0, 1:], obs2[0, :-1])      # `_last_obs` stays valid across the next step
+        assert np.all(obs[0] == obs[0, 0])
     env.close()
 
 
-def test_vecenv_done_infos_match_dummy_vec_env_conventions(golden):
+@pytest.mark.parametrize("host_obs,rings", HOST_OBS)
+def test_vecenv_done_infos_match_dummy_vec_env_conventions(golden, host_obs, rings):
     from f16_jsb_b200 import F16VecEnv
     t = golden["gentle1"]
     n = 70
-    env = F16VecEnv(n, mode="fp64", seed=5)
+    env = F16VecEnv(n, mode="fp64", seed=5, host_obs=host_obs, host_rings=rings)
     env.seed(11)         # env 0 gets the golden goal of seed 11 (trace gentle1)
     env.reset()
     for k in range(len(t["actions"])):
@@ -43,6 +50,45 @@ def test_vecenv_done_infos_match_dummy_vec_env_conventions(golden):
     assert np.all(obs[0] == obs[0, 0])                       # returned obs is the reset observation
     assert sum(1 for i in infos if i.get("episode")) == int(dones.sum())
     env.close()
+
+
+@pytest.mark.parametrize("rings", [1, 2])
+def test_window_mode_returns_what_copy_mode_returns(rings):
+    """Host-resident windows (60 B per env-step over PCIe) against the device-side stacks copied out whole
+    (600 B): identical observations, rewards, flags, terminal observations and episode statistics over a
+    rollout long enough for hundreds of crashes and auto-resets."""
+    from f16_jsb_b200 import F16VecEnv
+    n, steps = 4096, 260
+    a_env = F16VecEnv(n, mode="fp32", seed=3, host_obs="window", host_rings=rings)
+    b_env = F16VecEnv(n, mode="fp32", seed=3, host_obs="copy")
+    a_env.seed(100)
+    b_env.seed(100)
+    oa, ob = a_env.reset(), b_env.reset()
+    assert np.array_equal(oa, ob)
+    rng = np.random.default_rng(0)
+    finished = 0
+    prev = None
+    for k in range(steps):
+        act = rng.uniform([-1, -1, -1, 0], [1, 1, 1, 1], size=(n, 4)).astype(np.float32)
+        buf = a_env.action_buffer() if k % 2 else act          # pinned staging and plain arrays both work
+        if k % 2:
+            buf[...] = act
+        oa, ra, da, ia = a_env.step(buf)
+        ob, rb, db, ib = b_env.step(act)
+        assert np.array_equal(da, db) and np.array_equal(ra, rb), k
+        assert np.array_equal(oa, ob), k
+        if rings == 2 and prev is not None:
+            assert np.array_equal(prev[0], prev[1]), k          # last step's array is still intact
+        prev = (oa, ob.copy())
+        for i in np.flatnonzero(da):
+            assert np.array_equal(ia[i]["terminal_observation"], ib[i]["terminal_observation"]), (k, i)
+            assert ia[i]["TimeLimit.truncated"] == ib[i]["TimeLimit.truncated"]
+            assert ia[i]["episode"]["l"] == ib[i]["episode"]["l"] and ia[i]["episode"]["r"] == ib[i]["episode"]["r"]
+            finished += 1
+        assert ia[int(np.flatnonzero(~da)[0])] == {"TimeLimit.truncated": False}
+    assert finished > 100
+    a_env.close()
+    b_env.close()
 
 
 def test_single_env_gymnasium_adapter_matches_golden(golden):
@@ -61,7 +107,7 @@ def test_single_env_gymnasium_adapter_matches_golden(golden):
 
 def test_torch_fast_path_is_device_resident():
     from f16_jsb_b200 import F16VecEnv
-    env = F16VecEnv(256, mode="fp32")
+    env = F16VecEnv(256, mode="fp32", host_obs="copy")
     obs = env.reset_torch()
     a = torch.rand((256, 4), device="cuda") * 2 - 1
     o, r, d, tr = env.step_torch(a)

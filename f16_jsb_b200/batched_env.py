@@ -37,7 +37,8 @@ class F16BatchedEnv:
     """
 
     def __init__(self, num_envs: int, device=None, mode: str = "fp32", seed: int = 0,
-                 with_terminal_obs: bool = True, env_id_base: int = 0, obs_layout: str = "stacked"):
+                 with_terminal_obs: bool = True, env_id_base: int = 0, obs_layout: str = "stacked",
+                 done_list: bool = False):
         if not torch.cuda.is_available():
             raise _lib.F16Error("F16BatchedEnv needs a CUDA device: the F-16 env has no CPU fallback")
         self.lib = _lib.load()
@@ -71,9 +72,15 @@ class F16BatchedEnv:
                                  if with_terminal_obs else None)
             self.ep_return = torch.zeros(n, dtype=torch.float32, device=self.device)
             self.ep_len = torch.zeros(n, dtype=torch.int32, device=self.device)
+        self.done_records = self.done_count = None
         if obs_layout == "frame":
+            if done_list:
+                # f16_done_record[N] (36 words each: env, flags, ep_return, ep_len, terminal frame[16], reset frame[16])
+                with torch.cuda.device(self.device):
+                    self.done_records = torch.zeros((n, 36), dtype=torch.int32, device=self.device)
+                    self.done_count = torch.zeros(1, dtype=torch.int32, device=self.device)
             _lib.check(self.lib.f16_bind_frames(h, _ptr(self.state), _ptr(self._obs_buf), _ptr(self.reward), _ptr(self.done),
-                                                _ptr(self.truncated), None, None), "f16_bind_frames")
+                                                _ptr(self.truncated), _ptr(self.done_records), _ptr(self.done_count)), "f16_bind_frames")
         else:
             bind = self.lib.f16_bind_ring if obs_layout == "ring" else self.lib.f16_bind
             _lib.check(bind(h, _ptr(self.state), _ptr(self._obs_buf), _ptr(self.reward), _ptr(self.done),

@@ -9,6 +9,18 @@ pytestmark = pytest.mark.gpu
 HOST_OBS = [("window", 2), ("window", 1), ("copy", 2)]
 
 
+def _reset_with_near_goals(venv, n, seed):
+    """Goals 150..900 m straight ahead at the start altitude: reached (+10, terminated) between steps ~10 and
+    ~100, so terminal observations and auto-resets occur all along a short run."""
+    g = np.zeros((n, 3), np.float32)
+    g[:, 0] = np.random.default_rng(seed).uniform(150, 900, size=n)
+    g[:, 2] = 1524.0
+    venv.env.reset(goals=torch.from_numpy(g).cuda())
+    if venv._win is not None:
+        return venv._win.reset(venv.env, venv.env._stream()).obs
+    return venv.env.obs.cpu().numpy()
+
+
 @pytest.mark.parametrize("host_obs,rings", HOST_OBS)
 def test_vecenv_api_contract(golden, host_obs, rings):
     from f16_jsb_b200 import F16VecEnv
@@ -55,21 +67,21 @@ def test_vecenv_done_infos_match_dummy_vec_env_conventions(golden, host_obs, rin
 @pytest.mark.parametrize("rings", [1, 2])
 def test_window_mode_returns_what_copy_mode_returns(rings):
     """Host-resident windows (60 B per env-step over PCIe) against the device-side stacks copied out whole
-    (600 B): identical observations, rewards, flags, terminal observations and episode statistics over a
-    rollout long enough for hundreds of crashes and auto-resets."""
+    (600 B): identical observations, rewards, flags, terminal observations and episode statistics across
+    crashes and auto-resets. FP64 mode: there the two layouts' kernel instantiations agree bit for bit (the
+    float instantiations contract a few multiply-adds differently, see test_ring_layout_is_value_identical_to_stacked)."""
     from f16_jsb_b200 import F16VecEnv
-    n, steps = 4096, 260
-    a_env = F16VecEnv(n, mode="fp32", seed=3, host_obs="window", host_rings=rings)
-    b_env = F16VecEnv(n, mode="fp32", seed=3, host_obs="copy")
-    a_env.seed(100)
-    b_env.seed(100)
-    oa, ob = a_env.reset(), b_env.reset()
+    n, steps = 2048, 120
+    a_env = F16VecEnv(n, mode="fp64", seed=3, host_obs="window", host_rings=rings)
+    b_env = F16VecEnv(n, mode="fp64", seed=3, host_obs="copy")
+    oa, ob = _reset_with_near_goals(a_env, n, 5), _reset_with_near_goals(b_env, n, 5)
     assert np.array_equal(oa, ob)
     rng = np.random.default_rng(0)
     finished = 0
     prev = None
     for k in range(steps):
-        act = rng.uniform([-1, -1, -1, 0], [1, 1, 1, 1], size=(n, 4)).astype(np.float32)
+        act = (rng.uniform([-1, -1, -1, 0], [1, 1, 1, 1], size=(n, 4)) * 0.1).astype(np.float32)
+        act[:, 3] = 0.8
         buf = a_env.action_buffer() if k % 2 else act          # pinned staging and plain arrays both work
         if k % 2:
             buf[...] = act
@@ -89,6 +101,55 @@ def test_window_mode_returns_what_copy_mode_returns(rings):
     assert finished > 100
     a_env.close()
     b_env.close()
+
+
+def test_window_mode_fp32_is_the_deque_of_the_frame_layout():
+    """FP32 mode, 150 steps over 4 096 envs that reach their goals all along the run: F16VecEnv's host windows against a
+    deque model (jsbsim_gym.py:150,235,325-329; dummy_vec_env.py:63-72) fed with the device outputs of a second
+    env in the same frame layout - the same kernel instantiation, so everything is bit-exact."""
+    from collections import deque
+
+    from f16_jsb_b200 import F16BatchedEnv, F16VecEnv
+    n, steps = 4096, 150
+    venv = F16VecEnv(n, mode="fp32", seed=7, host_obs="window", host_rings=2)
+    ref = F16BatchedEnv(n, mode="fp32", seed=7, obs_layout="frame", done_list=True)
+    g = np.zeros((n, 3), np.float32)
+    g[:, 0] = np.random.default_rng(5).uniform(150, 900, size=n)
+    g[:, 2] = 1524.0
+    obs = _reset_with_near_goals(venv, n, 5)
+    f0 = ref.reset(goals=torch.from_numpy(g).cuda()).cpu().numpy()
+    stacks = [deque([f0[i]] * 10, maxlen=10) for i in range(n)]
+    assert np.array_equal(obs, np.array([np.array(d) for d in stacks]))
+    rng = np.random.default_rng(1)
+    finished = 0
+    for k in range(steps):
+        act = (rng.uniform([-1, -1, -1, 0], [1, 1, 1, 1], size=(n, 4)) * 0.1).astype(np.float32)
+        act[:, 3] = 0.8
+        obs, rew, dones, infos = venv.step(act)
+        fr, rw, dn, tr = ref.step(torch.from_numpy(act).cuda(), auto_reset=True)
+        fr, rw, dn, tr = fr.cpu().numpy(), rw.cpu().numpy(), dn.cpu().numpy().astype(bool), tr.cpu().numpy().astype(bool)
+        cnt = int(ref.done_count.item())
+        recs = ref.done_records[:cnt].cpu().numpy()
+        assert cnt == int(dn.sum()) and np.array_equal(dones, dn) and np.array_equal(rew, rw)
+        by_env = {int(r[0]): r for r in recs}
+        for i in range(n):
+            if dn[i]:
+                r = by_env[i]
+                tframe, rframe = r[4:19].view(np.float32), r[20:35].view(np.float32)
+                assert np.array_equal(rframe, fr[i])                    # the device emits the reset frame for a finished env
+                term = np.array(list(stacks[i])[1:] + [tframe])
+                assert np.array_equal(infos[i]["terminal_observation"], term), (k, i)
+                assert infos[i]["TimeLimit.truncated"] == bool(tr[i]) == bool(r[1] & 1)
+                assert infos[i]["episode"]["l"] == int(r[3]) and infos[i]["episode"]["r"] == float(r[2:3].view(np.float32)[0])
+                stacks[i] = deque([fr[i]] * 10, maxlen=10)
+                finished += 1
+            else:
+                stacks[i].append(fr[i])
+        if k % 10 == 0 or k == steps - 1:
+            assert np.array_equal(obs, np.array([np.array(d) for d in stacks])), k
+    assert finished > 300
+    venv.close()
+    ref.close()
 
 
 def test_single_env_gymnasium_adapter_matches_golden(golden):

@@ -14,7 +14,10 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -56,22 +59,79 @@ struct Fix {
   float frame[FEAT];
 };
 
-// run f(begin, end) over [0, n) on up to 16 host threads when there is enough work to pay for them
-template <class F>
-void parallel_for(int64_t n, int64_t grain, F f) {
-  unsigned hw = std::thread::hardware_concurrency();
-  int64_t t = std::min<int64_t>(std::min<int64_t>(hw ? hw : 1, 16), n / std::max<int64_t>(grain, 1));
-  if (t <= 1) { f((int64_t)0, n); return; }
-  std::vector<std::thread> th;
-  th.reserve((size_t)t - 1);
-  const int64_t chunk = (n + t - 1) / t;
-  for (int64_t i = 1; i < t; ++i) {
-    const int64_t b = i * chunk, e = std::min(n, b + chunk);
-    if (b < e) th.emplace_back([=] { f(b, e); });
+// A few persistent host threads: they run the fix-ups of finished envs while the frame DMA is in flight and
+// carry the newest slot over to the second ring in the background between two steps.
+class Pool {
+ public:
+  explicit Pool(int n) {
+    for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { worker(i); });
   }
-  f((int64_t)0, std::min(n, chunk));
-  for (auto& x : th) x.join();
-}
+  ~Pool() {
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_done_.wait(lk, [this] { return remaining_ == 0; });
+      stop_ = true;
+    }
+    cv_work_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int size() const { return (int)th_.size(); }
+  // every worker runs job(worker index, worker count); returns at once
+  void launch(std::function<void(int, int)> job) {
+    wait();
+    if (th_.empty()) { job(0, 1); return; }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = std::move(job);
+      remaining_ = (int)th_.size();
+      ++gen_;
+    }
+    cv_work_.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [this] { return remaining_ == 0; });
+  }
+  // f(begin, end) over [0, n), split over the workers when there is enough work to pay for the hand-off
+  template <class F>
+  void parallel_for(int64_t n, int64_t grain, F f) {
+    wait();
+    if (n <= 0) return;
+    if (th_.empty() || n < 2 * grain) { f((int64_t)0, n); return; }
+    launch([=](int i, int k) {
+      const int64_t chunk = (n + k - 1) / k, b = i * chunk, e = std::min(n, b + chunk);
+      if (b < e) f(b, e);
+    });
+    wait();
+  }
+
+ private:
+  void worker(int i) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<void(int, int)> job;
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_work_.wait(lk, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+        job = job_;
+      }
+      job(i, (int)th_.size());
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--remaining_ == 0) cv_done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_work_, cv_done_;
+  std::function<void(int, int)> job_;
+  uint64_t gen_ = 0;
+  int remaining_ = 0;
+  bool stop_ = false;
+};
 
 }  // namespace
 
@@ -93,6 +153,7 @@ struct f16_hostwin {
   std::vector<float> term[2];
   std::vector<Fix> pending;              // finished envs of the previous step, still to be applied to the other ring
   int device = -1;
+  Pool* pool = nullptr;
 
   float* row(int r, int slot, int64_t env) const { return (float*)(ring[r].base + (size_t)slot * ring[r].pitch + (size_t)env * ROW_BYTES); }
   void write_row(int r, int slot, int64_t env, const float* f) const {
@@ -186,11 +247,12 @@ inline int slot_back(int head, int k) { return (head - k + 2 * SLOTS) % SLOTS; }
 // may still be receiving its DMA - only the older slots are touched here.
 void post_step(f16_hostwin* w, int ring_now, const f16_done_record* recs, int64_t n_done, float* term) {
   const int head = w->head;
+  w->pool->wait();   // the previous step's carry-over into this ring (slot head-1) has to be complete
   // (1) finished envs of the previous step, for the ring that was not returned then: its window now is
   //     slots head-9 .. head; slot head-1 already holds their reset frame, head-9 .. head-2 still hold history
   if (!w->pending.empty()) {
     const Fix* P = w->pending.data();
-    parallel_for((int64_t)w->pending.size(), 512, [=](int64_t b, int64_t e) {
+    w->pool->parallel_for((int64_t)w->pending.size(), 512, [=](int64_t b, int64_t e) {
       for (int64_t i = b; i < e; ++i)
         for (int k = 2; k <= ROWS - 1; ++k) w->write_row(ring_now, slot_back(head, k), P[i].env, P[i].frame);
     });
@@ -199,7 +261,7 @@ void post_step(f16_hostwin* w, int ring_now, const f16_done_record* recs, int64_
   // (2) envs that finished in this step: terminal stack = the nine previous rows + the terminal frame
   //     (dummy_vec_env.py:68), then those nine rows become copies of the reset frame (jsbsim_gym.py:325-329)
   if (n_done > 0) {
-    parallel_for(n_done, 512, [=](int64_t b, int64_t e) {
+    w->pool->parallel_for(n_done, 512, [=](int64_t b, int64_t e) {
       for (int64_t j = b; j < e; ++j) {
         const f16_done_record& rc = recs[j];
         float* tj = term + (size_t)j * ROWS * FEAT;
@@ -221,6 +283,29 @@ void post_step(f16_hostwin* w, int ring_now, const f16_done_record* recs, int64_
       }
     }
   }
+}
+
+// Two rings: the frames of this step were DMA-ed into the returned ring only; host threads carry them over to
+// the other ring in the background, between this step and the next (which returns that ring).
+void carry_over(f16_hostwin* w, int ring_src) {
+  if (w->n_rings != 2 || (w->flags & F16_HOSTWIN_DMA_BOTH)) return;
+  const int ring_dst = 1 - ring_src;
+  const size_t bytes = (size_t)w->n * ROW_BYTES;
+  const char* src = (const char*)w->row(ring_src, w->head, 0);
+  char* dst = (char*)w->row(ring_dst, w->head, 0);
+  char* dst2 = w->ring[ring_dst].aliased ? nullptr : (char*)w->row(ring_dst, w->head + SLOTS, 0);
+  if (bytes < ((size_t)1 << 20) || w->pool->size() == 0) {
+    memcpy(dst, src, bytes);
+    if (dst2) memcpy(dst2, src, bytes);
+    return;
+  }
+  w->pool->launch([=](int i, int k) {
+    const size_t chunk = ((bytes + (size_t)k - 1) / (size_t)k + PAGE - 1) / PAGE * PAGE, b = (size_t)i * chunk;
+    if (b >= bytes) return;
+    const size_t len = std::min(chunk, bytes - b);
+    memcpy(dst + b, src + b, len);
+    if (dst2) memcpy(dst2 + b, src + b, len);
+  });
 }
 
 void fill_result(f16_hostwin* w, int ring_now, int cur, int64_t n_done, const f16_done_record* recs, f16_hostwin_result* out) {
@@ -258,6 +343,11 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
       return failf("f16_hostwin_create: F16_HOSTWIN_PIN needs a CUDA device; there is no CPU fallback for the env itself");
     }
   }
+  {
+    const unsigned hw = std::thread::hardware_concurrency();
+    w->pool = new (std::nothrow) Pool((int)std::max(1u, std::min(8u, hw > 1 ? hw - 1 : 1u)));
+    if (!w->pool) { delete w; return failf("out of host memory"); }
+  }
   int rc = 0;
   for (int r = 0; r < n_rings && !rc; ++r) rc = make_ring(w->ring[r], n_envs, w->pin, !(flags & F16_HOSTWIN_NO_ALIAS));
   for (int b = 0; b < 2 && !rc; ++b) {
@@ -279,6 +369,8 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
 
 int f16_hostwin_destroy(f16_hostwin_handle w) {
   if (!w) return 0;
+  delete w->pool;      // waits for a carry-over in flight
+  w->pool = nullptr;
   for (int r = 0; r < 2; ++r) free_ring(w->ring[r]);
   for (int b = 0; b < 2; ++b) {
     host_free(w->reward[b], w->pin);
@@ -308,6 +400,7 @@ float* f16_hostwin_action_buffer(f16_hostwin_handle w, int which) { return (w &&
 
 int f16_hostwin_fill(f16_hostwin_handle w, const float* frames, f16_hostwin_result* out) {
   if (!w || !frames) return failf("f16_hostwin_fill: NULL argument");
+  w->pool->wait();
   for (int r = 0; r < w->n_rings; ++r)
     for (int s = 0; s < (w->ring[r].aliased ? SLOTS : 2 * SLOTS); ++s) memcpy(w->row(r, s, 0), frames, (size_t)w->n * ROW_BYTES);
   w->head = SLOTS - 1;
@@ -327,6 +420,7 @@ int f16_hostwin_push(f16_hostwin_handle w, const float* frames, const float* rew
   w->head = (w->head + 1) % SLOTS;
   const int ring_now = w->n_rings == 2 ? (int)(w->t & 1) : 0, cur = (int)(w->t & 1);
   for (int r = 0; r < w->n_rings; ++r) {
+    if (r != ring_now && !(w->flags & F16_HOSTWIN_DMA_BOTH)) continue;      // carried over below
     memcpy(w->row(r, w->head, 0), frames, (size_t)w->n * ROW_BYTES);
     if (!w->ring[r].aliased) memcpy(w->row(r, w->head + SLOTS, 0), frames, (size_t)w->n * ROW_BYTES);
   }
@@ -335,6 +429,7 @@ int f16_hostwin_push(f16_hostwin_handle w, const float* frames, const float* rew
   if (truncated) memcpy(w->trunc[cur], truncated, (size_t)w->n);
   w->term[cur].resize((size_t)n_done * ROWS * FEAT);
   post_step(w, ring_now, records, n_done, w->term[cur].data());
+  carry_over(w, ring_now);
   fill_result(w, ring_now, cur, n_done, records, out);
   return 0;
 }
@@ -365,6 +460,7 @@ int f16_hostwin_reset(f16_hostwin_handle w, f16_handle env, void* stream, f16_ho
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bytes = (size_t)w->n * ROW_BYTES;
+  w->pool->wait();
   for (int r = 0; r < w->n_rings; ++r)
     for (int s = 0; s < (w->ring[r].aliased ? SLOTS : 2 * SLOTS); ++s)
       CUDA_OK(cudaMemcpyAsync(w->row(r, s, 0), obs_frame, bytes, cudaMemcpyDeviceToHost, st));
@@ -404,6 +500,7 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
   for (int r = 0; r < w->n_rings; ++r) {
     // the returned ring first
     const int rr = (r == 0) ? ring_now : 1 - ring_now;
+    if (rr != ring_now && !(w->flags & F16_HOSTWIN_DMA_BOTH)) continue;     // carried over by host threads after the sync
     CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head, 0), obs_frame, n * ROW_BYTES, cudaMemcpyDeviceToHost, st));
     if (!w->ring[rr].aliased) CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head + SLOTS, 0), obs_frame, n * ROW_BYTES, cudaMemcpyDeviceToHost, st));
   }
@@ -415,6 +512,7 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
   w->term[cur].resize((size_t)n_fix * ROWS * FEAT);
   post_step(w, ring_now, w->records, n_fix, w->term[cur].data());
   CUDA_OK(cudaStreamSynchronize(st));
+  carry_over(w, ring_now);
   fill_result(w, ring_now, cur, n_done, w->records, out);
   return 0;
 }

@@ -21,8 +21,10 @@
  * host threads while the frame DMA is still in flight.
  *
  * n_rings = 2 alternates two rings so that the array returned by step t is not written again before step
- * t + 2 (SB3 reads `_last_obs` after the next env.step, stable_baselines3/common/on_policy_algorithm.py:247);
- * n_rings = 1 halves the PCIe traffic and keeps an array valid only until the next step.
+ * t + 2 (SB3 reads `_last_obs` after the next env.step, stable_baselines3/common/on_policy_algorithm.py:247).
+ * The frames still cross PCIe once: they land in the ring being returned and a few host threads copy the slot
+ * into the other ring in the background, before the next step returns that one. n_rings = 1 keeps an array
+ * valid only until the next step.
  */
 #ifndef F16_HOSTWIN_H
 #define F16_HOSTWIN_H
@@ -39,7 +41,9 @@ typedef struct f16_hostwin* f16_hostwin_handle;
 
 enum { F16_HOSTWIN_SLOTS = 11 };
 enum { F16_HOSTWIN_PIN = 1,        /* pin the rings for CUDA DMA (needs a CUDA device) */
-       F16_HOSTWIN_NO_ALIAS = 2 }; /* skip the double mapping, use the mirrored 22-slot ring */
+       F16_HOSTWIN_NO_ALIAS = 2,   /* skip the double mapping, use the mirrored 22-slot ring */
+       F16_HOSTWIN_DMA_BOTH = 4 }; /* two rings: DMA every frame into both (default: DMA into the returned ring and let
+                                      host threads carry the slot over to the other ring before the next step) */
 
 typedef struct f16_hostwin_result {
   int32_t ring;                    /* which ring holds this step's window */

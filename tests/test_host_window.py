@@ -66,6 +66,38 @@ def test_windows_match_the_deque_model(n, n_rings, alias):
     w.close()
 
 
+@pytest.mark.parametrize("alias", [True, False])
+def test_carry_over_between_rings_on_host_threads(alias):
+    """Slots above 1 MB are carried over to the second ring by the library's worker threads between two
+    steps; a vectorised stack model checks every returned window and that the previous one stays intact."""
+    n = 20000
+    rng = np.random.default_rng(3)
+    w = HostWindow(n, n_rings=2, pin=False, alias=alias)
+    f0 = rng.normal(size=(n, 15)).astype(np.float32)
+    expected = np.repeat(f0[:, None, :], 10, axis=1)
+    res = w.fill(f0)
+    prev_view, prev_expected = res.obs, expected.copy()
+    for t in range(25):
+        frames = rng.normal(size=(n, 15)).astype(np.float32)
+        done = rng.random(n) < 0.05
+        reset_frames = rng.normal(size=(n, 15)).astype(np.float32)
+        idx = np.flatnonzero(done)
+        rec = np.zeros(idx.size, dtype=RECORD_DTYPE)
+        rec["env"] = idx
+        rec["terminal_frame"][:, :15] = frames[idx]
+        rec["reset_frame"][:, :15] = reset_frames[idx]
+        sent = frames.copy()
+        sent[idx] = reset_frames[idx]
+        res = w.push(sent, None, done.astype(np.uint8), None, rec)
+        expected = np.concatenate([expected[:, 1:], frames[:, None, :]], axis=1)
+        np.testing.assert_array_equal(res.terminal_obs, expected[res.records["env"]])
+        expected[idx] = reset_frames[idx][:, None, :]
+        np.testing.assert_array_equal(res.obs, expected)
+        np.testing.assert_array_equal(prev_view, prev_expected)
+        prev_view, prev_expected = res.obs, expected.copy()
+    w.close()
+
+
 def test_window_is_a_view_not_a_copy():
     w = HostWindow(64, n_rings=1, pin=False)
     res = w.fill(np.zeros((64, 15), np.float32))

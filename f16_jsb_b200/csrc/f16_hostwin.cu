@@ -5,6 +5,7 @@
 // host memory whose pages are mapped twice back to back, so that the reference's (N,10,15) stacked observation
 // (jsbsim_gym/jsbsim_gym.py:150,235,263) is a strided view of the ring and never has to be assembled.
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 #include <sys/mman.h>
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -153,7 +154,8 @@ struct f16_hostwin {
   std::vector<float> term[2];
   std::vector<Fix> pending;              // finished envs of the previous step, still to be applied to the other ring
   int device = -1;
-  Pool* pool = nullptr;
+  Pool* pool = nullptr;      // fix-ups of finished envs
+  Pool* copier = nullptr;    // carry-over of the newest slot to the other ring
 
   float* row(int r, int slot, int64_t env) const { return (float*)(ring[r].base + (size_t)slot * ring[r].pitch + (size_t)env * ROW_BYTES); }
   void write_row(int r, int slot, int64_t env, const float* f) const {
@@ -243,13 +245,14 @@ void host_free(T* p, bool pin) {
 inline int first_slot_of(int head) { return (head + 2) % SLOTS; }            // = head - 9 (mod 11)
 inline int slot_back(int head, int k) { return (head - k + 2 * SLOTS) % SLOTS; }  // the slot written k steps ago
 
-// Everything a step does on the host once the done records are known; the newest slot (`head`) of every ring
-// may still be receiving its DMA - only the older slots are touched here.
-void post_step(f16_hostwin* w, int ring_now, const f16_done_record* recs, int64_t n_done, float* term) {
+// The fix-ups of a step, in two phases. `early` runs once the done records are known, while the newest slot
+// (`head`) of the returned ring is still receiving its DMA and - with two rings - slot head-1 may still be
+// receiving the previous step's carry-over: it only touches slots head-9 .. head-2. `late` runs after both
+// have landed and handles slot head-1.
+void fix_early(f16_hostwin* w, int ring_now, const f16_done_record* recs, int64_t n_done, float* term) {
   const int head = w->head;
-  w->pool->wait();   // the previous step's carry-over into this ring (slot head-1) has to be complete
   // (1) finished envs of the previous step, for the ring that was not returned then: its window now is
-  //     slots head-9 .. head; slot head-1 already holds their reset frame, head-9 .. head-2 still hold history
+  //     slots head-9 .. head; slot head-1 holds (or is about to receive) their reset frame, the rest is history
   if (!w->pending.empty()) {
     const Fix* P = w->pending.data();
     w->pool->parallel_for((int64_t)w->pending.size(), 512, [=](int64_t b, int64_t e) {
@@ -265,9 +268,9 @@ void post_step(f16_hostwin* w, int ring_now, const f16_done_record* recs, int64_
       for (int64_t j = b; j < e; ++j) {
         const f16_done_record& rc = recs[j];
         float* tj = term + (size_t)j * ROWS * FEAT;
-        if (j + 2 < e)   // the nine rows of an env are a slot pitch apart: one TLB and one cache miss each
-          for (int k = 1; k <= ROWS - 1; ++k) __builtin_prefetch(w->row(ring_now, slot_back(head, k), recs[j + 2].env), 1);
-        for (int k = ROWS - 1; k >= 1; --k) {
+        if (j + 2 < e)   // the rows of an env are a slot pitch apart: one TLB and one cache miss each
+          for (int k = 2; k <= ROWS - 1; ++k) __builtin_prefetch(w->row(ring_now, slot_back(head, k), recs[j + 2].env), 1);
+        for (int k = ROWS - 1; k >= 2; --k) {
           const int slot = slot_back(head, k);
           memcpy(tj + (size_t)(ROWS - 1 - k) * FEAT, w->row(ring_now, slot, rc.env), ROW_BYTES);
           w->write_row(ring_now, slot, rc.env, rc.reset_frame);
@@ -284,6 +287,34 @@ void post_step(f16_hostwin* w, int ring_now, const f16_done_record* recs, int64_
     }
   }
 }
+void fix_late(f16_hostwin* w, int ring_now, const f16_done_record* recs, int64_t n_done, float* term) {
+  const int slot = slot_back(w->head, 1);
+  w->copier->wait();   // the previous step's carry-over into this ring (slot head-1) is complete from here on
+  if (n_done <= 0) return;
+  w->pool->parallel_for(n_done, 1024, [=](int64_t b, int64_t e) {
+    for (int64_t j = b; j < e; ++j) {
+      if (j + 4 < e) __builtin_prefetch(w->row(ring_now, slot, recs[j + 4].env), 1);
+      memcpy(term + ((size_t)j * ROWS + (ROWS - 2)) * FEAT, w->row(ring_now, slot, recs[j].env), ROW_BYTES);
+      w->write_row(ring_now, slot, recs[j].env, recs[j].reset_frame);
+    }
+  });
+}
+
+// streaming copy (non-temporal stores: the destination slot is not read again before the next step)
+void stream_copy(char* dst, const char* src, size_t len) {
+#if defined(__SSE2__)
+  if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+    const __m128i* s = (const __m128i*)src;
+    __m128i* d = (__m128i*)dst;
+    const size_t n16 = len / 16;
+    for (size_t i = 0; i < n16; ++i) _mm_stream_si128(d + i, _mm_load_si128(s + i));
+    _mm_sfence();
+    if (len & 15) memcpy(dst + n16 * 16, src + n16 * 16, len & 15);
+    return;
+  }
+#endif
+  memcpy(dst, src, len);
+}
 
 // Two rings: the frames of this step were DMA-ed into the returned ring only; host threads carry them over to
 // the other ring in the background, between this step and the next (which returns that ring).
@@ -294,17 +325,17 @@ void carry_over(f16_hostwin* w, int ring_src) {
   const char* src = (const char*)w->row(ring_src, w->head, 0);
   char* dst = (char*)w->row(ring_dst, w->head, 0);
   char* dst2 = w->ring[ring_dst].aliased ? nullptr : (char*)w->row(ring_dst, w->head + SLOTS, 0);
-  if (bytes < ((size_t)1 << 20) || w->pool->size() == 0) {
+  if (bytes < ((size_t)1 << 20) || w->copier->size() == 0) {
     memcpy(dst, src, bytes);
     if (dst2) memcpy(dst2, src, bytes);
     return;
   }
-  w->pool->launch([=](int i, int k) {
+  w->copier->launch([=](int i, int k) {
     const size_t chunk = ((bytes + (size_t)k - 1) / (size_t)k + PAGE - 1) / PAGE * PAGE, b = (size_t)i * chunk;
     if (b >= bytes) return;
     const size_t len = std::min(chunk, bytes - b);
-    memcpy(dst + b, src + b, len);
-    if (dst2) memcpy(dst2 + b, src + b, len);
+    stream_copy(dst + b, src + b, len);
+    if (dst2) stream_copy(dst2 + b, src + b, len);
   });
 }
 
@@ -345,8 +376,10 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
   }
   {
     const unsigned hw = std::thread::hardware_concurrency();
-    w->pool = new (std::nothrow) Pool((int)std::max(1u, std::min(8u, hw > 1 ? hw - 1 : 1u)));
-    if (!w->pool) { delete w; return failf("out of host memory"); }
+    const int nt = (int)std::max(1u, std::min(4u, hw > 2 ? (hw - 1) / 2 : 1u));
+    w->pool = new (std::nothrow) Pool(nt);
+    w->copier = new (std::nothrow) Pool(n_rings == 2 ? nt : 0);
+    if (!w->pool || !w->copier) { delete w->pool; delete w->copier; delete w; return failf("out of host memory"); }
   }
   int rc = 0;
   for (int r = 0; r < n_rings && !rc; ++r) rc = make_ring(w->ring[r], n_envs, w->pin, !(flags & F16_HOSTWIN_NO_ALIAS));
@@ -369,8 +402,9 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
 
 int f16_hostwin_destroy(f16_hostwin_handle w) {
   if (!w) return 0;
-  delete w->pool;      // waits for a carry-over in flight
-  w->pool = nullptr;
+  delete w->copier;    // waits for a carry-over in flight
+  delete w->pool;
+  w->pool = w->copier = nullptr;
   for (int r = 0; r < 2; ++r) free_ring(w->ring[r]);
   for (int b = 0; b < 2; ++b) {
     host_free(w->reward[b], w->pin);
@@ -400,7 +434,7 @@ float* f16_hostwin_action_buffer(f16_hostwin_handle w, int which) { return (w &&
 
 int f16_hostwin_fill(f16_hostwin_handle w, const float* frames, f16_hostwin_result* out) {
   if (!w || !frames) return failf("f16_hostwin_fill: NULL argument");
-  w->pool->wait();
+  w->copier->wait();
   for (int r = 0; r < w->n_rings; ++r)
     for (int s = 0; s < (w->ring[r].aliased ? SLOTS : 2 * SLOTS); ++s) memcpy(w->row(r, s, 0), frames, (size_t)w->n * ROW_BYTES);
   w->head = SLOTS - 1;
@@ -428,7 +462,8 @@ int f16_hostwin_push(f16_hostwin_handle w, const float* frames, const float* rew
   if (done) memcpy(w->done[cur], done, (size_t)w->n);
   if (truncated) memcpy(w->trunc[cur], truncated, (size_t)w->n);
   w->term[cur].resize((size_t)n_done * ROWS * FEAT);
-  post_step(w, ring_now, records, n_done, w->term[cur].data());
+  fix_early(w, ring_now, records, n_done, w->term[cur].data());
+  fix_late(w, ring_now, records, n_done, w->term[cur].data());
   carry_over(w, ring_now);
   fill_result(w, ring_now, cur, n_done, records, out);
   return 0;
@@ -460,7 +495,7 @@ int f16_hostwin_reset(f16_hostwin_handle w, f16_handle env, void* stream, f16_ho
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const size_t bytes = (size_t)w->n * ROW_BYTES;
-  w->pool->wait();
+  w->copier->wait();
   for (int r = 0; r < w->n_rings; ++r)
     for (int s = 0; s < (w->ring[r].aliased ? SLOTS : 2 * SLOTS); ++s)
       CUDA_OK(cudaMemcpyAsync(w->row(r, s, 0), obs_frame, bytes, cudaMemcpyDeviceToHost, st));
@@ -510,8 +545,9 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
   // without auto-reset a finished env keeps its history (its newest row is the terminal frame itself)
   const int64_t n_fix = auto_reset ? n_done : 0;
   w->term[cur].resize((size_t)n_fix * ROWS * FEAT);
-  post_step(w, ring_now, w->records, n_fix, w->term[cur].data());
+  fix_early(w, ring_now, w->records, n_fix, w->term[cur].data());
   CUDA_OK(cudaStreamSynchronize(st));
+  fix_late(w, ring_now, w->records, n_fix, w->term[cur].data());
   carry_over(w, ring_now);
   fill_result(w, ring_now, cur, n_done, w->records, out);
   return 0;

@@ -158,6 +158,7 @@ struct StepArgs {
   int ring_slot;     // ring layout only: slot (0..9) this step writes; the window is rows slot+1 .. slot+10
   f16_done_record* done_list;   // frame layout only: one record per env that finished this step (may be mapped host memory)
   int32_t* done_count;          // frame layout only: device counter of appended records
+  int64_t tile0;                // first 32-env tile of this launch (f16_step_range); n is the end of the range
 };
 
 template <typename R>
@@ -385,10 +386,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
   const StatePtrs<R> sp = state_ptrs<R>(a.state, a.r_off, a.e_off, a.np);
 #if F16_PERSISTENT
 #pragma unroll 1
-  for (int64_t tile = (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += warps_total) {
+  for (int64_t tile = a.tile0 + (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += warps_total) {
 #else
   (void)warps_total;
-  const int64_t tile = (int64_t)blockIdx.x * WARPS + warp;
+  const int64_t tile = a.tile0 + (int64_t)blockIdx.x * WARPS + warp;
   if (tile < n_tiles) {
 #endif
     const int64_t env0 = tile << 5;
@@ -757,21 +758,18 @@ int f16_reset(f16_handle h, const uint8_t* mask, const float* goals, uint64_t se
   return 0;
 }
 
-int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream) {
-  if (!h) return fail("f16_step: NULL handle");
-  if (!h->state) return fail("f16_step: call f16_bind first");
-  CUDA_OK(cudaSetDevice(h->device));
+// One launch of the step kernel over envs [first, first + count); first is a multiple of 32.
+static int launch_step(f16_handle h, const float* actions, int auto_reset, int64_t first, int64_t count, uint32_t step_counter, void* stream) {
   StepArgs a;
   a.state = h->state; a.tables = h->tables_dev; a.actions = actions; a.obs = h->obs; a.reward = h->reward;
   a.done = h->done; a.truncated = h->truncated; a.terminal_obs = h->terminal_obs; a.ep_return = h->ep_return;
-  a.ep_len = h->ep_len; a.stats = h->stats_dev; a.n = h->L.n; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
-  a.seed = h->seed; a.env_id_base = h->env_id_base; a.step_counter = h->step_counter++; a.auto_reset = auto_reset;
+  a.ep_len = h->ep_len; a.stats = h->stats_dev; a.n = first + count; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
+  a.seed = h->seed; a.env_id_base = h->env_id_base; a.step_counter = step_counter; a.auto_reset = auto_reset;
   a.ring_slot = h->ring_head;
   a.done_list = h->done_list; a.done_count = h->done_count;
-  if (h->ring == OBS_FRAME && h->done_count) CUDA_OK(cudaMemsetAsync(h->done_count, 0, sizeof(int32_t), (cudaStream_t)stream));
-  if (h->ring == OBS_RING) h->ring_head = (h->ring_head + 1) % F16_OBS_FRAMES;
+  a.tile0 = first / 32;
   // persistent grid: SMs x resident CTAs (capped by the number of 32-env tiles)
-  const int64_t tiles = (h->L.n + 31) / 32;
+  const int64_t tiles = (count + 31) / 32;
   int64_t want = (int64_t)h->num_sms * h->ctas_per_sm;
   const int64_t need = (tiles + WARPS - 1) / WARPS;
   unsigned grid = (unsigned)((F16_PERSISTENT && want < need) ? want : need);
@@ -796,9 +794,40 @@ int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream) {
   }
 #undef F16_LAUNCH_STEP
   g_launches++;
-  h->env_steps += (double)h->L.n;
+  h->env_steps += (double)count;
   CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream) {
+  if (!h) return fail("f16_step: NULL handle");
+  if (!h->state) return fail("f16_step: call f16_bind first");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (h->ring == OBS_FRAME && h->done_count) CUDA_OK(cudaMemsetAsync(h->done_count, 0, sizeof(int32_t), (cudaStream_t)stream));
+  const uint32_t counter = h->step_counter++;
+  int rc = launch_step(h, actions, auto_reset, 0, h->L.n, counter, stream);
+  if (h->ring == OBS_RING) h->ring_head = (h->ring_head + 1) % F16_OBS_FRAMES;
+  return rc;
+}
+
+int f16_step_begin(f16_handle h, void* stream) {
+  if (!h) return fail("f16_step_begin: NULL handle");
+  if (!h->state) return fail("f16_step_begin: call f16_bind first");
+  if (h->ring != OBS_FRAME) return fail("f16_step_begin: only the frame layout can be stepped in pieces (f16_bind_frames)");
+  CUDA_OK(cudaSetDevice(h->device));
+  h->step_counter++;
+  if (h->done_count) CUDA_OK(cudaMemsetAsync(h->done_count, 0, sizeof(int32_t), (cudaStream_t)stream));
+  return 0;
+}
+
+int f16_step_range(f16_handle h, const float* actions, int auto_reset, int64_t first, int64_t count, void* stream) {
+  if (!h) return fail("f16_step_range: NULL handle");
+  if (!h->state) return fail("f16_step_range: call f16_bind first");
+  if (h->ring != OBS_FRAME) return fail("f16_step_range: only the frame layout can be stepped in pieces (f16_bind_frames)");
+  if (first < 0 || count <= 0 || first + count > h->L.n || (first & 31) != 0)
+    return fail("f16_step_range: bad range [%lld, %lld) (first must be a multiple of 32)", (long long)first, (long long)(first + count));
+  CUDA_OK(cudaSetDevice(h->device));
+  return launch_step(h, actions, auto_reset, first, count, h->step_counter - 1, stream);
 }
 
 int f16_step_host(f16_handle h, const float* actions_host, int auto_reset, float* obs_host, float* reward_host,

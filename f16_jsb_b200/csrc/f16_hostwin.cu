@@ -11,6 +11,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -150,10 +152,16 @@ struct f16_hostwin {
   f16_done_record* records = nullptr;    // mapped pinned memory the step kernel appends to (PIN only)
   int32_t* count_dev = nullptr;
   int32_t* count_host = nullptr;
-  cudaEvent_t ev = nullptr;
+  cudaEvent_t ev = nullptr, fork = nullptr;
+  int n_chunks = 1;                      // pieces one step is pipelined in (upload | kernel | download)
+  cudaStream_t cs[F16_HOSTWIN_MAX_CHUNKS] = {};
+  cudaEvent_t kdone[F16_HOSTWIN_MAX_CHUNKS] = {};
   std::vector<float> term[2];
   std::vector<Fix> pending;              // finished envs of the previous step, still to be applied to the other ring
   int device = -1;
+  double phase_s[F16_HOSTWIN_PHASES] = {0, 0, 0, 0, 0, 0, 0, 0};   // accumulated wall time per phase of f16_hostwin_step
+  int64_t phase_steps = 0;
+  std::atomic<int64_t> copy_ns{0};   // duration of the last carry-over, launch to last worker done
   Pool* pool = nullptr;      // fix-ups of finished envs
   Pool* copier = nullptr;    // carry-over of the newest slot to the other ring
 
@@ -319,7 +327,7 @@ void stream_copy(char* dst, const char* src, size_t len) {
 // Two rings: the frames of this step were DMA-ed into the returned ring only; host threads carry them over to
 // the other ring in the background, between this step and the next (which returns that ring).
 void carry_over(f16_hostwin* w, int ring_src) {
-  if (w->n_rings != 2 || (w->flags & F16_HOSTWIN_DMA_BOTH)) return;
+  if (w->n_rings != 2 || !(w->flags & F16_HOSTWIN_HOST_CARRY)) return;
   const int ring_dst = 1 - ring_src;
   const size_t bytes = (size_t)w->n * ROW_BYTES;
   const char* src = (const char*)w->row(ring_src, w->head, 0);
@@ -330,12 +338,17 @@ void carry_over(f16_hostwin* w, int ring_src) {
     if (dst2) memcpy(dst2, src, bytes);
     return;
   }
+  const auto t0 = std::chrono::steady_clock::now();
+  w->copy_ns.store(0);
   w->copier->launch([=](int i, int k) {
     const size_t chunk = ((bytes + (size_t)k - 1) / (size_t)k + PAGE - 1) / PAGE * PAGE, b = (size_t)i * chunk;
     if (b >= bytes) return;
     const size_t len = std::min(chunk, bytes - b);
     stream_copy(dst + b, src + b, len);
     if (dst2) stream_copy(dst2 + b, src + b, len);
+    const int64_t ns = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    int64_t seen = w->copy_ns.load();
+    while (ns > seen && !w->copy_ns.compare_exchange_weak(seen, ns)) {}
   });
 }
 
@@ -394,6 +407,18 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
     if (!rc) rc = host_array(&w->count_host, 1, true);
     if (!rc && cudaMalloc(&w->count_dev, sizeof(int32_t)) != cudaSuccess) rc = failf("f16_hostwin_create: cudaMalloc failed");
     if (!rc && cudaEventCreateWithFlags(&w->ev, cudaEventDisableTiming) != cudaSuccess) rc = failf("f16_hostwin_create: cudaEventCreate failed");
+    if (!rc && cudaEventCreateWithFlags(&w->fork, cudaEventDisableTiming) != cudaSuccess) rc = failf("f16_hostwin_create: cudaEventCreate failed");
+    for (int c = 0; c < F16_HOSTWIN_MAX_CHUNKS && !rc; ++c) {
+      if (cudaStreamCreateWithFlags(&w->cs[c], cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&w->kdone[c], cudaEventDisableTiming) != cudaSuccess)
+        rc = failf("f16_hostwin_create: stream / event creation failed");
+    }
+    // a step is worth cutting in pieces once a piece still fills the GPU for a wave or two
+    w->n_chunks = n_envs >= 524288 ? 4 : n_envs >= 131072 ? 2 : 1;
+    if (const char* e = getenv("F16_HOSTWIN_CHUNKS")) {
+      const int c = atoi(e);
+      if (c >= 1 && c <= F16_HOSTWIN_MAX_CHUNKS) w->n_chunks = c;
+    }
   }
   if (rc) { f16_hostwin_destroy(w); return rc; }
   *out = w;
@@ -416,6 +441,11 @@ int f16_hostwin_destroy(f16_hostwin_handle w) {
   host_free(w->count_host, w->pin);
   if (w->count_dev) cudaFree(w->count_dev);
   if (w->ev) cudaEventDestroy(w->ev);
+  if (w->fork) cudaEventDestroy(w->fork);
+  for (int c = 0; c < F16_HOSTWIN_MAX_CHUNKS; ++c) {
+    if (w->cs[c]) cudaStreamDestroy(w->cs[c]);
+    if (w->kdone[c]) cudaEventDestroy(w->kdone[c]);
+  }
   delete w;
   return 0;
 }
@@ -427,6 +457,17 @@ int f16_hostwin_layout(f16_hostwin_handle w, int ring, float** base, int64_t* sl
   if (slot_pitch_bytes) *slot_pitch_bytes = (int64_t)w->ring[ring].pitch;
   if (n_slots) *n_slots = 2 * SLOTS;
   if (aliased) *aliased = w->ring[ring].aliased ? 1 : 0;
+  return 0;
+}
+
+int f16_hostwin_timing(f16_hostwin_handle w, double* seconds_per_step, int reset) {
+  if (!w) return failf("f16_hostwin_timing: NULL handle");
+  if (seconds_per_step)
+    for (int i = 0; i < F16_HOSTWIN_PHASES; ++i) seconds_per_step[i] = w->phase_steps ? w->phase_s[i] / (double)w->phase_steps : 0.0;
+  if (reset) {
+    for (int i = 0; i < F16_HOSTWIN_PHASES; ++i) w->phase_s[i] = 0.0;
+    w->phase_steps = 0;
+  }
   return 0;
 }
 
@@ -454,7 +495,7 @@ int f16_hostwin_push(f16_hostwin_handle w, const float* frames, const float* rew
   w->head = (w->head + 1) % SLOTS;
   const int ring_now = w->n_rings == 2 ? (int)(w->t & 1) : 0, cur = (int)(w->t & 1);
   for (int r = 0; r < w->n_rings; ++r) {
-    if (r != ring_now && !(w->flags & F16_HOSTWIN_DMA_BOTH)) continue;      // carried over below
+    if (r != ring_now && (w->flags & F16_HOSTWIN_HOST_CARRY)) continue;      // carried over below
     memcpy(w->row(r, w->head, 0), frames, (size_t)w->n * ROW_BYTES);
     if (!w->ring[r].aliased) memcpy(w->row(r, w->head + SLOTS, 0), frames, (size_t)w->n * ROW_BYTES);
   }
@@ -510,6 +551,15 @@ int f16_hostwin_reset(f16_hostwin_handle w, f16_handle env, void* stream, f16_ho
 int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_host, int auto_reset, void* stream,
                      f16_hostwin_result* out) {
   if (!actions_host) return failf("f16_hostwin_step: actions_host is NULL");
+  using clk = std::chrono::steady_clock;
+  auto t_prev = clk::now();
+  int phase = 0;
+  auto lap = [&]() {
+    const auto now = clk::now();
+    if (w) w->phase_s[phase] += std::chrono::duration<double>(now - t_prev).count();
+    ++phase;
+    t_prev = now;
+  };
   float *obs_frame, *reward, *act_stage;
   uint8_t *done, *trunc;
   int rc = env_buffers(w, env, &obs_frame, &reward, &done, &trunc, &act_stage);
@@ -520,35 +570,71 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
   CUDA_OK(cudaHostGetDevicePointer((void**)&recs_dev, w->records, 0));
   rc = f16_set_done_list(env, recs_dev, w->count_dev);
   if (rc) return rc;
-  CUDA_OK(cudaMemcpyAsync(act_stage, actions_host, n * F16_ACTION_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
-  rc = f16_step(env, act_stage, auto_reset, stream);
-  if (rc) return rc;
   w->t += 1;
   w->head = (w->head + 1) % SLOTS;
   const int ring_now = w->n_rings == 2 ? (int)(w->t & 1) : 0, cur = (int)(w->t & 1);
-  // the count first (4 bytes) so the host can start on the finished envs while the frames are still in flight
-  CUDA_OK(cudaMemcpyAsync(w->count_host, w->count_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaEventRecord(w->ev, st));
-  CUDA_OK(cudaMemcpyAsync(w->done[cur], done, n, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaMemcpyAsync(w->trunc[cur], trunc, n, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaMemcpyAsync(w->reward[cur], reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  for (int r = 0; r < w->n_rings; ++r) {
-    // the returned ring first
-    const int rr = (r == 0) ? ring_now : 1 - ring_now;
-    if (rr != ring_now && !(w->flags & F16_HOSTWIN_DMA_BOTH)) continue;     // carried over by host threads after the sync
-    CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head, 0), obs_frame, n * ROW_BYTES, cudaMemcpyDeviceToHost, st));
-    if (!w->ring[rr].aliased) CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head + SLOTS, 0), obs_frame, n * ROW_BYTES, cudaMemcpyDeviceToHost, st));
+  // One step in n_chunks pieces, each on its own stream: piece c's actions go up while piece c-1 computes and
+  // piece c-2's frames come down (the three run on different engines). The done count is read once every
+  // kernel has finished, so the host can start on the finished envs while the frames are still in flight.
+  const int C = (int)std::min<int64_t>(w->n_chunks, (w->n + 127) / 128);
+  const int64_t per = ((w->n + C - 1) / C + 127) / 128 * 128;
+  rc = f16_step_begin(env, stream);
+  if (rc) return rc;
+  if (C > 1) CUDA_OK(cudaEventRecord(w->fork, st));
+  for (int c = 0; c < C; ++c) {
+    const int64_t first = (int64_t)c * per;
+    if (first >= w->n) break;
+    const size_t cnt = (size_t)std::min<int64_t>(per, w->n - first);
+    const cudaStream_t s = C > 1 ? w->cs[c] : st;
+    if (C > 1) CUDA_OK(cudaStreamWaitEvent(s, w->fork, 0));
+    CUDA_OK(cudaMemcpyAsync(act_stage + first * F16_ACTION_DIM, actions_host + first * F16_ACTION_DIM, cnt * F16_ACTION_DIM * sizeof(float),
+                            cudaMemcpyHostToDevice, s));
+    rc = f16_step_range(env, act_stage, auto_reset, first, (int64_t)cnt, (void*)s);
+    if (rc) return rc;
+    if (C > 1) CUDA_OK(cudaEventRecord(w->kdone[c], s));
+    else {
+      CUDA_OK(cudaMemcpyAsync(w->count_host, w->count_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaEventRecord(w->ev, st));
+    }
+    CUDA_OK(cudaMemcpyAsync(w->done[cur] + first, done + first, cnt, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(w->trunc[cur] + first, trunc + first, cnt, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(w->reward[cur] + first, reward + first, cnt * sizeof(float), cudaMemcpyDeviceToHost, s));
+    for (int r = 0; r < w->n_rings; ++r) {
+      const int rr = (r == 0) ? ring_now : 1 - ring_now;      // the returned ring first
+      if (rr != ring_now && (w->flags & F16_HOSTWIN_HOST_CARRY)) continue;     // carried over by host threads after the sync
+      CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head, first), obs_frame + first * FEAT, cnt * ROW_BYTES, cudaMemcpyDeviceToHost, s));
+      if (!w->ring[rr].aliased)
+        CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head + SLOTS, first), obs_frame + first * FEAT, cnt * ROW_BYTES, cudaMemcpyDeviceToHost, s));
+    }
   }
+  if (C > 1) {
+    for (int c = 0; c < C; ++c)
+      if ((int64_t)c * per < w->n) CUDA_OK(cudaStreamWaitEvent(st, w->kdone[c], 0));
+    CUDA_OK(cudaMemcpyAsync(w->count_host, w->count_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaEventRecord(w->ev, st));
+  }
+  lap();                                    // [0] enqueue: copies and the kernel launch
   CUDA_OK(cudaEventSynchronize(w->ev));     // kernel finished: the records it wrote to mapped host memory are complete
   const int64_t n_done = *w->count_host;
   if (n_done < 0 || n_done > w->n) return failf("f16_hostwin_step: done count %lld out of range", (long long)n_done);
   // without auto-reset a finished env keeps its history (its newest row is the terminal frame itself)
   const int64_t n_fix = auto_reset ? n_done : 0;
+  lap();                                    // [1] wait for the actions' upload and the kernel
   w->term[cur].resize((size_t)n_fix * ROWS * FEAT);
   fix_early(w, ring_now, w->records, n_fix, w->term[cur].data());
+  lap();                                    // [2] fix-ups of slots head-9 .. head-2 (under the frame DMA)
+  if (C > 1)
+    for (int c = 0; c < C; ++c) CUDA_OK(cudaStreamSynchronize(w->cs[c]));
   CUDA_OK(cudaStreamSynchronize(st));
+  lap();                                    // [3] wait for the rest of the device->host copies
+  w->copier->wait();
+  w->phase_s[7] += 1e-9 * (double)w->copy_ns.load();   // [7] how long that carry-over took on the copier threads (not part of the step's wall time)
+  lap();                                    // [4] wait for the previous step's carry-over
   fix_late(w, ring_now, w->records, n_fix, w->term[cur].data());
+  lap();                                    // [5] fix-ups of slot head-1
   carry_over(w, ring_now);
+  lap();                                    // [6] hand the newest slot to the copier threads
+  w->phase_steps += 1;
   fill_result(w, ring_now, cur, n_done, w->records, out);
   return 0;
 }

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from .constants import NUM_FEATURES, NUM_STACKED_FRAMES
 
-PIN, NO_ALIAS, DMA_BOTH = 1, 2, 4
+PIN, NO_ALIAS, HOST_CARRY = 1, 2, 4
 RECORD_DTYPE = np.dtype([("env", "<i4"), ("flags", "<i4"), ("ep_return", "<f4"), ("ep_len", "<i4"),
                          ("terminal_frame", "<f4", 16), ("reset_frame", "<f4", 16)])
 assert RECORD_DTYPE.itemsize == C.sizeof(_lib.DoneRecord) == 144
@@ -37,12 +37,12 @@ class StepResult:
 
 
 class HostWindow:
-    def __init__(self, num_envs: int, n_rings: int = 2, pin: bool = True, alias: bool = True, dma_both: bool = False):
+    def __init__(self, num_envs: int, n_rings: int = 2, pin: bool = True, alias: bool = True, host_carry: bool = False):
         self.lib = _lib.load()
         self.num_envs = int(num_envs)
         self.n_rings = int(n_rings)
         h = C.c_void_p()
-        flags = (PIN if pin else 0) | (0 if alias else NO_ALIAS) | (DMA_BOTH if dma_both else 0)
+        flags = (PIN if pin else 0) | (0 if alias else NO_ALIAS) | (HOST_CARRY if host_carry else 0)
         _lib.check(self.lib.f16_hostwin_create(C.byref(h), self.num_envs, self.n_rings, flags), "f16_hostwin_create")
         self._h = h
         self._rings = []
@@ -100,6 +100,14 @@ class HostWindow:
         _lib.check(self.lib.f16_hostwin_step(self._h, env._h, C.c_void_p(actions.ctypes.data), int(auto_reset), stream_ptr,
                                              C.byref(self._res)), "f16_hostwin_step")
         return self._result()
+
+    PHASES = ("enqueue", "wait_upload_kernel", "fix_older_slots", "wait_d2h", "wait_carry_over", "fix_newest_slot", "hand_off", "carry_over_duration")
+
+    def timing(self, reset: bool = False) -> dict:
+        """Average milliseconds per step spent in each phase of f16_hostwin_step since the last reset."""
+        out = (C.c_double * 8)()
+        _lib.check(self.lib.f16_hostwin_timing(self._h, out, int(reset)), "f16_hostwin_timing")
+        return {k: 1e3 * v for k, v in zip(self.PHASES, out)}
 
     # ------------------------------------------------------------------ host-only path (tests, replay)
     def fill(self, frames: np.ndarray) -> StepResult:

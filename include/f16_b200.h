@@ -96,6 +96,14 @@ int f16_reset(f16_handle h, const uint8_t* mask, const float* goals, uint64_t se
  * the reset observation, as DummyVecEnv does. */
 int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream);
 
+/* One env-step in pieces (frame layout only), so that a caller can pipeline it over several streams: upload of
+ * one piece, kernel of the previous, download of the one before. f16_step_begin advances the step counter that
+ * keys in-kernel random actions and zeroes the done count on `stream`; every piece's stream must be ordered
+ * after it. f16_step_range steps the envs [first, first + count), first a multiple of 32; actions is the full
+ * N x 4 device array. Every env has to be covered exactly once between two f16_step_begin calls. */
+int f16_step_begin(f16_handle h, void* stream);
+int f16_step_range(f16_handle h, const float* actions, int auto_reset, int64_t first, int64_t count, void* stream);
+
 /* Same step through HOST buffers (the reference-facing call: NumPy in, NumPy out). Copies
  * actions host->device, steps, copies obs/reward/done/truncated device->host and synchronises.
  * Pinned host memory makes the copies asynchronous DMA; pageable memory works but is slower.

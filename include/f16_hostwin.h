@@ -22,9 +22,12 @@
  *
  * n_rings = 2 alternates two rings so that the array returned by step t is not written again before step
  * t + 2 (SB3 reads `_last_obs` after the next env.step, stable_baselines3/common/on_policy_algorithm.py:247).
- * The frames still cross PCIe once: they land in the ring being returned and a few host threads copy the slot
- * into the other ring in the background, before the next step returns that one. n_rings = 1 keeps an array
- * valid only until the next step.
+ * Both rings receive every frame (2 x 60 B per env-step over PCIe; F16_HOSTWIN_HOST_CARRY sends it once and lets
+ * host threads copy the slot to the other ring between two steps). n_rings = 1 keeps an array valid only until
+ * the next step.
+ *
+ * A step of a large batch is pipelined in pieces over several streams (f16_step_range): the upload of one
+ * piece's actions, the kernel of the previous piece and the download of the one before run concurrently.
  */
 #ifndef F16_HOSTWIN_H
 #define F16_HOSTWIN_H
@@ -42,8 +45,10 @@ typedef struct f16_hostwin* f16_hostwin_handle;
 enum { F16_HOSTWIN_SLOTS = 11 };
 enum { F16_HOSTWIN_PIN = 1,        /* pin the rings for CUDA DMA (needs a CUDA device) */
        F16_HOSTWIN_NO_ALIAS = 2,   /* skip the double mapping, use the mirrored 22-slot ring */
-       F16_HOSTWIN_DMA_BOTH = 4 }; /* two rings: DMA every frame into both (default: DMA into the returned ring and let
-                                      host threads carry the slot over to the other ring before the next step) */
+       F16_HOSTWIN_HOST_CARRY = 4 }; /* two rings: DMA every frame into the returned ring only and let host threads
+                                        carry the slot over to the other ring before the next step (default: DMA into
+                                        both; measured equal on the B200 box, and the DMA engine costs no cores) */
+enum { F16_HOSTWIN_MAX_CHUNKS = 8 };
 
 typedef struct f16_hostwin_result {
   int32_t ring;                    /* which ring holds this step's window */
@@ -78,6 +83,14 @@ int f16_hostwin_reset(f16_hostwin_handle w, f16_handle env, void* stream, f16_ho
  * Synchronises `stream` before returning. */
 int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_host, int auto_reset, void* stream,
                      f16_hostwin_result* out);
+
+/* Average wall time per f16_hostwin_step since the last reset of the counters, by phase, in seconds:
+ * [0] enqueue (copies, kernel launch), [1] wait for upload + kernel, [2] fix-ups of the older slots (under the
+ * frame DMA), [3] wait for the device->host copies, [4] wait for the previous carry-over, [5] fix-ups of slot
+ * head-1, [6] hand-off to the copier threads, [7] duration of the carry-over on the copier threads (overlaps the
+ * next step; not part of its wall time). */
+enum { F16_HOSTWIN_PHASES = 8 };
+int f16_hostwin_timing(f16_hostwin_handle w, double* seconds_per_step, int reset);
 
 /* The same two operations for a producer that already has the data in host memory (tests, replay):
  * frames N x 15, reward N, done N, truncated N, records[n_done]. No CUDA calls. */

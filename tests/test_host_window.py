@@ -72,7 +72,7 @@ def test_carry_over_between_rings_on_host_threads(alias):
     steps; a vectorised stack model checks every returned window and that the previous one stays intact."""
     n = 20000
     rng = np.random.default_rng(3)
-    w = HostWindow(n, n_rings=2, pin=False, alias=alias)
+    w = HostWindow(n, n_rings=2, pin=False, alias=alias, host_carry=True)
     f0 = rng.normal(size=(n, 15)).astype(np.float32)
     expected = np.repeat(f0[:, None, :], 10, axis=1)
     res = w.fill(f0)

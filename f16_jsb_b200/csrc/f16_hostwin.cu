@@ -1,6 +1,6 @@
 // f16_hostwin.cu - host-resident observation windows (include/f16_hostwin.h).
 //
-// Host code only (CUDA runtime calls for pinning and DMA, no kernels): the step kernel in its frame layout
+// Host code (CUDA runtime calls for pinning and DMA; the only kernel is a one-thread publish of the done count): the step kernel in its frame layout
 // (f16_b200.cu, OBS_FRAME) emits 60 B per env-step; this file lands those frames in a slot-major ring of pinned
 // host memory whose pages are mapped twice back to back, so that the reference's (N,10,15) stacked observation
 // (jsbsim_gym/jsbsim_gym.py:150,235,263) is a strided view of the ring and never has to be assembled.
@@ -30,6 +30,12 @@
 extern "C" int f16_internal_fail(const char* msg);
 extern "C" int f16_internal_frame_buffers(f16_handle h, int64_t* n, int* device, float** obs_frame, float** reward, uint8_t** done,
                                           uint8_t** truncated, float** actions_stage);
+
+// The done count goes to mapped host memory by a store from the device, not by a copy: a 4-byte cudaMemcpyAsync
+// would queue behind the frame downloads of the earlier pieces on the copy engine, and the host wants the
+// count as soon as the last kernel is done so that the fix-ups run under the remaining DMA.
+__global__ void f16_publish_count_kernel(const int32_t* __restrict__ count_dev, volatile int32_t* count_host) { *count_host = *count_dev; }
+extern "C" void f16_internal_count_launch(void);
 
 namespace {
 
@@ -327,7 +333,7 @@ void stream_copy(char* dst, const char* src, size_t len) {
 // Two rings: the frames of this step were DMA-ed into the returned ring only; host threads carry them over to
 // the other ring in the background, between this step and the next (which returns that ring).
 void carry_over(f16_hostwin* w, int ring_src) {
-  if (w->n_rings != 2 || !(w->flags & F16_HOSTWIN_HOST_CARRY)) return;
+  if (w->n_rings != 2 || (w->flags & F16_HOSTWIN_DMA_BOTH)) return;
   const int ring_dst = 1 - ring_src;
   const size_t bytes = (size_t)w->n * ROW_BYTES;
   const char* src = (const char*)w->row(ring_src, w->head, 0);
@@ -404,7 +410,7 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
   }
   if (!rc && w->pin) {
     rc = host_array(&w->records, (size_t)n_envs, true, cudaHostAllocPortable | cudaHostAllocMapped);
-    if (!rc) rc = host_array(&w->count_host, 1, true);
+    if (!rc) rc = host_array(&w->count_host, 16, true, cudaHostAllocPortable | cudaHostAllocMapped);
     if (!rc && cudaMalloc(&w->count_dev, sizeof(int32_t)) != cudaSuccess) rc = failf("f16_hostwin_create: cudaMalloc failed");
     if (!rc && cudaEventCreateWithFlags(&w->ev, cudaEventDisableTiming) != cudaSuccess) rc = failf("f16_hostwin_create: cudaEventCreate failed");
     if (!rc && cudaEventCreateWithFlags(&w->fork, cudaEventDisableTiming) != cudaSuccess) rc = failf("f16_hostwin_create: cudaEventCreate failed");
@@ -495,7 +501,7 @@ int f16_hostwin_push(f16_hostwin_handle w, const float* frames, const float* rew
   w->head = (w->head + 1) % SLOTS;
   const int ring_now = w->n_rings == 2 ? (int)(w->t & 1) : 0, cur = (int)(w->t & 1);
   for (int r = 0; r < w->n_rings; ++r) {
-    if (r != ring_now && (w->flags & F16_HOSTWIN_HOST_CARRY)) continue;      // carried over below
+    if (r != ring_now && !(w->flags & F16_HOSTWIN_DMA_BOTH)) continue;      // carried over below
     memcpy(w->row(r, w->head, 0), frames, (size_t)w->n * ROW_BYTES);
     if (!w->ring[r].aliased) memcpy(w->row(r, w->head + SLOTS, 0), frames, (size_t)w->n * ROW_BYTES);
   }
@@ -565,9 +571,10 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
   int rc = env_buffers(w, env, &obs_frame, &reward, &done, &trunc, &act_stage);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t n = (size_t)w->n;
   f16_done_record* recs_dev = nullptr;
   CUDA_OK(cudaHostGetDevicePointer((void**)&recs_dev, w->records, 0));
+  int32_t* count_host_dev = nullptr;
+  CUDA_OK(cudaHostGetDevicePointer((void**)&count_host_dev, w->count_host, 0));
   rc = f16_set_done_list(env, recs_dev, w->count_dev);
   if (rc) return rc;
   w->t += 1;
@@ -593,7 +600,8 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
     if (rc) return rc;
     if (C > 1) CUDA_OK(cudaEventRecord(w->kdone[c], s));
     else {
-      CUDA_OK(cudaMemcpyAsync(w->count_host, w->count_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      f16_publish_count_kernel<<<1, 1, 0, st>>>(w->count_dev, count_host_dev);
+      f16_internal_count_launch();
       CUDA_OK(cudaEventRecord(w->ev, st));
     }
     CUDA_OK(cudaMemcpyAsync(w->done[cur] + first, done + first, cnt, cudaMemcpyDeviceToHost, s));
@@ -601,7 +609,7 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
     CUDA_OK(cudaMemcpyAsync(w->reward[cur] + first, reward + first, cnt * sizeof(float), cudaMemcpyDeviceToHost, s));
     for (int r = 0; r < w->n_rings; ++r) {
       const int rr = (r == 0) ? ring_now : 1 - ring_now;      // the returned ring first
-      if (rr != ring_now && (w->flags & F16_HOSTWIN_HOST_CARRY)) continue;     // carried over by host threads after the sync
+      if (rr != ring_now && !(w->flags & F16_HOSTWIN_DMA_BOTH)) continue;     // carried over by host threads after the sync
       CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head, first), obs_frame + first * FEAT, cnt * ROW_BYTES, cudaMemcpyDeviceToHost, s));
       if (!w->ring[rr].aliased)
         CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head + SLOTS, first), obs_frame + first * FEAT, cnt * ROW_BYTES, cudaMemcpyDeviceToHost, s));
@@ -610,7 +618,8 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
   if (C > 1) {
     for (int c = 0; c < C; ++c)
       if ((int64_t)c * per < w->n) CUDA_OK(cudaStreamWaitEvent(st, w->kdone[c], 0));
-    CUDA_OK(cudaMemcpyAsync(w->count_host, w->count_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    f16_publish_count_kernel<<<1, 1, 0, st>>>(w->count_dev, count_host_dev);
+    f16_internal_count_launch();
     CUDA_OK(cudaEventRecord(w->ev, st));
   }
   lap();                                    // [0] enqueue: copies and the kernel launch

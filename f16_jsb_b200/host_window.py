@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 from .constants import NUM_FEATURES, NUM_STACKED_FRAMES
 
-PIN, NO_ALIAS, HOST_CARRY = 1, 2, 4
+PIN, NO_ALIAS, DMA_BOTH = 1, 2, 4
 RECORD_DTYPE = np.dtype([("env", "<i4"), ("flags", "<i4"), ("ep_return", "<f4"), ("ep_len", "<i4"),
                          ("terminal_frame", "<f4", 16), ("reset_frame", "<f4", 16)])
 assert RECORD_DTYPE.itemsize == C.sizeof(_lib.DoneRecord) == 144
@@ -37,12 +37,12 @@ class StepResult:
 
 
 class HostWindow:
-    def __init__(self, num_envs: int, n_rings: int = 2, pin: bool = True, alias: bool = True, host_carry: bool = False):
+    def __init__(self, num_envs: int, n_rings: int = 2, pin: bool = True, alias: bool = True, dma_both: bool = False):
         self.lib = _lib.load()
         self.num_envs = int(num_envs)
         self.n_rings = int(n_rings)
         h = C.c_void_p()
-        flags = (PIN if pin else 0) | (0 if alias else NO_ALIAS) | (HOST_CARRY if host_carry else 0)
+        flags = (PIN if pin else 0) | (0 if alias else NO_ALIAS) | (DMA_BOTH if dma_both else 0)
         _lib.check(self.lib.f16_hostwin_create(C.byref(h), self.num_envs, self.n_rings, flags), "f16_hostwin_create")
         self._h = h
         self._rings = []

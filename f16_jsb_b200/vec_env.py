@@ -98,7 +98,7 @@ class F16VecEnv(VecEnvBase):
     def __init__(self, num_envs: int, device=None, mode: str = "fp32", seed: int = 0, host_ring: int = 2,
                  copy_obs: bool = False, lazy_infos: Optional[bool] = None, env_id_base: int = 0,
                  obs_layout: str = "stacked", host_obs: str = "window", host_rings: int = 2,
-                 host_carry: bool = False):
+                 host_dma_both: bool = False):
         obs_space, act_space = make_spaces()
         if host_obs not in ("window", "copy"):
             raise ValueError("host_obs must be 'window' or 'copy'")
@@ -120,7 +120,7 @@ class F16VecEnv(VecEnvBase):
         self._win = None
         if host_obs == "window":
             with torch.cuda.device(self.env.device):
-                self._win = HostWindow(n, n_rings=int(host_rings), pin=True, host_carry=host_carry)
+                self._win = HostWindow(n, n_rings=int(host_rings), pin=True, dma_both=host_dma_both)
             self._act_bufs = self._win.action_buffers
         else:
             self._h_obs = [torch.empty((n, NUM_STACKED_FRAMES, NUM_FEATURES), dtype=torch.float32, pin_memory=True) for _ in range(ring)]

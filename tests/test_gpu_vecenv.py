@@ -64,15 +64,15 @@ def test_vecenv_done_infos_match_dummy_vec_env_conventions(golden, host_obs, rin
     env.close()
 
 
-@pytest.mark.parametrize("rings", [1, 2])
-def test_window_mode_returns_what_copy_mode_returns(rings):
+@pytest.mark.parametrize("rings,dma_both", [(1, False), (2, False), (2, True)])
+def test_window_mode_returns_what_copy_mode_returns(rings, dma_both):
     """Host-resident windows (60 B per env-step over PCIe) against the device-side stacks copied out whole
     (600 B): identical observations, rewards, flags, terminal observations and episode statistics across
     crashes and auto-resets. FP64 mode: there the two layouts' kernel instantiations agree bit for bit (the
     float instantiations contract a few multiply-adds differently, see test_ring_layout_is_value_identical_to_stacked)."""
     from f16_jsb_b200 import F16VecEnv
     n, steps = 2048, 120
-    a_env = F16VecEnv(n, mode="fp64", seed=3, host_obs="window", host_rings=rings)
+    a_env = F16VecEnv(n, mode="fp64", seed=3, host_obs="window", host_rings=rings, host_dma_both=dma_both)
     b_env = F16VecEnv(n, mode="fp64", seed=3, host_obs="copy")
     oa, ob = _reset_with_near_goals(a_env, n, 5), _reset_with_near_goals(b_env, n, 5)
     assert np.array_equal(oa, ob)
@@ -103,14 +103,16 @@ def test_window_mode_returns_what_copy_mode_returns(rings):
     b_env.close()
 
 
-def test_window_mode_fp32_is_the_deque_of_the_frame_layout():
+@pytest.mark.parametrize("chunks", [1, 3, 8])
+def test_window_mode_fp32_is_the_deque_of_the_frame_layout(chunks, monkeypatch):
     """FP32 mode, 150 steps over 4 096 envs that reach their goals all along the run: F16VecEnv's host windows against a
     deque model (jsbsim_gym.py:150,235,325-329; dummy_vec_env.py:63-72) fed with the device outputs of a second
     env in the same frame layout - the same kernel instantiation, so everything is bit-exact."""
     from collections import deque
 
     from f16_jsb_b200 import F16BatchedEnv, F16VecEnv
-    n, steps = 4096, 150
+    monkeypatch.setenv("F16_HOSTWIN_CHUNKS", str(chunks))     # pieces one step is pipelined in (default: by batch size)
+    n, steps = 4096 - 37 * (chunks == 3), 150                  # a ragged batch for the odd split
     venv = F16VecEnv(n, mode="fp32", seed=7, host_obs="window", host_rings=2)
     ref = F16BatchedEnv(n, mode="fp32", seed=7, obs_layout="frame", done_list=True)
     g = np.zeros((n, 3), np.float32)

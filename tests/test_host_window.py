@@ -25,11 +25,11 @@ class DequeModel:
 
 
 @pytest.mark.parametrize("alias", [True, False])
-@pytest.mark.parametrize("n_rings", [1, 2])
+@pytest.mark.parametrize("n_rings,dma_both", [(1, False), (2, False), (2, True)])
 @pytest.mark.parametrize("n", [1, 37, 1500])
-def test_windows_match_the_deque_model(n, n_rings, alias):
+def test_windows_match_the_deque_model(n, n_rings, dma_both, alias):
     rng = np.random.default_rng(n * 7 + n_rings)
-    w = HostWindow(n, n_rings=n_rings, pin=False, alias=alias)
+    w = HostWindow(n, n_rings=n_rings, pin=False, alias=alias, dma_both=dma_both)
     assert all(a == alias for a in w.aliased) or alias     # the aliased mapping may be unavailable; the mirror never is
     f0 = rng.normal(size=(n, 15)).astype(np.float32)
     model = DequeModel(f0)
@@ -72,7 +72,7 @@ def test_carry_over_between_rings_on_host_threads(alias):
     steps; a vectorised stack model checks every returned window and that the previous one stays intact."""
     n = 20000
     rng = np.random.default_rng(3)
-    w = HostWindow(n, n_rings=2, pin=False, alias=alias, host_carry=True)
+    w = HostWindow(n, n_rings=2, pin=False, alias=alias)
     f0 = rng.normal(size=(n, 15)).astype(np.float32)
     expected = np.repeat(f0[:, None, :], 10, axis=1)
     res = w.fill(f0)

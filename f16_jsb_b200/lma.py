@@ -1,0 +1,252 @@
+"""LMA feature extractor and actor-critic heads for device-resident training on the F-16 env.
+
+What the reference builds for `PPO('MlpPolicy', env, policy_kwargs=...)` (train.py:21-32,81-84):
+StackedLMAFeaturesExtractor (jsbsim_gym/LMA_features.py:636-777) = per-frame JSBSimFeatureExtractor
+(jsbsim_gym/features.py:37-67, here the CUDA kernel behind include/f16_features.h) -> LMAFeaturesExtractor
+(:410-530): Linear 17->64 + ReLU + sinusoidal positions, head stacking 4 x 16 along the sequence, re-chunk of the
+640 values into L'=5 tokens of 128, Linear 128->32 + ReLU, two pre-LayerNorm blocks (4-head attention over the 5
+tokens, GELU MLP 32->128->32), flatten to 160 features; then SB3's ActorCriticPolicy heads
+(stable_baselines3/common/policies.py:416-760, torch_layers.py MlpExtractor): tanh MLPs pi [64,64] / vf [128,64],
+Linear action mean, state-independent log-std, Linear value.
+
+Parameter names follow the reference's state_dict keys, so checkpoints interchange
+(`lma_extractor.initial_transform.input_embedding.weight`, `lma_extractor.lma_blocks.0.attn.c_attn.weight`, ...;
+heads: `mlp_extractor.policy_net.0.weight`, `action_net.weight`, `value_net.weight`, `log_std`). The code is
+this repo's own: the stacking / re-chunk is one permute, attention is one fused SDPA call over (B, 4, 5, 8).
+"""
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .constants import NUM_FEATURES, NUM_STACKED_FRAMES
+from .features import FEATURES_PER_FRAME, jsbsim_features
+
+
+def closest_divisor(total: int, target: int, max_delta: int = 100) -> int:
+    """Divisor of `total` nearest to `target`, smaller one first on ties within +-max_delta
+    (find_closest_divisor, jsbsim_gym/LMA_features.py:23-96)."""
+    if total <= 0:
+        raise ValueError("total must be positive")
+    target = max(1, int(target))
+    if total % target == 0:
+        return target
+    for delta in range(1, max_delta + 1):
+        lo, hi = target - delta, target + delta
+        if lo > 0 and total % lo == 0:
+            return lo
+        if total % hi == 0:
+            return hi
+    divisors = [d for i in range(1, int(math.isqrt(total)) + 1) if total % i == 0 for d in (i, total // i)]
+    return min(divisors, key=lambda d: (abs(d - target), d))
+
+
+@dataclass
+class LMAConfig:
+    """Shapes of the extractor (LMAConfigRL, jsbsim_gym/LMA_features.py:99-169; defaults = train.py:21-32)."""
+    seq_len: int = NUM_STACKED_FRAMES
+    in_features: int = FEATURES_PER_FRAME
+    embed_dim: int = 64
+    num_heads_stacking: int = 4
+    num_heads_latent: int = 4
+    ff_hidden: int = 128
+    num_layers: int = 2
+    dropout: float = 0.1
+    bias: bool = True
+
+    def __post_init__(self):
+        if self.embed_dim % self.num_heads_stacking:
+            raise ValueError("embed_dim must be divisible by num_heads_stacking")
+        self.d_new = self.embed_dim // 2                                 # StackedLMAFeaturesExtractor :706
+        if self.d_new % self.num_heads_latent:
+            raise ValueError("d_new must be divisible by num_heads_latent")
+        total = self.seq_len * self.embed_dim
+        self.l_new = closest_divisor(total, self.seq_len // 2)           # :705, LMAConfigRL.__post_init__
+        self.c_new = total // self.l_new
+        self.features_dim = self.l_new * self.d_new
+
+
+def sinusoidal_positions(seq_len: int, dim: int) -> torch.Tensor:
+    pos = torch.arange(seq_len, dtype=torch.float32).unsqueeze(1)
+    freq = torch.exp(torch.arange(0, dim, 2, dtype=torch.float32) * (-math.log(10000.0) / dim))
+    pe = torch.zeros(seq_len, dim)
+    pe[:, 0::2] = torch.sin(pos * freq)
+    pe[:, 1::2] = torch.cos(pos * freq)
+    return pe
+
+
+def features17_torch(frames: torch.Tensor) -> torch.Tensor:
+    """PyTorch form of the per-frame transform for tensors that are not on a GPU (tests; the CUDA kernel
+    f16_features17 is what runs on device tensors)."""
+    pos, mach, ab, rates = frames[..., 0:3], frames[..., 3:4], frames[..., 4:6], frames[..., 6:9]
+    pt, psi, goal = frames[..., 9:11], frames[..., 11:12], frames[..., 12:15]
+    disp = goal - pos
+    dist = torch.sqrt((disp[..., :2] ** 2).sum(-1, keepdim=True))
+    rel = torch.atan2(disp[..., 1:2], disp[..., 0:1]) - psi
+    return torch.cat([1 / (1 + dist * 1e-3), disp[..., 2:3] / 15000, pos[..., 2:3] / 15000, mach, rates, torch.cos(ab), torch.sin(ab),
+                      torch.cos(pt), torch.sin(pt), torch.cos(rel), torch.sin(rel)], dim=-1)
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim: int, heads: int, dropout: float, bias: bool):
+        super().__init__()
+        self.heads, self.p = heads, dropout
+        self.c_attn = nn.Linear(dim, 3 * dim, bias=bias)
+        self.c_proj = nn.Linear(dim, dim, bias=bias)
+
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        b, t, d = z.shape
+        qkv = self.c_attn(z).view(b, t, 3, self.heads, d // self.heads).permute(2, 0, 3, 1, 4)      # (3, B, H, T, dh)
+        y = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], dropout_p=self.p if self.training else 0.0)
+        y = self.c_proj(y.transpose(1, 2).reshape(b, t, d))
+        return F.dropout(y, self.p, self.training)
+
+
+class _MLP(nn.Module):
+    def __init__(self, dim: int, hidden: int, dropout: float, bias: bool):
+        super().__init__()
+        self.p = dropout
+        self.c_fc = nn.Linear(dim, hidden, bias=bias)
+        self.c_proj = nn.Linear(hidden, dim, bias=bias)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return F.dropout(self.c_proj(F.gelu(self.c_fc(x))), self.p, self.training)
+
+
+class _Norm(nn.Module):
+    def __init__(self, dim: int, bias: bool):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.bias = nn.Parameter(torch.zeros(dim)) if bias else None
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return F.layer_norm(x, self.weight.shape, self.weight, self.bias, 1e-5)
+
+
+class _Block(nn.Module):
+    def __init__(self, cfg: LMAConfig):
+        super().__init__()
+        self.ln_1 = _Norm(cfg.d_new, cfg.bias)
+        self.attn = _Attention(cfg.d_new, cfg.num_heads_latent, cfg.dropout, cfg.bias)
+        self.ln_2 = _Norm(cfg.d_new, cfg.bias)
+        self.mlp = _MLP(cfg.d_new, cfg.ff_hidden, cfg.dropout, cfg.bias)
+
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        z = z + self.attn(self.ln_1(z))
+        return z + self.mlp(self.ln_2(z))
+
+
+class _InitialTransform(nn.Module):
+    def __init__(self, cfg: LMAConfig):
+        super().__init__()
+        self.cfg = cfg
+        self.input_embedding = nn.Linear(cfg.in_features, cfg.embed_dim, bias=cfg.bias)
+        self.embed_layer_2 = nn.Linear(cfg.c_new, cfg.d_new, bias=cfg.bias)
+        self.register_buffer("positions", sinusoidal_positions(cfg.seq_len, cfg.embed_dim), persistent=False)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        c = self.cfg
+        b = x.shape[0]
+        y = F.dropout(F.relu(self.input_embedding(x)) + self.positions, c.dropout, self.training)
+        # head stacking (split the 64 channels in 4 heads, lay the heads one after the other along the
+        # sequence) and re-chunking into L' tokens of C' values is a single permutation of the 640 values
+        h = c.num_heads_stacking
+        y = y.view(b, c.seq_len, h, c.embed_dim // h).permute(0, 2, 1, 3).reshape(b, c.l_new, c.c_new)
+        return F.relu(self.embed_layer_2(y))
+
+
+class _LMACore(nn.Module):
+    def __init__(self, cfg: LMAConfig):
+        super().__init__()
+        self.initial_transform = _InitialTransform(cfg)
+        self.lma_blocks = nn.ModuleList([_Block(cfg) for _ in range(cfg.num_layers)])
+
+    def forward(self, feats: torch.Tensor) -> torch.Tensor:
+        z = self.initial_transform(feats)
+        for blk in self.lma_blocks:
+            z = blk(z)
+        return z.flatten(1)
+
+
+class LMAExtractor(nn.Module):
+    """(B, 10, 15) stacked observations -> (B, 160) features."""
+
+    def __init__(self, cfg: Optional[LMAConfig] = None):
+        super().__init__()
+        self.cfg = cfg or LMAConfig()
+        self.lma_extractor = _LMACore(self.cfg)
+        self.features_dim = self.cfg.features_dim
+
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        assert obs.shape[1:] == (self.cfg.seq_len, NUM_FEATURES), obs.shape
+        with torch.no_grad():     # the transform has no parameters and observations carry no gradient
+            feats = jsbsim_features(obs) if obs.is_cuda else features17_torch(obs.float())
+        return self.lma_extractor(feats)
+
+
+def _mlp(sizes, act=nn.Tanh) -> nn.Sequential:
+    layers = []
+    for i in range(len(sizes) - 1):
+        layers += [nn.Linear(sizes[i], sizes[i + 1]), act()]
+    return nn.Sequential(*layers)
+
+
+class _MlpExtractor(nn.Module):
+    def __init__(self, in_dim: int, pi, vf):
+        super().__init__()
+        self.policy_net = _mlp([in_dim] + list(pi))
+        self.value_net = _mlp([in_dim] + list(vf))
+
+
+class LMAActorCritic(nn.Module):
+    """ActorCriticPolicy of the reference run: shared LMA extractor, pi [64,64] / vf [128,64] tanh MLPs
+    (train.py:84), diagonal Gaussian with a state-independent log-std initialised to 0
+    (stable_baselines3/common/distributions.py:125-190), orthogonal init with gains sqrt(2) / 0.01 / 1
+    (policies.py:580-600)."""
+
+    def __init__(self, cfg: Optional[LMAConfig] = None, pi=(64, 64), vf=(128, 64), action_dim: int = 4, log_std_init: float = 0.0,
+                 ortho_init: bool = True):
+        super().__init__()
+        self.features_extractor = LMAExtractor(cfg)
+        d = self.features_extractor.features_dim
+        self.mlp_extractor = _MlpExtractor(d, pi, vf)
+        self.action_net = nn.Linear(pi[-1], action_dim)
+        self.value_net = nn.Linear(vf[-1], 1)
+        self.log_std = nn.Parameter(torch.full((action_dim,), float(log_std_init)))
+        if ortho_init:
+            for mod, gain in ((self.features_extractor, math.sqrt(2)), (self.mlp_extractor, math.sqrt(2)), (self.action_net, 0.01),
+                              (self.value_net, 1.0)):
+                for m in mod.modules():
+                    if isinstance(m, nn.Linear):
+                        nn.init.orthogonal_(m.weight, gain=gain)
+                        if m.bias is not None:
+                            m.bias.data.zero_()
+
+    def _heads(self, obs: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        f = self.features_extractor(obs)
+        mean = self.action_net(self.mlp_extractor.policy_net(f))
+        value = self.value_net(self.mlp_extractor.value_net(f)).squeeze(-1)
+        return mean, value
+
+    def _log_prob(self, mean: torch.Tensor, actions: torch.Tensor) -> torch.Tensor:
+        var = torch.exp(2 * self.log_std)
+        return (-((actions - mean) ** 2) / (2 * var) - self.log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+
+    def forward(self, obs: torch.Tensor, deterministic: bool = False):
+        """policy(obs) -> actions, values, log_probs (policies.py:636-658)."""
+        mean, value = self._heads(obs)
+        actions = mean if deterministic else mean + torch.exp(self.log_std) * torch.randn_like(mean)
+        return actions, value, self._log_prob(mean, actions)
+
+    def evaluate_actions(self, obs: torch.Tensor, actions: torch.Tensor):
+        """-> values, log_prob, entropy (policies.py:719-745)."""
+        mean, value = self._heads(obs)
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + self.log_std).sum(-1).expand(mean.shape[0])
+        return value, self._log_prob(mean, actions), entropy
+
+    def predict_values(self, obs: torch.Tensor) -> torch.Tensor:
+        f = self.features_extractor(obs)
+        return self.value_net(self.mlp_extractor.value_net(f)).squeeze(-1)

@@ -29,8 +29,12 @@ for r in rows[2:]:
         pass
 d = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=d, capture_output=True)
-cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cubin)], capture_output=True, text=True).stdout
+txt = ""
+for cubin in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):      # one cubin per .cu of the library
+    t = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cubin)], capture_output=True, text=True).stdout
+    if pat in t:
+        txt = t
+        break
 in_fn, cur, lines = False, None, []
 for line in txt.splitlines():
     if line.startswith("//--------------------- .text."):

@@ -75,6 +75,11 @@ def load():
     L.f16_rollout_gae.argtypes = [i64, i64, C.c_float, C.c_float] + [vp] * 8
     L.f16_rollout_gather.argtypes = [i64, i64, i64] + [vp] * 15
     L.f16_features17.argtypes = [i64, vp, vp, vp]
+    L.f16_lma_attention_forward.argtypes = [i64, i32, i32, i32, vp, vp, C.c_float, u64, vp]
+    L.f16_lma_attention_backward.argtypes = [i64, i32, i32, i32, vp, vp, vp, C.c_float, u64, vp]
+    L.f16_lma_attention_mask.argtypes = [i64, i32, i32, vp, C.c_float, u64, vp]
+    for name in ("f16_lma_attention_forward", "f16_lma_attention_backward", "f16_lma_attention_mask"):
+        getattr(L, name).restype = i32
     L.f16_features17.restype = i32
     for name in ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather"):
         getattr(L, name).restype = i32

@@ -90,6 +90,57 @@ def features17_torch(frames: torch.Tensor) -> torch.Tensor:
                       torch.cos(pt), torch.sin(pt), torch.cos(rel), torch.sin(rel)], dim=-1)
 
 
+class _LatentAttentionFn(torch.autograd.Function):
+    """softmax(q k^T / sqrt(dh)) v over the five latent tokens by the hand-written kernels of
+    csrc/f16_lma_attention.cu (include/f16_lma.h): (B, T, 3*H*dh) fused projection in, (B, T, H*dh) out."""
+
+    @staticmethod
+    def forward(ctx, qkv: torch.Tensor, heads: int, dropout_p: float):
+        import ctypes as C
+
+        from . import _lib
+        qkv = qkv.contiguous()
+        b, t, d3 = qkv.shape
+        d = d3 // 3
+        y = torch.empty((b, t, d), dtype=torch.float32, device=qkv.device)
+        # the mask is a function of (seed, sample, head): the backward kernel regenerates it
+        seed = int(torch.empty((), dtype=torch.int64).random_()) if dropout_p > 0 else 0
+        stream = C.c_void_p(torch.cuda.current_stream(qkv.device).cuda_stream)
+        with torch.cuda.device(qkv.device):
+            _lib.check(_lib.load().f16_lma_attention_forward(b, t, heads, d // heads, C.c_void_p(qkv.data_ptr()), C.c_void_p(y.data_ptr()),
+                                                             float(dropout_p), seed, stream), "f16_lma_attention_forward")
+        ctx.save_for_backward(qkv)
+        ctx.meta = (heads, float(dropout_p), seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        import ctypes as C
+
+        from . import _lib
+        (qkv,) = ctx.saved_tensors
+        heads, p, seed = ctx.meta
+        b, t, d3 = qkv.shape
+        dy = dy.contiguous()
+        dqkv = torch.empty_like(qkv)
+        stream = C.c_void_p(torch.cuda.current_stream(qkv.device).cuda_stream)
+        with torch.cuda.device(qkv.device):
+            _lib.check(_lib.load().f16_lma_attention_backward(b, t, heads, d3 // 3 // heads, C.c_void_p(qkv.data_ptr()), C.c_void_p(dy.data_ptr()),
+                                                              C.c_void_p(dqkv.data_ptr()), p, seed, stream), "f16_lma_attention_backward")
+        return dqkv, None, None
+
+
+def latent_attention(qkv: torch.Tensor, heads: int, dropout_p: float = 0.0) -> torch.Tensor:
+    """(B, T, 3*D) -> (B, T, D). CUDA float32 tensors with T = 5 and D / heads = 8 (the reference's LMA shape)
+    go through the hand-written kernels; anything else through torch's scaled_dot_product_attention."""
+    b, t, d3 = qkv.shape
+    d = d3 // 3
+    if qkv.is_cuda and qkv.dtype == torch.float32 and t == 5 and d // heads == 8:
+        return _LatentAttentionFn.apply(qkv, heads, dropout_p)
+    q, k, v = qkv.view(b, t, 3, heads, d // heads).permute(2, 0, 3, 1, 4)
+    return F.scaled_dot_product_attention(q, k, v, dropout_p=dropout_p).transpose(1, 2).reshape(b, t, d)
+
+
 class _Attention(nn.Module):
     def __init__(self, dim: int, heads: int, dropout: float, bias: bool):
         super().__init__()
@@ -98,11 +149,8 @@ class _Attention(nn.Module):
         self.c_proj = nn.Linear(dim, dim, bias=bias)
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
-        b, t, d = z.shape
-        qkv = self.c_attn(z).view(b, t, 3, self.heads, d // self.heads).permute(2, 0, 3, 1, 4)      # (3, B, H, T, dh)
-        y = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], dropout_p=self.p if self.training else 0.0)
-        y = self.c_proj(y.transpose(1, 2).reshape(b, t, d))
-        return F.dropout(y, self.p, self.training)
+        y = latent_attention(self.c_attn(z), self.heads, self.p if self.training else 0.0)
+        return F.dropout(self.c_proj(y), self.p, self.training)
 
 
 class _MLP(nn.Module):

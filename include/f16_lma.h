@@ -1,0 +1,33 @@
+/* f16_lma.h - C ABI of the latent-attention kernels (libf16b200.so), SURVEY.md 8(f) rows 2-3.
+ *
+ * The attention inside the reference's LMA feature extractor (LatentAttention_RL.forward,
+ * jsbsim_gym/LMA_features.py:315-354) runs over L' = 5 latent tokens with 4 heads of 8 channels
+ * (train.py:21-32). The reference calls F.scaled_dot_product_attention (:337-342), whose library kernels tile
+ * the sequence in blocks of 64: at a sequence length of 5 they spend two thirds of an AM-PPO update and 40 % of
+ * a rollout step (measured, tools/profile_amppo_update.py). Here one thread owns one (sample, head): 120 floats
+ * of q, k, v in registers, 25 scores, softmax, optional dropout on the probabilities, 40 outputs - read
+ * straight from the fused projection's (B, T, 3*H*DH) output and written in (B, T, H*DH) order, so no
+ * transposes are materialised. The backward kernel recomputes the probabilities and regenerates the same
+ * Philox dropout mask from (seed, sample, head).
+ *
+ * Device pointers, caller's stream. Supported shape: T = 5, DH = 8 (any H); other shapes are refused. */
+#ifndef F16_LMA_H
+#define F16_LMA_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* qkv: [B][T][3*H*DH] float32 (q | k | v along the last axis) -> y: [B][T][H*DH].
+ * dropout_p in [0,1): probability of zeroing an attention weight (0 at inference); kept weights are scaled by
+ * 1/(1-p). */
+int f16_lma_attention_forward(int64_t batch, int seq_len, int heads, int head_dim, const float* qkv, float* y,
+                              float dropout_p, uint64_t seed, void* stream);
+/* dy: [B][T][H*DH] -> dqkv: [B][T][3*H*DH] (every element written). Same dropout_p and seed as the forward. */
+int f16_lma_attention_backward(int64_t batch, int seq_len, int heads, int head_dim, const float* qkv, const float* dy,
+                               float* dqkv, float dropout_p, uint64_t seed, void* stream);
+/* The keep mask the two kernels use, as floats (0 or 1/(1-p')): [B][H][T][T]. For tests. */
+int f16_lma_attention_mask(int64_t batch, int seq_len, int heads, float* mask, float dropout_p, uint64_t seed, void* stream);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -22,6 +22,49 @@ def test_lma_extractor_on_device_matches_reference():
     assert torch.allclose(out, g["features"], rtol=1e-4, atol=1e-4), float((out - g["features"]).abs().max())
 
 
+def _attention_reference(qkv, heads, mask=None):
+    """Plain PyTorch float32: softmax(q k^T / sqrt(dh)) [* mask] v."""
+    b, t, d3 = qkv.shape
+    d = d3 // 3
+    q, k, v = qkv.view(b, t, 3, heads, d // heads).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(q @ k.transpose(-2, -1) / (d // heads) ** 0.5, dim=-1)
+    if mask is not None:
+        p = p * mask
+    return (p @ v).transpose(1, 2).reshape(b, t, d)
+
+
+@pytest.mark.parametrize("batch,dropout", [(1, 0.0), (1000, 0.0), (4097, 0.1), (333, 0.5)])
+def test_latent_attention_kernels_match_pytorch(batch, dropout):
+    """Forward and backward of the hand-written latent-attention kernels (include/f16_lma.h) against a plain
+    PyTorch float32 reference of the same op; with dropout the reference multiplies by the kernels' own keep mask
+    (f16_lma_attention_mask). Tolerance 2e-5 relative to the largest value."""
+    import ctypes as C
+
+    from f16_jsb_b200 import _lib
+    from f16_jsb_b200.lma import _LatentAttentionFn
+    g = torch.Generator(device="cuda").manual_seed(batch)
+    qkv = (torch.randn((batch, 5, 96), device="cuda", generator=g) * 1.5).requires_grad_(True)
+    dy = torch.randn((batch, 5, 32), device="cuda", generator=g)
+    torch.manual_seed(7)
+    y = _LatentAttentionFn.apply(qkv, 4, dropout)
+    seed = y.grad_fn.meta[2]
+    mask = None
+    if dropout > 0:
+        mask = torch.empty((batch, 4, 5, 5), device="cuda")
+        _lib.check(_lib.load().f16_lma_attention_mask(batch, 5, 4, C.c_void_p(mask.data_ptr()), float(dropout), seed,
+                                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mask")
+        kept = float((mask > 0).float().mean())
+        assert set(mask.unique().tolist()) <= {0.0, float(mask.max())} and abs(float(mask.max()) - 1 / (1 - dropout)) < 1e-3
+        if batch > 1000:
+            assert abs(kept - (1 - dropout)) < 0.01
+    (gq,) = torch.autograd.grad(y, qkv, dy)
+    ref_in = qkv.detach().clone().requires_grad_(True)
+    y_ref = _attention_reference(ref_in, 4, mask)
+    (gq_ref,) = torch.autograd.grad(y_ref, ref_in, dy)
+    assert torch.allclose(y, y_ref, rtol=2e-5, atol=2e-5 * float(y_ref.abs().max()))
+    assert torch.allclose(gq, gq_ref, rtol=2e-5, atol=2e-5 * float(gq_ref.abs().max())), float((gq - gq_ref).abs().max())
+
+
 @pytest.mark.parametrize("use_am_ppo,optimizer", [(True, "DAG"), (True, "Adam"), (False, "Adam")])
 def test_rollout_and_update_run_on_device(use_am_ppo, optimizer):
     from f16_jsb_b200 import F16BatchedEnv

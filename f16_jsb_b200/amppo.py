@@ -114,6 +114,8 @@ class AMPPOConfig:
     dynago: DynagoConfig = field(default_factory=DynagoConfig)
     lma: LMAConfig = field(default_factory=LMAConfig)
     seed: int = 1
+    cuda_graph: bool = True           # replay the rollout's policy forward (~50 small launches) as one CUDA graph
+    tf32: bool = False                # TF32 tensor-core matmuls for the policy (the reference computes in FP32)
 
 
 class AMPPO:
@@ -138,11 +140,34 @@ class AMPPO:
         self.generator.manual_seed(c.seed)
         self._obs = None
         self._episode_starts = None
+        self._graph = None
+        if c.tf32:
+            torch.backends.cuda.matmul.allow_tf32 = True
         self.num_timesteps = 0
         self.n_updates = 0
         self.last_stats: Dict[str, float] = {}
 
     # ------------------------------------------------------------------ rollout (on_policy_algorithm.py:162-275)
+    def _act(self, obs: torch.Tensor):
+        actions, values, log_probs = self.policy(obs)
+        clipped = torch.maximum(torch.minimum(actions, self.act_high), self.act_low)              # :216
+        return actions, values, log_probs, clipped
+
+    def _capture_act(self) -> None:
+        """The per-step policy forward is ~50 launches of tiny kernels; at a few thousand envs the rollout is
+        launch-bound, so it is captured once (static observation buffer in, static outputs out) and replayed.
+        The optimizers update the weights in place, so the graph stays valid across updates."""
+        self._g_obs = torch.zeros((self.env.num_envs,) + tuple(self._obs.shape[1:]), dtype=torch.float32, device=self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._act(self._g_obs)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_out = self._act(self._g_obs)
+
     @torch.no_grad()
     def collect_rollouts(self) -> None:
         c, env = self.cfg, self.env
@@ -150,11 +175,18 @@ class AMPPO:
             self._obs = env.reset()
             self._episode_starts = torch.ones(env.num_envs, dtype=torch.uint8, device=self.device)
         self.policy.eval()
+        if c.cuda_graph and self._graph is None:
+            self._capture_act()
         self.buffer.reset()
         for _ in range(c.n_steps):
-            obs = self._obs.contiguous().clone()        # the env shifts its observation tensor in place
-            actions, values, log_probs = self.policy(obs)
-            clipped = torch.maximum(torch.minimum(actions, self.act_high), self.act_low)          # :216
+            if self._graph is not None:
+                self._g_obs.copy_(self._obs)            # the env shifts its observation tensor in place: keep this step's
+                self._graph.replay()
+                obs = self._g_obs
+                actions, values, log_probs, clipped = self._g_out
+            else:
+                obs = self._obs.contiguous().clone()
+                actions, values, log_probs, clipped = self._act(obs)
             new_obs, rewards, dones, truncated = env.step(clipped, auto_reset=True)
             rewards = rewards.clone()
             tr = truncated.nonzero().flatten()          # time-limit bootstrap (:236-245); rare (step 1200 of an episode)

@@ -29,10 +29,12 @@ def main():
     ap.add_argument("--iterations", type=int, default=2)
     ap.add_argument("--optimizer", default="DAG")
     ap.add_argument("--no-am-ppo", action="store_true")
+    ap.add_argument("--tf32", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     env = F16BatchedEnv(args.envs, mode="fp32", seed=0)
     cfg = AMPPOConfig(n_steps=args.n_steps, batch_size=args.batch_size, n_epochs=args.n_epochs, optimizer=args.optimizer,
-                      use_am_ppo=not args.no_am_ppo)
+                      use_am_ppo=not args.no_am_ppo, tf32=args.tf32, cuda_graph=not args.no_graph)
     algo = AMPPO(env, cfg)
     rows = []
     for it in range(args.iterations + 1):          # iteration 0 is the warm-up
@@ -52,7 +54,7 @@ def main():
     st = env.stats()
     print(json.dumps({
         "workload": "BASELINE configs[4]: AM-PPO (n_steps %d, LMA extractor, %s) rollout + update on GPU env observations" % (args.n_steps, args.optimizer),
-        "envs": args.envs, "n_steps": args.n_steps, "batch_size": args.batch_size, "n_epochs": args.n_epochs,
+        "tf32": args.tf32, "cuda_graph": not args.no_graph, "envs": args.envs, "n_steps": args.n_steps, "batch_size": args.batch_size, "n_epochs": args.n_epochs,
         "transitions_per_iteration": n, "rollout_s": roll, "update_s": upd,
         "rollout_env_steps_per_s": n / roll, "update_samples_per_s": n * args.n_epochs / upd,
         "overall_env_steps_per_s": n / (roll + upd), "last_stats": algo.last_stats,

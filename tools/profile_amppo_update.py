@@ -7,7 +7,7 @@ from f16_jsb_b200 import F16BatchedEnv
 from f16_jsb_b200.amppo import AMPPO, AMPPOConfig
 
 env = F16BatchedEnv(1024, mode="fp32")
-algo = AMPPO(env, AMPPOConfig(n_steps=64, batch_size=32768, n_epochs=1))
+algo = AMPPO(env, AMPPOConfig(n_steps=128, batch_size=131072, n_epochs=1))
 algo.collect_rollouts(); algo.train(); torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     algo.train(); torch.cuda.synchronize()

@@ -295,6 +295,10 @@ def run_ours(args):
 
 
 def main():
+    # exactly one line on stdout: whatever libraries print there (NCCL's version banner, ...) is sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)

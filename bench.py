@@ -172,7 +172,9 @@ def run_ours(args):
     total_envs = n_env * world
     lo, hi = shard_range(total_envs, rank, world)
     mode = args.mode
-    env = F16BatchedEnv(hi - lo, device=dev, mode=mode, seed=args.seed, env_id_base=lo)
+    env = F16BatchedEnv(hi - lo, device=dev, mode=mode, seed=args.seed, env_id_base=lo,
+                        ground_reactions={"default": None, "on": True, "off": False}[args.ground])
+    ground_main = env.ground_reactions
     env.reset()
     # actions resident in HBM before the timed region: a ring of distinct uniform action batches
     ring = 8
@@ -208,6 +210,21 @@ def run_ours(args):
                            dtype=torch.float64, device=dev)
     allreduce_stats(stats_t)                        # the only collective: rollout statistics over NVLink
     stats = stats_t.cpu().tolist()
+
+    # ---- the same rollout, continued with the other setting of the ground reactions (include/f16_b200.h)
+    from f16_jsb_b200 import _lib as _f16lib
+    _f16lib.check(env.lib.f16_set_ground_reactions(env._h, 0 if ground_main else 1), "f16_set_ground_reactions")
+    for w in range(3):
+        env.step(actions[w % ring], auto_reset=True)
+    g_steps = max(10, args.steps // 4)
+    barrier()
+    torch.cuda.synchronize(dev)
+    ev0.record()
+    for k in range(g_steps):
+        env.step(actions[k % ring], auto_reset=True)
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    ground_other_ms = max_over_ranks(ev0.elapsed_time(ev1), device=dev) / g_steps
 
     # ---- end to end through the public VecEnv API with host buffers
     env.close()
@@ -269,6 +286,10 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "envs_per_gpu": n_env, "total_envs": total_envs, "mode": mode,
                    "frames_per_env_step": 4, "fdm_frames_per_s": value * 4, "l2": "inputs larger than L2 (state+obs %.0f MB per GPU); no flush" % ((hi - lo) * (bpe - 22) / 2e6),
                    "parallelism": "env-sharded x%d, no data-path collective" % world,
+                   "ground_reactions": {"timed": "on" if ground_main else "off",
+                                        "note": "default of the mode (on in fp64, off in fp32); they only act inside the last env-step of a crash",
+                                        "other_setting_ms_per_step": ground_other_ms,
+                                        "other_setting_value": total_envs / (ground_other_ms * 1e-3)},
                    "rollout_stats": {"episodes": stats[0], "mean_return": (stats[1] / stats[0]) if stats[0] else None,
                                      "mean_length": (stats[2] / stats[0]) if stats[0] else None, "crashes": stats[3], "goals": stats[4],
                                      "truncations": stats[5]}},
@@ -307,6 +328,8 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--mode", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--ground", default="default", choices=["default", "on", "off"],
+                    help="ground reactions of the device-resident run (default: on in fp64, off in fp32)")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--e2e-warmup", type=int, default=600)
     ap.add_argument("--no-e2e-variants", dest="e2e_variants", action="store_false",

@@ -42,6 +42,8 @@ def load():
     L.f16_destroy.argtypes = [vp]
     L.f16_state_bytes.argtypes = [vp]
     L.f16_state_bytes.restype = C.c_size_t
+    L.f16_set_ground_reactions.argtypes = [vp, i32]
+    L.f16_get_ground_reactions.argtypes = [vp]
     L.f16_bind.argtypes = [vp] + [vp] * 8
     L.f16_bind_ring.argtypes = [vp] + [vp] * 8
     L.f16_bind_frames.argtypes = [vp] + [vp] * 7
@@ -106,7 +108,7 @@ def check(rc: int, what: str = "") -> None:
 
 
 EXPORTED_SYMBOLS = (
-    "f16_create", "f16_destroy", "f16_state_bytes", "f16_bind", "f16_bind_ring", "f16_bind_frames", "f16_set_done_list", "f16_obs_window", "f16_reset", "f16_step", "f16_step_begin", "f16_step_range", "f16_step_host",
+    "f16_create", "f16_destroy", "f16_state_bytes", "f16_set_ground_reactions", "f16_get_ground_reactions", "f16_bind", "f16_bind_ring", "f16_bind_frames", "f16_set_done_list", "f16_obs_window", "f16_reset", "f16_step", "f16_step_begin", "f16_step_range", "f16_step_host",
     "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states", "f16_unpack_states",
     "f16_set_env_step", "f16_get_snapshot", "f16_get_stats", "f16_stats_device_ptr", "f16_launch_count", "f16_num_state_fields",
     "f16_last_error", "f16_version")

@@ -28,6 +28,11 @@ class F16BatchedEnv:
     mode: "fp64" (parity: all model math in double) or "fp32" (throughput: float math, double
     kinematic state). Observations are (N, 10, 15) float32, row 0 oldest, row 9 newest.
 
+    ground_reactions: None keeps the mode's default - on in "fp64", off in "fp32". JSBSim's ground contacts
+    (aircraft/f16/f16.xml:85-215) can only act inside the last env-step of an episode that ends in a crash;
+    with them on, such a step is redone by a cold copy of the step that includes the contact and friction
+    forces (one crash in fifteen under random actions; see DESIGN.md for what it costs).
+
     obs_layout: "frame" keeps no observation history on the device: `obs` is the (N, 15) tensor of newest
     frames, 60 B written per env-step; the ten-frame windows then live in host memory (host_window.py,
     F16VecEnv's default) or in the frame-only rollout store (rollout.py). "stacked" (default) keeps a contiguous (N, 10, 15) tensor that the step kernel shifts in
@@ -38,7 +43,7 @@ class F16BatchedEnv:
 
     def __init__(self, num_envs: int, device=None, mode: str = "fp32", seed: int = 0,
                  with_terminal_obs: bool = True, env_id_base: int = 0, obs_layout: str = "stacked",
-                 done_list: bool = False):
+                 done_list: bool = False, ground_reactions=None):
         if not torch.cuda.is_available():
             raise _lib.F16Error("F16BatchedEnv needs a CUDA device: the F-16 env has no CPU fallback")
         self.lib = _lib.load()
@@ -53,6 +58,10 @@ class F16BatchedEnv:
         h = C.c_void_p()
         _lib.check(self.lib.f16_create(C.byref(h), self.num_envs, dev_index, self.mode), "f16_create")
         self._h = h
+        # ground reactions (include/f16_b200.h): None keeps the mode's default (on in fp64, off in fp32)
+        if ground_reactions is not None:
+            _lib.check(self.lib.f16_set_ground_reactions(h, 1 if ground_reactions else 0), "f16_set_ground_reactions")
+        self.ground_reactions = bool(self.lib.f16_get_ground_reactions(h))
         n = self.num_envs
         with torch.cuda.device(self.device):
             self.state = torch.zeros(self.lib.f16_state_bytes(h), dtype=torch.uint8, device=self.device)

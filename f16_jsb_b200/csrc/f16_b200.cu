@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -356,9 +357,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The env-step of one env with ground reactions (env_step_one<R, true>, f16_ground.cuh), from the state in HBM
+// back to HBM. Cold and deliberately not inlined: it is compiled with its own register allocation, so the
+// contact and friction code (double precision, ~4 kB of stack) costs the hot path one compare per frame.
+struct GroundStepOut { int flags; float reward, ep_ret; int32_t ep_len; };
+template <typename R>
+__device__ __noinline__ void env_step_ground(const StatePtrs<R> sp, int64_t e, const Tables<R>* T, float4 action, uint64_t seed,
+                                             uint64_t gid, int auto_reset, float* frame16, float* tframe16, GroundStepOut* out) {
+  Veh<R> s;
+  EnvScalars es;
+  load_veh(s, sp, e);
+  load_env(es, sp, e);
+  const float act[4] = {action.x, action.y, action.z, action.w};
+  float reward = 0.0f, ep_ret = 0.0f;
+  int32_t ep_len = 0;
+  out->flags = env_step_one<R, GROUND_FULL>(s, es, *T, msets_for<R>(), c_msets, c_snapshot, c_snapshot_props, act, seed, gid, auto_reset,
+                                     frame16, tframe16, &reward, &ep_ret, &ep_len);
+  out->reward = reward; out->ep_ret = ep_ret; out->ep_len = ep_len;
+  store_veh(s, sp, e);
+  store_env(es, sp, e);
+}
+
 #ifndef F16_PERSISTENT
 #define F16_PERSISTENT 0
 #endif
+
 #ifndef F16_PREFETCH_OBS
 #define F16_PREFETCH_OBS 1
 #endif
@@ -367,7 +390,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // += total warps). Warps never synchronise with each other after the staging barrier, so their
 // load / compute / store phases drift apart and overlap on each SM.
 enum { OBS_STACKED = 0, OBS_RING = 1, OBS_FRAME = 2 };
-template <typename R, int MINB, int OBS>
+template <typename R, int MINB, int OBS, bool GROUND>
 __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a) {
   __shared__ __align__(128) Tables<R> T;
   __shared__ __align__(16) float frame_s[WARPS][32][16];
@@ -428,8 +451,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
         pf.stride = (int)(left < 19200 ? (left & ~15) : 19200);
       }
 #endif
-      flags = env_step_one<R>(s, es, T, msets_for<R>(), c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
-                              frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len, pf);
+      flags = env_step_one<R, GROUND ? GROUND_DETECT : GROUND_OFF>(s, es, T, msets_for<R>(), c_msets, c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
+                                     frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len, pf);
+      if (GROUND && (flags & STEP_NEAR_GROUND)) {
+        // a contact point reached the ground (last env-step of a crash): redo the step with the contact forces
+        // from the state still in HBM; the cold copy stores the new state itself
+        GroundStepOut go;
+        env_step_ground<R>(sp, e, &T, make_float4(act[0], act[1], act[2], act[3]), a.seed, gid, a.auto_reset,
+                           frame_s[warp][lane], tframe_s[warp][lane], &go);
+        flags = go.flags; reward = go.reward; ep_ret = go.ep_ret; ep_len = go.ep_len;
+      } else {
+        store_veh(s, sp, e);
+        store_env(es, sp, e);
+      }
       a.reward[e] = reward;
       a.done[e] = (flags & STEP_DONE) ? 1 : 0;
       a.truncated[e] = (flags & STEP_TRUNCATED) ? 1 : 0;
@@ -460,8 +494,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
           w[5 + q] = make_uint4(__float_as_uint(r4.x), __float_as_uint(r4.y), __float_as_uint(r4.z), __float_as_uint(r4.w));
         }
       }
-      store_veh(s, sp, e);
-      store_env(es, sp, e);
     }
     flags_s[warp][lane] = (uint8_t)(flags & (STEP_ACTIVE | STEP_RESET | STEP_TERMINAL));
     __syncwarp();
@@ -576,6 +608,7 @@ struct f16_ctx {
   int ring = 0, ring_head = 0;       // observation layout (OBS_STACKED / OBS_RING / OBS_FRAME); ring layout: next slot to write
   f16_done_record* done_list = nullptr;   // frame layout: where the step kernel appends finished envs
   int32_t* done_count = nullptr;
+  int ground = 1;                         // ground reactions (f16_set_ground_reactions); default: on in FP64 mode, off in FP32 mode
 };
 
 template <typename R>
@@ -627,6 +660,7 @@ int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
   c->device = device;
   c->mode = mode;
   c->L = make_layout(n_envs, mode);
+  c->ground = mode == F16_MODE_FP64 ? 1 : 0;
   // constants shared by every context on this device
   MassSetT<double> ms[MS_COUNT];
   MassSetT<float> msf[MS_COUNT];
@@ -663,9 +697,10 @@ int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
     CUDA_OK(cudaMemcpyToSymbol(c_snapshot_props, c->snapshot + F16_NUM_STATE_FIELDS, 12 * sizeof(double)));
   }
   CUDA_OK(cudaMalloc(&c->actions_stage, (size_t)n_envs * F16_ACTION_DIM * sizeof(float)));
+
   CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
-  if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, 1, OBS_STACKED>, BLOCK, 0));
-  else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float, F16_MIN_BLOCKS_F32, OBS_STACKED>, BLOCK, 0));
+  if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, 1, OBS_STACKED, true>, BLOCK, 0));
+  else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float, F16_MIN_BLOCKS_F32, OBS_STACKED, false>, BLOCK, 0));
   if (c->ctas_per_sm < 1) c->ctas_per_sm = 1;
   *out = c;
   return 0;
@@ -683,6 +718,13 @@ int f16_destroy(f16_handle h) {
 }
 
 size_t f16_state_bytes(f16_handle h) { return h ? h->L.total : 0; }
+
+int f16_set_ground_reactions(f16_handle h, int on) {
+  if (!h) return fail("f16_set_ground_reactions: NULL handle");
+  h->ground = on ? 1 : 0;
+  return 0;
+}
+int f16_get_ground_reactions(f16_handle h) { return h ? h->ground : -1; }
 
 int f16_bind(f16_handle h, void* state, float* obs, float* reward, uint8_t* done, uint8_t* truncated, float* terminal_obs,
              float* ep_return, int32_t* ep_len) {
@@ -773,12 +815,18 @@ static int launch_step(f16_handle h, const float* actions, int auto_reset, int64
   int64_t want = (int64_t)h->num_sms * h->ctas_per_sm;
   const int64_t need = (tiles + WARPS - 1) / WARPS;
   unsigned grid = (unsigned)((F16_PERSISTENT && want < need) ? want : need);
+
   const cudaStream_t st = (cudaStream_t)stream;
+#define F16_LAUNCH_STEP_G(R, MINB, G)                                                                      \
+  do {                                                                                                    \
+    if (h->ring == OBS_FRAME) f16_step_kernel<R, MINB, OBS_FRAME, G><<<grid, BLOCK, 0, st>>>(a);          \
+    else if (h->ring == OBS_RING) f16_step_kernel<R, MINB, OBS_RING, G><<<grid, BLOCK, 0, st>>>(a);       \
+    else f16_step_kernel<R, MINB, OBS_STACKED, G><<<grid, BLOCK, 0, st>>>(a);                             \
+  } while (0)
 #define F16_LAUNCH_STEP(R, MINB)                                                                           \
   do {                                                                                                    \
-    if (h->ring == OBS_FRAME) f16_step_kernel<R, MINB, OBS_FRAME><<<grid, BLOCK, 0, st>>>(a);             \
-    else if (h->ring == OBS_RING) f16_step_kernel<R, MINB, OBS_RING><<<grid, BLOCK, 0, st>>>(a);          \
-    else f16_step_kernel<R, MINB, OBS_STACKED><<<grid, BLOCK, 0, st>>>(a);                                \
+    if (h->ground) F16_LAUNCH_STEP_G(R, MINB, true);                                                      \
+    else F16_LAUNCH_STEP_G(R, MINB, false);                                                               \
   } while (0)
   if (h->mode == F16_MODE_FP64) {
     F16_LAUNCH_STEP(double, 1);
@@ -793,6 +841,7 @@ static int launch_step(f16_handle h, const float* actions, int auto_reset, int64
     else F16_LAUNCH_STEP(float, F16_MIN_BLOCKS_F32);
   }
 #undef F16_LAUNCH_STEP
+#undef F16_LAUNCH_STEP_G
   g_launches++;
   h->env_steps += (double)count;
   CUDA_OK(cudaGetLastError());

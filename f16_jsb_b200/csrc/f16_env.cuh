@@ -180,42 +180,33 @@ F16_HD void env_reset_one(Veh<R>& s, EnvScalars& es, const double* snapshot, con
   es.ep_len = 0;
 }
 
-enum { STEP_ACTIVE = 1, STEP_RESET = 2, STEP_TERMINAL = 4, STEP_DONE = 8, STEP_TRUNCATED = 16, STEP_CRASH = 32, STEP_GOAL = 64 };
+enum { STEP_ACTIVE = 1, STEP_RESET = 2, STEP_TERMINAL = 4, STEP_DONE = 8, STEP_TRUNCATED = 16, STEP_CRASH = 32, STEP_GOAL = 64,
+       STEP_NEAR_GROUND = 128 };
 
-// One env-step. On return frame16 is the newest row of the env's observation stack (or, if the env
-// auto-reset, the reset frame, with tframe16 holding the terminal step's newest row).
+// ------------------------------------------------------------------------------------ one env-step
+// On return frame16 is the newest row of the env's observation stack (or, if the env auto-reset, the
+// reset frame, with tframe16 holding the terminal step's newest row).
+//
+// Ground reactions (f16_ground.cuh), three instantiations. GROUND_OFF: no ground at all (the FP32
+// throughput mode's default: identical code to a model without contacts). GROUND_DETECT (hot): never
+// includes ground forces, but if a contact point reached the surface in some frame, and that can have
+// changed anything the caller will see, it returns STEP_NEAR_GROUND with s / es / the outputs in an
+// unspecified state and the caller redoes the step from the env's saved state with GROUND_FULL (cold: a
+// separate, non-inlined function on the device), where every touching frame has its accelerations
+// replaced by ground_fix(). "Can have changed": the forces of
+// frame k act on the rates from frame k+1 and on the position from frame k+2, so a first contact in the
+// last frame only changes the stored accelerations - irrelevant when the env is reset in this very step.
+//
 // Optional L2 prefetch issued by each lane just before the last FDM frame: the caller's observation
 // rows are needed right after that frame, and one frame of compute covers the HBM latency.
 struct PrefetchHint { const char* ptr; int count; int stride; };   // count < 0: one bulk (TMA) prefetch of `stride` bytes
 
+// observation frame, reward, termination, auto-reset - everything after the last frame (jsbsim_gym.py:235-263)
 template <typename R>
-F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const MassSetT<R>* msets, const double* snapshot,
-                        const double* snapshot_props, const float* act, uint64_t seed, uint64_t env_id, int auto_reset,
-                        float* frame16, float* tframe16, float* reward_out, float* ep_ret_out, int32_t* ep_len_out,
-                        PrefetchHint pf = PrefetchHint{nullptr, 0, 0}) {
-  // action -> fcs/*-cmd-norm (jsbsim_gym.py:216-222): float32 -> double widening, no clipping
-  Cmd<R> cmd = {(R)act[0], (R)act[1], (R)act[2], (R)act[3]};
-  es.step += 1;
-  // 4 FDM frames (jsbsim_gym.py:225-232); tanks stay at 1000 lb and gear at 0 by construction
-  FrameObs<R> fo;
-  FrameCfg cfg = {kDt, 0.0, MS_FLIGHT};
-#ifdef __CUDA_ARCH__
-#pragma unroll 1
-#endif
-  for (int k = 0; k < 4; ++k) {
-#ifdef __CUDA_ARCH__
-#ifndef F16_PREFETCH_AT_FRAME
-#define F16_PREFETCH_AT_FRAME 3
-#endif
-    if (k == F16_PREFETCH_AT_FRAME) {
-      if (pf.count < 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.ptr), "r"(pf.stride) : "memory");
-      for (int i = 0; i < pf.count; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf.ptr + (size_t)i * pf.stride));
-    }
-#endif
-    fdm_frame<R, false>(s, T, msets, cfg, cmd, es.step == 1 && k == 0, fo);
-  }
-
-  // observation frame, reward, termination - all on the float32 frame (jsbsim_gym.py:237-261)
+F16_HD int env_step_epilogue(Veh<R>& s, EnvScalars& es, const FrameObs<R>& fo, const double* snapshot, const double* snapshot_props,
+                             uint64_t seed, uint64_t env_id, int auto_reset, float* frame16, float* tframe16, float* reward_out,
+                             float* ep_ret_out, int32_t* ep_len_out) {
+  // all on the float32 frame (jsbsim_gym.py:237-261)
   float o[12];
   frame_from_fdm<R>(s, fo, o);
   float reward = 0.0f;
@@ -252,6 +243,50 @@ F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const Mas
       env_reset_one<R>(s, es, snapshot, snapshot_props, g, frame16);
     }
   }
+  return flags;
+}
+
+enum { GROUND_OFF = 0, GROUND_DETECT = 1, GROUND_FULL = 2 };
+template <typename R, int GMODE>
+F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const MassSetT<R>* msets, const MassSetT<double>* msets_d,
+                        const double* snapshot, const double* snapshot_props, const float* act, uint64_t seed, uint64_t env_id,
+                        int auto_reset, float* frame16, float* tframe16, float* reward_out, float* ep_ret_out, int32_t* ep_len_out,
+                        PrefetchHint pf = PrefetchHint{nullptr, 0, 0}) {
+  // action -> fcs/*-cmd-norm (jsbsim_gym.py:216-222): float32 -> double widening, no clipping
+  Cmd<R> cmd = {(R)act[0], (R)act[1], (R)act[2], (R)act[3]};
+  es.step += 1;
+  // 4 FDM frames (jsbsim_gym.py:225-232); tanks stay at 1000 lb and gear at 0 by construction
+  FrameObs<R> fo;
+  FrameCfg cfg = {kDt, 0.0, MS_FLIGHT};
+  constexpr bool GROUND = GMODE == GROUND_FULL;
+  GroundMem gm;      // friction multipliers of the contacts (GROUND_FULL only; contact is confined to one env-step)
+  if (GROUND) gm.started = 0;
+  int first_touch = 4;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 4; ++k) {
+#ifdef __CUDA_ARCH__
+#ifndef F16_PREFETCH_AT_FRAME
+#define F16_PREFETCH_AT_FRAME 3
+#endif
+    if (k == F16_PREFETCH_AT_FRAME) {
+      if (pf.count < 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.ptr), "r"(pf.stride) : "memory");
+      for (int i = 0; i < pf.count; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf.ptr + (size_t)i * pf.stride));
+    }
+#endif
+    const bool first = es.step == 1 && k == 0;
+    fdm_frame<R, false, GMODE != GROUND_OFF>(s, T, msets, cfg, cmd, first, fo);
+    if (GROUND) {
+      if (fo.may_touch) ground_fix<R>(s, fo, msets_d[first ? MS_FLIGHT_FIRST : MS_FLIGHT], gm);
+      else if (gm.started) { for (int i = 0; i < 3 * kNumStructure; ++i) gm.lm[i] = 0.0; }   // FGLGear: not compressed
+    } else if (GMODE == GROUND_DETECT) {
+      if (fo.may_touch && first_touch == 4) first_touch = k;
+    }
+  }
+  const int flags = env_step_epilogue<R>(s, es, fo, snapshot, snapshot_props, seed, env_id, auto_reset, frame16, tframe16,
+                                         reward_out, ep_ret_out, ep_len_out);
+  if (GMODE == GROUND_DETECT && first_touch < 4 && !(first_touch == 3 && (flags & STEP_RESET))) return STEP_ACTIVE | STEP_NEAR_GROUND;
   return flags;
 }
 

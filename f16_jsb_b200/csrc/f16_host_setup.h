@@ -72,12 +72,22 @@ V3h compute_mass_set(const double contents[4], const V3h& cg_prev, MassSet* ms) 
   ms->r_rp[0] = rp.x; ms->r_rp[1] = rp.y; ms->r_rp[2] = rp.z;
   ms->r_eye[0] = ey.x; ms->r_eye[1] = ey.y; ms->r_eye[2] = ey.z;
   ms->r_thr[0] = th.x; ms->r_thr[1] = th.y; ms->r_thr[2] = th.z;
+  ms->cg[0] = cg.x; ms->cg[1] = cg.y; ms->cg[2] = cg.z;
+  // the ground-reaction path is entered below kGroundReach: every contact must lie inside that sphere
+  const double sl[n_structure][3] = F16_STRUCT_LOC;
+  for (int i = 0; i < n_structure; ++i) {
+    V3h r = s2b(cg, {sl[i][0], sl[i][1], sl[i][2]});
+    if (std::sqrt(r.x * r.x + r.y * r.y + r.z * r.z) > kGroundReach - 1.0) { fprintf(stderr, "f16: contact %d is out of kGroundReach\n", i); abort(); }
+    ms->r_ct[i][0] = r.x; ms->r_ct[i][1] = r.y; ms->r_ct[i][2] = r.z;
+  }
   return cg;
 }
 inline void convert_mass_set(const MassSetT<double>& a, MassSetT<float>* b) {
   b->mass = (float)a.mass; b->inv_mass = (float)a.inv_mass;
   for (int i = 0; i < 9; ++i) { b->J[i] = (float)a.J[i]; b->Jinv[i] = (float)a.Jinv[i]; }
-  for (int i = 0; i < 3; ++i) { b->r_rp[i] = (float)a.r_rp[i]; b->r_eye[i] = (float)a.r_eye[i]; b->r_thr[i] = (float)a.r_thr[i]; }
+  for (int i = 0; i < 3; ++i) { b->r_rp[i] = (float)a.r_rp[i]; b->r_eye[i] = (float)a.r_eye[i]; b->r_thr[i] = (float)a.r_thr[i]; b->cg[i] = (float)a.cg[i]; }
+  for (int i = 0; i < 7; ++i)
+    for (int k = 0; k < 3; ++k) b->r_ct[i][k] = (float)a.r_ct[i][k];
 }
 void build_mass_sets(MassSet out[MS_COUNT]) {
   double ic[4], fl[4];

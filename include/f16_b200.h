@@ -44,6 +44,16 @@ int f16_destroy(f16_handle h);
 /* Bytes of device memory the caller must provide for the structure-of-arrays state. */
 size_t f16_state_bytes(f16_handle h);
 
+/* Ground reactions: JSBSim's FGGroundReactions / FGLGear for the seven STRUCTURE contacts of
+ * aircraft/f16/f16.xml:137-214 plus the friction solve of FGAccelerations (the three BOGEY contacts are
+ * retracted by jsbsim_gym.py:230-231). They can only act inside the last env-step of an episode that ends
+ * in a crash (termination below 10 m, jsbsim_gym.py:240): about one crash in fifteen under random actions,
+ * where they change the rates and the angles of attack / sideslip of the terminal frame; rewards move by
+ * ~1e-5 and done flags do not change. Default: on in F16_MODE_FP64 (parity), off in F16_MODE_FP32
+ * (throughput: the step kernel is then the instantiation without any ground code). */
+int f16_set_ground_reactions(f16_handle h, int on);
+int f16_get_ground_reactions(f16_handle h);
+
 /* Bind caller-owned device buffers. state: f16_state_bytes() bytes, 256-byte aligned.
  * obs: N x 10 x 15 float (row 0 oldest, row 9 newest; jsbsim_gym.py:150,235,263).
  * reward: N float. done/truncated: N uint8. terminal_obs: N x 10 x 15 float or NULL.

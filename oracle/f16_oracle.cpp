@@ -516,10 +516,29 @@ struct FDM {
   double bi2vel = 0, ci2vel = 0;
   V3 aero_vFw, aero_vForces, aero_vMoments;
   double aero_fval[64];
+  // ---- FGGroundReactions / FGLGear (contacts of f16.xml:85-215)
+  struct LagrangeMultiplier { V3 ForceJacobian, LeverArm; double Min = 0, Max = 0, value = 0; };
+  enum { ftRoll = 0, ftSide = 1, ftDynamic = 2 };
+  struct Contact {
+    bool WOW = false, lastWOW = false, StaticFriction = false;
+    double compressLength = 0, compressSpeed = 0, StrutForce = 0;
+    V3 vFn, vGroundNormal, vGroundWhlVel, vWhlVelVec, vActingXYZn;
+    M33 mT;
+    LagrangeMultiplier LMultiplier[3];
+  } gear[modelk::n_contacts];
+  struct {
+    double TotalDeltaT = 0;
+    M33 Tb2l, Tec2l, Tec2b;
+    V3 PQR, UVW, vXYZcg;
+    Location location;
+  } gr_in;
+  V3 gr_vForces, gr_vMoments;
+  LagrangeMultiplier* multipliers[3 * modelk::n_contacts];
+  int n_multipliers = 0;
   // ---- FGAircraft
   V3 ac_vForces, ac_vMoments;
   // ---- FGAccelerations
-  V3 vPQRidot, vUVWidot, vUVWdot, vBodyAccel;
+  V3 vPQRidot, vPQRdot, vUVWidot, vUVWdot, vBodyAccel, vFrictionForces, vFrictionMoments;
 
   FDM() {
     for (int i = 0; i < 4; i++) tank_contents[i] = modelk::tank_contents0[i];
@@ -957,23 +976,226 @@ struct FDM {
     aero_vMoments = vMomentsMRC + aero_in.RPBody * aero_vForces;   // M = r x F about the CG
   }
 
+  // ================================================================ FGGroundReactions / FGLGear
+  // [UPSTREAM] FGLGear::GetBodyForces and helpers for the contacts of f16.xml:85-215, terrain =
+  // FGDefaultGroundCallback (WGS84 ellipsoid, elevation 0, at rest in ECEF). The three BOGEY contacts
+  // are retractable and the reference forces gear/gear-pos-norm to 0 before every run()
+  // (jsbsim_gym.py:230-231), so in flight only their "gear up" branch executes; a BOGEY that is
+  // down AND compressed (tyre slip, brakes, steering) cannot occur on the reference's path (gear is
+  // only down during run_ic at 5000 ft) and is reported instead of modelled.
+  void load_groundreactions() {
+    gr_in.TotalDeltaT = dT;
+    gr_in.Tb2l = Tb2l;
+    gr_in.Tec2l = Tec2l;
+    gr_in.Tec2b = Tec2b;
+    gr_in.PQR = VState.vPQR;
+    gr_in.UVW = VState.vUVW;
+    gr_in.vXYZcg = vXYZcg;
+    gr_in.location = VState.vLocation;
+  }
+  static V3 mat_col_mul(const M33& m, const V3& a) { return m * a; }
+  // FGLGear::GetBodyForces for contact i; returns the body force, *moment receives FGForce::GetMoments
+  V3 gear_body_forces(int i, V3* moment) {
+    const modelk::ContactDef& def = modelk::contacts[i];
+    Contact& c = gear[i];
+    const V3 vXYZn(def.loc[0], def.loc[1], def.loc[2]);
+    double gearPos = 1.0;
+    c.vFn = V3();
+    if (def.retractable) gearPos = P.gear_gear_pos_norm;     // GetGearUnitPos
+    c.vActingXYZn = vXYZn;
+    if (gearPos > 0.99) {   // gear down (always, for a STRUCTURE contact)
+      // Ts2b * (vXYZn - vXYZcg): structural inches -> body feet
+      V3 d = vXYZn - gr_in.vXYZcg;
+      V3 vWhlBodyVec(-inchtoft * d(1), inchtoft * d(2), -inchtoft * d(3));
+      V3 vLocalGear = gr_in.Tb2l * vWhlBodyVec;
+      // FGLocation::LocalToLocation + FGDefaultGroundCallback::GetAGLevel
+      Location gearLoc;
+      gearLoc.mECLoc = gr_in.location.mTl2ec * vLocalGear + gr_in.location.mECLoc;
+      gearLoc.ComputeDerived();
+      double cosLat = std::cos(gearLoc.mGeodLat);
+      V3 normal(cosLat * std::cos(gearLoc.mLon), cosLat * std::sin(gearLoc.mLon), std::sin(gearLoc.mGeodLat));
+      double height = gearLoc.GeodeticAltitude - 0.0;
+      V3 vWhlDisplVec;
+      if (height < 0.0) {
+        c.WOW = true;
+        c.vGroundNormal = gr_in.Tec2b * normal;
+        double normalZ = (gr_in.Tec2l * normal)(3);
+        if (def.bogey) {
+          std::fprintf(stderr, "f16 oracle: BOGEY contact %s compressed - not on the reference's path\n", def.name);
+          c.WOW = false;
+        } else {
+          double nn = normal(1) * normal(1) + normal(2) * normal(2) + normal(3) * normal(3);
+          c.compressLength = height * normalZ / nn;
+          vWhlDisplVec = c.compressLength * c.vGroundNormal;
+        }
+      } else {
+        c.WOW = false;
+      }
+      if (c.WOW) {
+        V3 vWhlContactVec = vWhlBodyVec + vWhlDisplVec;
+        // vActingXYZn = vXYZn + Tb2s * vWhlDisplVec (body feet -> structural inches)
+        c.vActingXYZn = vXYZn + V3(-12.0 * vWhlDisplVec(1), 12.0 * vWhlDisplVec(2), -12.0 * vWhlDisplVec(3));
+        V3 vBodyWhlVel = gr_in.PQR * vWhlContactVec;
+        vBodyWhlVel += gr_in.UVW;                            // terrain velocity is zero
+        c.vWhlVelVec = vBodyWhlVel;                          // mTGear = identity (no strut angles in the file)
+        // ComputeGroundFrame, SteerAngle = 0
+        V3 roll(1.0, 0.0, 0.0);
+        V3 side = c.vGroundNormal * roll;
+        double rn = roll(1) * c.vGroundNormal(1) + roll(2) * c.vGroundNormal(2) + roll(3) * c.vGroundNormal(3);
+        roll -= rn * c.vGroundNormal;
+        { double m = roll.Magnitude(); if (m != 0.0) roll = roll / m; }      // FGColumnVector3::Normalize
+        { double m = side.Magnitude(); if (m != 0.0) side = side / m; }
+        c.mT = M33(roll(1), side(1), c.vGroundNormal(1),
+                   roll(2), side(2), c.vGroundNormal(2),
+                   roll(3), side(3), c.vGroundNormal(3));
+        c.vGroundWhlVel = c.mT.Transposed() * vBodyWhlVel;
+        c.compressSpeed = -c.vGroundWhlVel(3);               // ctSTRUCTURE: along the ground normal
+        // ComputeVerticalStrutForce: linear spring, linear damping (same coefficient on rebound)
+        double springForce = -c.compressLength * def.spring;
+        double dampForce = -c.compressSpeed * def.damping;
+        c.StrutForce = std::min(springForce + dampForce, 0.0);
+        c.vFn(3) = -c.StrutForce;                            // ctSTRUCTURE: normal to the ground
+        // ComputeJacobian
+        const double staticFFactor = 1.0;                    // FGSurface defaults
+        if (c.vGroundWhlVel.Magnitude(1, 2) > 1E-3) {
+          V3 velocityDirection = c.vGroundWhlVel;
+          c.StaticFriction = false;
+          velocityDirection(3) = 0.0;
+          { double m = velocityDirection.Magnitude(); if (m != 0.0) velocityDirection = velocityDirection / m; }
+          LagrangeMultiplier& L = c.LMultiplier[ftDynamic];
+          L.ForceJacobian = c.mT * velocityDirection;
+          L.LeverArm = vWhlContactVec;
+          L.Max = 0.0;
+          L.Min = -std::fabs(staticFFactor * def.dynamic_f * c.vFn(3));
+          L.value = constrain(L.Min, L.value, L.Max);
+          multipliers[n_multipliers++] = &L;
+        } else {
+          c.StaticFriction = true;
+          LagrangeMultiplier& Lr = c.LMultiplier[ftRoll];
+          LagrangeMultiplier& Ls = c.LMultiplier[ftSide];
+          Lr.ForceJacobian = c.mT * V3(1.0, 0.0, 0.0);
+          Ls.ForceJacobian = c.mT * V3(0.0, 1.0, 0.0);
+          Lr.LeverArm = vWhlContactVec;
+          Ls.LeverArm = vWhlContactVec;
+          Lr.Max = std::fabs(staticFFactor * def.static_f * c.vFn(3));
+          Ls.Max = Lr.Max;
+          Lr.Min = -Lr.Max;
+          Ls.Min = -Ls.Max;
+          Lr.value = constrain(Lr.Min, Lr.value, Lr.Max);
+          Ls.value = constrain(Ls.Min, Ls.value, Ls.Max);
+          multipliers[n_multipliers++] = &Lr;
+          multipliers[n_multipliers++] = &Ls;
+        }
+      } else {   // not compressed
+        c.compressLength = 0.0;
+        c.compressSpeed = 0.0;
+        c.StrutForce = 0.0;
+        c.LMultiplier[ftRoll].value = 0.0;
+        c.LMultiplier[ftSide].value = 0.0;
+        c.LMultiplier[ftDynamic].value = 0.0;
+        c.vWhlVelVec(1) -= 13.0 * gr_in.TotalDeltaT;         // wheel spin-down (no effect on forces)
+        if (c.vWhlVelVec(1) < 0.0) c.vWhlVelVec(1) = 0.0;
+      }
+    } else if (gearPos < 0.01) {   // gear up
+      c.WOW = false;
+      c.vWhlVelVec = V3();
+    }
+    c.lastWOW = c.WOW;             // CrashDetect only reports
+    // FGForce::GetBodyForces: vFb = mT * vFn; vM = StructuralToBody(vActingXYZn) x vFb
+    V3 vFb = c.WOW ? c.mT * c.vFn : V3();
+    *moment = StructuralToBody(c.vActingXYZn) * vFb;
+    return vFb;
+  }
+  void run_groundreactions() {
+    gr_vForces = V3();
+    gr_vMoments = V3();
+    n_multipliers = 0;
+    for (int i = 0; i < modelk::n_contacts; i++) {
+      V3 m;
+      gr_vForces += gear_body_forces(i, &m);
+      gr_vMoments += m;
+    }
+  }
+
   // ================================================================ FGAircraft / FGAccelerations
   void run_aircraft() {
     ac_vForces = V3();
     ac_vMoments = V3();
     ac_vForces += aero_vForces;
-    ac_vForces += prop_vForces;      // ground, external and buoyant reactions are zero in flight
+    ac_vForces += prop_vForces;
+    ac_vForces += gr_vForces;        // external (pushback, hook: magnitude 0) and buoyant reactions are zero
     ac_vMoments += aero_vMoments;
     ac_vMoments += prop_vMoments;
+    ac_vMoments += gr_vMoments;
+  }
+  // [UPSTREAM] FGAccelerations::CalculateFrictionForces: projected Gauss-Seidel on the Lagrange
+  // multipliers registered by the contacts, <= 50 sweeps, stops when the summed change is < 1e-5
+  void resolve_friction_forces(double dt) {
+    const int n = n_multipliers;
+    vFrictionForces = V3();
+    vFrictionMoments = V3();
+    if (!n) return;
+    std::vector<double> a((size_t)n * n), rhs(n);
+    auto dot = [](const V3& x, const V3& y) { return x(1) * y(1) + x(2) * y(2) + x(3) * y(3); };
+    for (int i = 0; i < n; i++) {
+      V3 U = multipliers[i]->ForceJacobian;
+      V3 r = multipliers[i]->LeverArm;
+      V3 v1 = U / Mass;
+      V3 v2 = mJinv * (r * U);
+      for (int j = 0; j < i; j++) a[i * n + j] = a[j * n + i];
+      for (int j = i; j < n; j++) {
+        U = multipliers[j]->ForceJacobian;
+        r = multipliers[j]->LeverArm;
+        a[i * n + j] = dot(U, v1 + v2 * r);
+      }
+    }
+    V3 vdot = vUVWdot;
+    if (dt > 0.) vdot += VState.vUVW / dt;          // terrain at rest
+    V3 wdot = vPQRdot;
+    if (dt > 0.) wdot += VState.vPQR / dt;
+    for (int i = 0; i < n; i++) {
+      double d = a[i * n + i];
+      V3 U = multipliers[i]->ForceJacobian;
+      V3 r = multipliers[i]->LeverArm;
+      rhs[i] = -dot(U, vdot + wdot * r) / d;
+      for (int j = 0; j < n; j++) a[i * n + j] /= d;
+    }
+    for (int iter = 0; iter < 50; iter++) {
+      double norm = 0.;
+      for (int i = 0; i < n; i++) {
+        double lambda0 = multipliers[i]->value;
+        double dlambda = rhs[i];
+        for (int j = 0; j < n; j++) dlambda -= a[i * n + j] * multipliers[j]->value;
+        multipliers[i]->value = constrain(multipliers[i]->Min, lambda0 + dlambda, multipliers[i]->Max);
+        dlambda = multipliers[i]->value - lambda0;
+        norm += std::fabs(dlambda);
+      }
+      if (norm < 1E-5) break;
+    }
+    for (int i = 0; i < n; i++) {
+      double lambda = multipliers[i]->value;
+      V3 F = lambda * multipliers[i]->ForceJacobian;
+      vFrictionForces += F;
+      vFrictionMoments += multipliers[i]->LeverArm * F;
+    }
+    V3 accel = vFrictionForces / Mass;
+    V3 omegadot = mJinv * vFrictionMoments;
+    vBodyAccel += accel;
+    vUVWdot += accel;
+    vUVWidot += Tb2i * accel;
+    vPQRdot += omegadot;
+    vPQRidot += omegadot;
   }
   void run_accelerations() {
     const V3& wp = prop_in.vOmegaPlanet;
     vPQRidot = mJinv * (ac_vMoments - VState.vPQRi * (mJ * VState.vPQRi));
+    vPQRdot = vPQRidot - VState.vPQRi * (Ti2b * wp);
     vBodyAccel = ac_vForces / Mass;
     vUVWdot = vBodyAccel - (VState.vPQR + 2.0 * (Ti2b * wp)) * VState.vUVW;
     vUVWdot -= Ti2b * (wp * (wp * VState.vInertialPosition));
     vUVWdot += Tec2b * vGravAccel;
     vUVWidot = Tb2i * vBodyAccel + Tec2i * vGravAccel;
+    resolve_friction_forces(dT);
   }
 
   // ================================================================ FGFDMExec::Run / RunIC
@@ -987,6 +1209,7 @@ struct FDM {
     load_auxiliary();  run_auxiliary();
     load_propulsion();  run_propulsion();
     load_aerodynamics();  run_aerodynamics();
+    load_groundreactions();  run_groundreactions();
     run_aircraft();
     run_accelerations();
     return true;
@@ -1066,6 +1289,22 @@ struct FDM {
     if (name == "moments/m-aero-lbsft") { *out = aero_vMoments(2); return true; }
     if (name == "moments/n-aero-lbsft") { *out = aero_vMoments(3); return true; }
     if (name == "moments/m-prop-lbsft") { *out = prop_vMoments(2); return true; }
+    if (name == "forces/fbx-gear-lbs") { *out = gr_vForces(1); return true; }
+    if (name == "forces/fby-gear-lbs") { *out = gr_vForces(2); return true; }
+    if (name == "forces/fbz-gear-lbs") { *out = gr_vForces(3); return true; }
+    if (name == "moments/l-gear-lbsft") { *out = gr_vMoments(1); return true; }
+    if (name == "moments/m-gear-lbsft") { *out = gr_vMoments(2); return true; }
+    if (name == "moments/n-gear-lbsft") { *out = gr_vMoments(3); return true; }
+    if (name == "gear/num-friction-multipliers") { *out = (double)n_multipliers; return true; }   // not a JSBSim property
+    if (name.rfind("gear/unit[", 0) == 0) {
+      int i = std::atoi(name.c_str() + 10);
+      if (i >= 0 && i < modelk::n_contacts) {
+        std::string tail = name.substr(name.find(']') + 1);
+        if (tail == "/WOW") { *out = gear[i].WOW ? 1.0 : 0.0; return true; }
+        if (tail == "/compression-ft") { *out = gear[i].compressLength; return true; }
+        if (tail == "/compression-velocity-fps") { *out = gear[i].compressSpeed; return true; }
+      }
+    }
     if (name == "simulation/frame") { *out = (double)Frame; return true; }
     if (name == "simulation/epa-rad") { *out = epa; return true; }
     if (name.rfind("aero/coefficient/", 0) == 0) {
@@ -1118,6 +1357,50 @@ void pack_state(const FDM& f, double* s) {
   s[F16S_YAW_I] = f.M.fcs_yaw_load_pid.I_out_total;
   s[F16S_N2] = f.N2;
   s[F16S_AUG] = f.Augmentation ? 1.0 : 0.0;
+}
+
+// Inverse of pack_state, for tests that need the oracle in a synthetic state (ground contact at a chosen
+// attitude and speed). The FDM must already be in flight configuration (reset + at least one env-step:
+// engine running, gear up, tanks at 1000 lb, steady CG); only the packed fields are overwritten and the
+// values Propagate derives from them (vQtrndot) are refreshed. Everything else is recomputed by the next Run().
+void unpack_state(FDM& f, const double* s) {
+  auto& V = f.VState;
+  for (int i = 0; i < 4; i++) V.qAttitudeECI.d[i] = s[F16S_Q0 + i];
+  for (int i = 0; i < 3; i++) {
+    V.vPQRi.v[i] = s[F16S_WI_X + i];
+    V.vInertialPosition.v[i] = s[F16S_RI_X + i];
+    V.vInertialVelocity.v[i] = s[F16S_VI_X + i];
+    V.dqInertialVelocity[0].v[i] = s[F16S_VI1_X + i];
+    V.dqInertialVelocity[1].v[i] = s[F16S_VI2_X + i];
+    f.vUVWidot.v[i] = s[F16S_AI0_X + i];
+    V.dqUVWidot[0].v[i] = s[F16S_AI1_X + i];
+    f.vPQRidot.v[i] = s[F16S_WDOT_X + i];
+    f.vBodyAccel.v[i] = s[F16S_ABODY_X + i];
+    f.vAeroPQR.v[i] = s[F16S_PQR_X + i];
+  }
+  f.epa = s[F16S_EPA];
+  V.vQtrndot = V.qAttitudeECI.GetQDot(V.vPQRi);
+  f.alpha = s[F16S_ALPHA];
+  f.Mach = s[F16S_MACH];
+  f.vcas = s[F16S_VC_KTS] * ktstofps;
+  f.Vground = s[F16S_VG];
+  f.vPilotAccelN.v[1] = s[F16S_NPY];
+  f.vPilotAccelN.v[2] = s[F16S_NPZ];
+  f.P.fcs_tef_control = s[F16S_TEF];
+  f.P.fcs_left_aileron_pos_norm = s[F16S_AIL];
+  f.P.fcs_elevator_pos_norm = s[F16S_ELEV];
+  f.P.fcs_speedbrake_pos_deg = s[F16S_SB_DEG];
+  f.M.fcs_roll_rate_pid.Input_prev = s[F16S_ROLL_INPREV];
+  f.M.fcs_roll_rate_pid.I_out_total = s[F16S_ROLL_I];
+  f.M.fcs_g_load_pid.Input_prev = s[F16S_PITCH_INPREV];
+  f.M.fcs_g_load_pid.I_out_total = s[F16S_PITCH_I];
+  f.M.fcs_yaw_load_pid.Input_prev = s[F16S_YAW_INPREV];
+  f.M.fcs_yaw_load_pid.I_out_total = s[F16S_YAW_I];
+  f.N2 = s[F16S_N2];
+  f.N2norm = (f.N2 - modelk::idlen2) / (modelk::maxn2 - modelk::idlen2);
+  f.Augmentation = s[F16S_AUG] > 0.5;
+  for (int i = 0; i < modelk::n_contacts; i++)
+    for (int k = 0; k < 3; k++) f.gear[i].LMultiplier[k].value = 0.0;
 }
 
 // ------------------------------------------------------------------ env layer (jsbsim_gym/jsbsim_gym.py restated)
@@ -1232,6 +1515,7 @@ int f16o_fdm_run_ic(void* h) { return ((FDM*)h)->RunIC() ? 0 : -1; }
 int f16o_fdm_run(void* h) { return ((FDM*)h)->Run() ? 0 : -1; }
 int f16o_num_state_fields(void) { return F16_NUM_STATE_FIELDS; }
 void f16o_fdm_pack_state(void* h, double* out) { pack_state(*(FDM*)h, out); }
+void f16o_fdm_unpack_state(void* h, const double* in) { unpack_state(*(FDM*)h, in); }
 
 // ---- env-shaped handle (JSBSimEnv + PositionReward restated)
 void* f16o_env_create(void) { return new Env(); }

@@ -39,6 +39,7 @@ def lib():
         L.f16o_fdm_run_ic.argtypes = [C.c_void_p]
         L.f16o_fdm_run.argtypes = [C.c_void_p]
         L.f16o_fdm_pack_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.f16o_fdm_unpack_state.argtypes = [C.c_void_p, C.c_void_p]
         L.f16o_env_create.restype = C.c_void_p
         L.f16o_env_destroy.argtypes = [C.c_void_p]
         L.f16o_env_fdm.restype = C.c_void_p
@@ -92,6 +93,13 @@ class OracleFDM:
         out = np.zeros(n, dtype=np.float64)
         lib().f16o_fdm_pack_state(self._h, out.ctypes.data)
         return out
+
+
+    def unpack_state(self, packed) -> None:
+        """Overwrite the packed fields (include/f16_state_fields.h); the FDM must be in flight configuration."""
+        p = np.ascontiguousarray(packed, dtype=np.float64)
+        assert p.shape == (lib().f16o_num_state_fields(),)
+        lib().f16o_fdm_unpack_state(self._h, p.ctypes.data)
 
 
 class OracleEnv:

@@ -53,7 +53,7 @@ class HostSim:
         d = os.path.join(ROOT, "tests", "hostsim")
         so = os.path.join(d, "libf16hostsim.so")
         srcs = [os.path.join(d, "f16_hostsim.cpp")] + [os.path.join(ROOT, "f16_jsb_b200", "csrc", f) for f in
-                                                      ("f16_model.cuh", "f16_env.cuh", "f16_host_setup.h", "f16_model_data.h")]
+                                                      ("f16_model.cuh", "f16_ground.cuh", "f16_env.cuh", "f16_host_setup.h", "f16_model_data.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-D_GNU_SOURCE",
                                    "-o", so, srcs[0]])

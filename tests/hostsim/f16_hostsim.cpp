@@ -67,10 +67,24 @@ int hs_env_step(void* h, const float* action, int auto_reset, uint64_t seed, uin
   float fr[16], tfr[16], ep_ret = 0;
   int32_t ep_len = 0;
   int flags;
-  if (e->mode == 0)
-    flags = env_step_one<double>(e->sd, e->es, c.Td, c.ms, c.snap, c.snap + F16_NUM_STATE_FIELDS, action, seed, env_id, auto_reset, fr, tfr, reward, &ep_ret, &ep_len);
-  else
-    flags = env_step_one<float>(e->sf, e->es, c.Tf, c.msf, c.snap, c.snap + F16_NUM_STATE_FIELDS, action, seed, env_id, auto_reset, fr, tfr, reward, &ep_ret, &ep_len);
+  // as the kernel does: hot instantiation first; if a contact point reached the ground, redo the step from the
+  // saved state with the ground-reaction instantiation
+  const EnvScalars es0 = e->es;
+  if (e->mode == 0) {
+    const Veh<double> s0 = e->sd;
+    flags = env_step_one<double, GROUND_DETECT>(e->sd, e->es, c.Td, c.ms, c.ms, c.snap, c.snap + F16_NUM_STATE_FIELDS, action, seed, env_id, auto_reset, fr, tfr, reward, &ep_ret, &ep_len);
+    if (flags & STEP_NEAR_GROUND) {
+      e->sd = s0; e->es = es0;
+      flags = env_step_one<double, GROUND_FULL>(e->sd, e->es, c.Td, c.ms, c.ms, c.snap, c.snap + F16_NUM_STATE_FIELDS, action, seed, env_id, auto_reset, fr, tfr, reward, &ep_ret, &ep_len);
+    }
+  } else {
+    const Veh<float> s0 = e->sf;
+    flags = env_step_one<float, GROUND_DETECT>(e->sf, e->es, c.Tf, c.msf, c.ms, c.snap, c.snap + F16_NUM_STATE_FIELDS, action, seed, env_id, auto_reset, fr, tfr, reward, &ep_ret, &ep_len);
+    if (flags & STEP_NEAR_GROUND) {
+      e->sf = s0; e->es = es0;
+      flags = env_step_one<float, GROUND_FULL>(e->sf, e->es, c.Tf, c.msf, c.ms, c.snap, c.snap + F16_NUM_STATE_FIELDS, action, seed, env_id, auto_reset, fr, tfr, reward, &ep_ret, &ep_len);
+    }
+  }
   // same stack update as warp_write_obs
   if (flags & STEP_TERMINAL) {
     std::memcpy(e->tobs[0], e->obs[1], 9 * 15 * sizeof(float));

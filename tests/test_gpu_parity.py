@@ -281,3 +281,73 @@ def test_ring_layout_is_value_identical_to_stacked(F16BatchedEnv, mode):
             same(a.obs, b.obs.contiguous())
     sa, sb = a.stats(), b.stats()
     assert sa["goals"] > 100 and sa["episodes"] == sb["episodes"] and sa["goals"] == sb["goals"] and sa["length_sum"] == sb["length_sum"]
+
+
+@pytest.mark.parametrize("mode,tol", [("fp64", 1e-8), ("fp32", 1e-3)])
+def test_ground_contact_step_parity(F16BatchedEnv, oracle, state_fields, mode, tol):
+    """ground reactions (f16.xml:85-215). One batch holds every synthetic contact state of
+    tests/test_ground_contact.py (each STRUCTURE contact, several at once, static and dynamic friction)
+    followed by the crash steps of random-action episodes and by ordinary in-flight states, so lanes of
+    one warp take the cold ground path and the hot path side by side; one teacher-forced env-step against
+    the oracle. The layouts other than the default take the same path (checked in frame layout too)."""
+    from test_ground_contact import CASES, crash_steps, flying_oracle_env, synthetic_state
+    floors = state_floors(state_fields)
+    act0 = np.array([0.2, -0.1, 0.1, 0.7], np.float32)
+    s0, s1, acts, goals, steps, frames, touched = [], [], [], [], [], [], []
+    for name, h, phi, th, psi, uvw, pqr, want in CASES:
+        env, goal = flying_oracle_env(oracle)
+        st = synthetic_state(env.fdm.pack_state(), state_fields, h, phi, th, psi, uvw, pqr)
+        env.fdm.unpack_state(st)
+        obs, r, term, trunc = env.step(act0)
+        s0.append(st); s1.append(env.fdm.pack_state()); acts.append(act0); goals.append(goal); steps.append(5)
+        frames.append(obs[-1]); touched.append(True)
+        # an ordinary state in flight right beside it
+        env2, goal2 = flying_oracle_env(oracle)
+        st2 = env2.fdm.pack_state()
+        obs2, _, _, _ = env2.step(act0)
+        s0.append(st2); s1.append(env2.fdm.pack_state()); acts.append(act0); goals.append(goal2); steps.append(3)
+        frames.append(obs2[-1]); touched.append(False)
+    for goal, st, t, a, st1, frame, reward, wow in crash_steps(oracle, n_episodes=24):
+        s0.append(st); s1.append(st1); acts.append(a); goals.append(goal); steps.append(t); frames.append(frame); touched.append(any(wow))
+    n = len(s0)
+    for layout in ("stacked", "frame"):
+        env = F16BatchedEnv(n, mode=mode, obs_layout=layout, ground_reactions=True)   # the fp32 default is off
+        assert env.ground_reactions
+        env.reset(goals=torch.from_numpy(np.stack(goals)).cuda())
+        env.unpack_states(torch.from_numpy(np.stack(s0)).cuda())
+        _set_all_steps(env, np.array(steps, dtype=np.int32))
+        out = env.step(torch.from_numpy(np.stack(acts)).cuda(), auto_reset=False)
+        got = env.pack_states().cpu().numpy()
+        e = rel_err(got, np.stack(s1), floors[None, :])
+        if mode == "fp32":
+            e[2 * [c[0] for c in CASES].index("at_rest_static_friction"), state_fields.index("VC_KTS")] = 0.0   # see test_ground_contact
+        worst = np.unravel_index(int(e.argmax()), e.shape)
+        assert e.max() < tol, (layout, int(worst[0]), state_fields[int(worst[1])], float(e.max()))
+        if mode == "fp64" and layout == "stacked":
+            fr = out[0][:, -1, :12].cpu().numpy()
+            assert np.allclose(fr, np.stack(frames)[:, :12], rtol=1e-6, atol=1e-6)
+    assert sum(touched) >= len(CASES) + 1
+
+
+def test_ground_reactions_default_and_switch(F16BatchedEnv):
+    """On by default in FP64 (parity) mode, off in FP32 (throughput) mode; with them off the step is the
+    ground-less instantiation: a state at the surface then keeps its aerodynamic accelerations."""
+    assert F16BatchedEnv(32, mode="fp64").ground_reactions and not F16BatchedEnv(32, mode="fp32").ground_reactions
+    from test_ground_contact import synthetic_state
+    import re, os
+    txt = open(os.path.join(os.path.dirname(__file__), "..", "include", "f16_state_fields.h")).read()
+    body = txt.split("enum f16_state_field")[1].split("F16_NUM_STATE_FIELDS")[0]
+    fields = []
+    for m in re.finditer(r"F16S_([A-Z0-9_]+)", body):
+        if m.group(1) not in fields:
+            fields.append(m.group(1))
+    out = {}
+    for on in (False, True):
+        env = F16BatchedEnv(32, mode="fp64", ground_reactions=on)
+        env.reset()
+        st = synthetic_state(env.snapshot()[0], fields, 2.0, 0.0, 0.0, 0.3, (150.0, 0.0, 8.0))
+        env.unpack_states(torch.from_numpy(np.tile(st, (32, 1))).cuda())
+        env.step(torch.zeros((32, 4), device="cuda"), auto_reset=False)
+        out[on] = env.pack_states().cpu().numpy()[0]
+    i = fields.index("WDOT_X")
+    assert np.abs(out[True][i:i + 3] - out[False][i:i + 3]).max() > 1e-2

@@ -94,6 +94,19 @@ def parse_model(ref):
         thruster_orient=[float(thr.find("orient").find(k).text) for k in ("roll", "pitch", "yaw")],
         tanks=[dict(loc=triple(t.find("location")), capacity=float(t.find("capacity").text),
                     contents=float(t.find("contents").text)) for t in prop.findall("tank")])
+    # ---- ground reactions (f16.xml:85-215): contact points, units as in the file (IN, LBS/FT, LBS/FT/SEC)
+    contacts = []
+    for c in f16.find("ground_reactions").findall("contact"):
+        assert c.find("location").get("unit") == "IN"
+        assert c.find("spring_coeff").get("unit") == "LBS/FT" and c.find("damping_coeff").get("unit") == "LBS/FT/SEC"
+        assert c.find("damping_coeff_rebound") is None and c.find("orientation") is None
+        contacts.append(dict(
+            name=c.get("name"), type=c.get("type"), loc=triple(c.find("location")),
+            static_friction=float(c.find("static_friction").text), dynamic_friction=float(c.find("dynamic_friction").text),
+            rolling_friction=float(c.find("rolling_friction").text), spring=float(c.find("spring_coeff").text),
+            damping=float(c.find("damping_coeff").text),
+            retractable=int(float(c.find("retractable").text)) if c.find("retractable") is not None else 0))
+    M["contacts"] = contacts
     E = {}
     for k in ("milthrust", "maxthrust", "bypassratio", "tsfc", "atsfc", "bleed", "idlen1", "idlen2",
               "maxn1", "maxn2", "augmented", "augmethod", "injected"):
@@ -416,6 +429,17 @@ class OracleGen:
             out.append("static const double %s = %s;" % (k, fnum(eng[k])))
         for k in ("augmented", "augmethod", "injected"):
             out.append("static const int %s = %d;" % (k, int(eng[k])))
+        cs = M["contacts"]
+        out.append("// ground_reactions f16.xml:85-215, file order")
+        out.append("static const int n_contacts = %d;" % len(cs))
+        out.append("struct ContactDef { const char* name; bool bogey; bool retractable; double loc[3]; double static_f, dynamic_f, rolling_f, spring, damping; };")
+        out.append("static const ContactDef contacts[%d] = {" % len(cs))
+        for c in cs:
+            out.append('  {"%s", %s, %s, {%s}, %s, %s, %s, %s, %s},' % (
+                c["name"], "true" if c["type"] == "BOGEY" else "false", "true" if c["retractable"] else "false",
+                ", ".join(map(fnum, c["loc"])), fnum(c["static_friction"]), fnum(c["dynamic_friction"]),
+                fnum(c["rolling_friction"]), fnum(c["spring"]), fnum(c["damping"])))
+        out.append("};")
         out.append("} // namespace modelk")
         return "\n".join(out) + "\n"
 
@@ -484,6 +508,16 @@ def gen_product_header(M):
         o.append("constexpr double %s = %s;" % (k, fnum(eng[k])))
     assert int(eng["augmethod"]) == 2 and int(eng["augmented"]) == 1 and int(eng["injected"]) == 0
 
+    # ---- structure contacts (f16.xml:137-214); the three BOGEY contacts are retractable and the env keeps the gear up
+    st = [c for c in M["contacts"] if c["type"] == "STRUCTURE"]
+    assert all(c["retractable"] for c in M["contacts"] if c["type"] == "BOGEY")
+    o.append("// ground_reactions f16.xml:137-214: STRUCTURE contacts (location IN, spring LBS/FT, damping LBS/FT/SEC)")
+    o.append("constexpr int n_structure = %d;" % len(st))
+    o.append("#define F16_STRUCT_LOC {%s}" % ", ".join("{%s}" % ", ".join(map(fnum, c["loc"])) for c in st))
+    o.append("#define F16_STRUCT_SPRING {%s}" % ", ".join(fnum(c["spring"]) for c in st))
+    o.append("#define F16_STRUCT_DAMPING {%s}" % ", ".join(fnum(c["damping"]) for c in st))
+    o.append("#define F16_STRUCT_STATIC_F {%s}" % ", ".join(fnum(c["static_friction"]) for c in st))
+    o.append("#define F16_STRUCT_DYNAMIC_F {%s}" % ", ".join(fnum(c["dynamic_friction"]) for c in st))
     # ---- FCS named constants (f16.xml:317-935)
     o.append("// flight_control f16.xml:317-935")
     sw = find_comp(M, "fcs/tef-pos-rad")

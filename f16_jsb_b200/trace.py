@@ -4,14 +4,14 @@ Why it exists: the reference's arithmetic lives in the 
 package, which is not installable where this repository is built, so parity against real JSBSim is
 unpinned. A maintainer who has `jsbsim` runs `python tools/record_trace.py --backend jsbsim` once; the
 file it writes is dropped into tests/golden/ and from then on `tests/test_traces.py` replays it through
-the oracle (CPU) and through the CUDA library (B200) with the tolerances below - no code changes.
+the CPU restatement and through the CUDA library (B200) with the tolerances below - no code changes.
 
 Format (NumPy .npz, every array little-endian, version 1):
 
     header       0-d <U array holding a JSON object:
                    format       "f16trace"
                    version      1
-                   producer     "jsbsim <version>" | "oracle-restatement" | ...
+                   producer     "jsbsim <version>" | "cpu-restatement" | ...
                    aircraft     "f16"
                    dt           1/120 (s, one FDM frame)        down_sample  4 frames per env-step
                    seed         the reset seed (goal draw, jsbsim_gym.py:312-323) or null
@@ -36,7 +36,7 @@ import numpy as np
 
 FORMAT_VERSION = 1
 
-# Properties recorded next to the observation: real JSBSim names, all served by the oracle too.
+# Properties recorded next to the observation: real JSBSim names (the CPU restatement used by the tests serves them too).
 TRACE_PROPERTIES = [
     # the twelve STATE_FORMAT entries (jsbsim_gym.py:12-25), as doubles before the float32 cast chain
     "position/lat-gc-rad", "position/long-gc-rad", "position/h-sl-meters", "velocities/mach",

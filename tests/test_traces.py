@@ -1,7 +1,7 @@
 """Every tests/golden/*.f16trace.npz (format: f16_jsb_b200/trace.py) is replayed through the kernel source on
 the CPU (tests/hostsim), through the oracle's C env layer, and - on the B200 - through the CUDA library.
 Traces whose producer is "jsbsim <version>" pin parity against the real JSBSim; the ones committed today
-were recorded where JSBSim is not installable (producer "oracle-restatement": the reference's own Python env
+were recorded where JSBSim is not installable (producer "cpu-restatement": the reference's own Python env
 layer on top of the oracle FDM), so they pin the format and the env layer, and exercise a steep impact with
 ground contact (oracle_dive21). Dropping a JSBSim-recorded file into tests/golden/ is all it takes to pin
 the FDM: `python tools/record_trace.py --backend jsbsim --out tests/golden/jsbsim_<name>.f16trace.npz`."""
@@ -49,7 +49,7 @@ def test_replay_through_the_oracle_env_layer(path, oracle):
         return obs[-1], r, term or trunc, trunc
 
     rep = replay_trace(t, step, env.reset, mode="fp64")
-    if t["header"]["producer"] == "oracle-restatement":
+    if t["header"]["producer"] == "cpu-restatement":
         assert rep["max_err_early"] == 0.0 and rep["max_err_late"] == 0.0      # same FDM: bit for bit
 
 

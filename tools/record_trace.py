@@ -59,7 +59,7 @@ def main():
 
     env = gym.make("JSBSim-v0", root=a.reference)
     fdm = env.unwrapped.simulation
-    producer = "jsbsim %s" % getattr(jsbsim, "__version__", "?") if a.backend == "jsbsim" else "oracle-restatement"
+    producer = "jsbsim %s" % getattr(jsbsim, "__version__", "?") if a.backend == "jsbsim" else "cpu-restatement"
     actions = make_actions(a.actions, 1000 + a.seed if a.action_seed is None else a.action_seed, a.max_steps)
     rec = record_episode(env, fdm, a.seed, actions)
     save_trace(a.out, producer=producer, notes="actions=%s" % a.actions, **rec)

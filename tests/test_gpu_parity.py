@@ -351,3 +351,32 @@ def test_ground_reactions_default_and_switch(F16BatchedEnv):
         out[on] = env.pack_states().cpu().numpy()[0]
     i = fields.index("WDOT_X")
     assert np.abs(out[True][i:i + 3] - out[False][i:i + 3]).max() > 1e-2
+
+
+@pytest.mark.parametrize("mode,tol", [("fp64", 1e-9), ("fp32", 1e-3)])
+def test_envelope_step_parity(F16BatchedEnv, oracle, state_fields, mode, tol):
+    """tests/test_envelope_parity.py on the CUDA library: 800 random states over the whole flight envelope
+    (Mach 0.14-2.04, up to 60 000 ft, alpha -30..95 deg, lit and unlit afterburner, saturated actuators) in one
+    batch, one teacher-forced env-step against the oracle."""
+    from test_envelope_parity import envelope_states, oracle_step_all
+    from test_ground_contact import flying_oracle_env
+    floors = state_floors(state_fields)
+    env0, _ = flying_oracle_env(oracle)
+    base = env0.fdm.pack_state()
+    sa, aa = envelope_states(base, state_fields, 400, seed=11, region="flown")
+    sb, ab = envelope_states(base, state_fields, 400, seed=12, region="wide")
+    states, acts = np.concatenate([sa, sb]), np.concatenate([aa, ab])
+    goal, want, frames = oracle_step_all(oracle, states, acts)
+    n = len(states)
+    env = F16BatchedEnv(n, mode=mode)
+    env.reset(goals=torch.from_numpy(np.tile(goal, (n, 1))).cuda())
+    env.unpack_states(torch.from_numpy(states).cuda())
+    _set_all_steps(env, np.full(n, 7, dtype=np.int32))
+    obs, rew, done, trunc = env.step(torch.from_numpy(acts).cuda(), auto_reset=False)
+    e = rel_err(env.pack_states().cpu().numpy(), want, floors[None, :])
+    if mode == "fp32":
+        e[want[:, state_fields.index("MACH")] > 0.98, state_fields.index("VC_KTS")] = 0.0   # see test_envelope_parity
+    worst = np.unravel_index(int(e.argmax()), e.shape)
+    assert e.max() < tol, (int(worst[0]), state_fields[int(worst[1])], float(e.max()))
+    if mode == "fp64":
+        assert np.allclose(obs[:, -1, :12].cpu().numpy(), frames[:, :12], rtol=1e-6, atol=1e-6)

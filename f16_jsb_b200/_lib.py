@@ -60,6 +60,7 @@ def load():
     L.f16_hostwin_fill.argtypes = [vp, vp, C.POINTER(HostwinResult)]
     L.f16_hostwin_push.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.POINTER(HostwinResult)]
     L.f16_reset.argtypes = [vp, vp, vp, u64, vp]
+    L.f16_reset_carryover.argtypes = [vp, vp, vp, u64, vp, vp]
     L.f16_step.argtypes = [vp, vp, i32, vp]
     L.f16_step_begin.argtypes = [vp, vp]
     L.f16_step_range.argtypes = [vp, vp, i32, i64, i64, vp]
@@ -92,7 +93,7 @@ def load():
     for name in HOSTWIN_SYMBOLS:
         if name != "f16_hostwin_action_buffer":
             getattr(L, name).restype = i32
-    for name in ("f16_create", "f16_destroy", "f16_bind", "f16_bind_ring", "f16_bind_frames", "f16_set_done_list", "f16_obs_window", "f16_reset", "f16_step", "f16_step_begin", "f16_step_range", "f16_step_host",
+    for name in ("f16_create", "f16_destroy", "f16_bind", "f16_bind_ring", "f16_bind_frames", "f16_set_done_list", "f16_obs_window", "f16_reset", "f16_reset_carryover", "f16_step", "f16_step_begin", "f16_step_range", "f16_step_host",
                  "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states",
                  "f16_unpack_states", "f16_set_env_step", "f16_get_snapshot", "f16_get_stats",
                  "f16_stats_device_ptr"):
@@ -108,7 +109,7 @@ def check(rc: int, what: str = "") -> None:
 
 
 EXPORTED_SYMBOLS = (
-    "f16_create", "f16_destroy", "f16_state_bytes", "f16_set_ground_reactions", "f16_get_ground_reactions", "f16_bind", "f16_bind_ring", "f16_bind_frames", "f16_set_done_list", "f16_obs_window", "f16_reset", "f16_step", "f16_step_begin", "f16_step_range", "f16_step_host",
+    "f16_create", "f16_destroy", "f16_state_bytes", "f16_set_ground_reactions", "f16_get_ground_reactions", "f16_bind", "f16_bind_ring", "f16_bind_frames", "f16_set_done_list", "f16_obs_window", "f16_reset", "f16_reset_carryover", "f16_step", "f16_step_begin", "f16_step_range", "f16_step_host",
     "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states", "f16_unpack_states",
     "f16_set_env_step", "f16_get_snapshot", "f16_get_stats", "f16_stats_device_ptr", "f16_launch_count", "f16_num_state_fields",
     "f16_last_error", "f16_version")

@@ -39,11 +39,18 @@ class F16BatchedEnv:
     place, exactly the reference's array. "ring" keeps (N, 20, 15) and writes each new frame twice, so
     `obs` is a zero-copy strided view (N, 10, 15) of the current window - same values, 2.4x less HBM
     traffic per step; each env's 150 floats stay contiguous (obs.view(N, 150) is a valid strided matrix).
+
+    reset_mode: "snapshot" (default) starts every episode from the canonical state of a FRESH reference env
+    object. "carryover" does what JSBSimEnv.reset does to an env object that already exists
+    (jsbsim_gym.py:305-306: run_ic() + set-running on top of the actuator positions, control-law memories, stale
+    air data and accelerations the last episode left behind; include/f16_b200.h, f16_reset_carryover) - the
+    second and later episodes of one reference env. It turns ground reactions on (both belong to the
+    reference-detail build of the step kernel).
     """
 
     def __init__(self, num_envs: int, device=None, mode: str = "fp32", seed: int = 0,
                  with_terminal_obs: bool = True, env_id_base: int = 0, obs_layout: str = "stacked",
-                 done_list: bool = False, ground_reactions=None):
+                 done_list: bool = False, ground_reactions=None, reset_mode: str = "snapshot"):
         if not torch.cuda.is_available():
             raise _lib.F16Error("F16BatchedEnv needs a CUDA device: the F-16 env has no CPU fallback")
         self.lib = _lib.load()
@@ -58,6 +65,14 @@ class F16BatchedEnv:
         h = C.c_void_p()
         _lib.check(self.lib.f16_create(C.byref(h), self.num_envs, dev_index, self.mode), "f16_create")
         self._h = h
+        if reset_mode not in ("snapshot", "carryover"):
+            raise ValueError("reset_mode must be 'snapshot' or 'carryover'")
+        self.reset_mode = reset_mode
+        self._last_actions = None      # carry-over reset: the action of the last step (fcs/*-cmd-norm stay set)
+        if reset_mode == "carryover":
+            if ground_reactions is not None and not ground_reactions:
+                raise ValueError("reset_mode='carryover' needs ground_reactions on")
+            ground_reactions = True
         # ground reactions (include/f16_b200.h): None keeps the mode's default (on in fp64, off in fp32)
         if ground_reactions is not None:
             _lib.check(self.lib.f16_set_ground_reactions(h, 1 if ground_reactions else 0), "f16_set_ground_reactions")
@@ -138,7 +153,11 @@ class F16BatchedEnv:
         if goals is not None:
             goals = goals.to(device=self.device, dtype=torch.float32).contiguous()
             assert goals.shape == (self.num_envs, 3)
-        _lib.check(self.lib.f16_reset(self._h, _ptr(mask), _ptr(goals), self.seed, self._stream()), "f16_reset")
+        if self.reset_mode == "carryover":
+            _lib.check(self.lib.f16_reset_carryover(self._h, _ptr(mask), _ptr(goals), self.seed, _ptr(self._last_actions),
+                                                    self._stream()), "f16_reset_carryover")
+        else:
+            _lib.check(self.lib.f16_reset(self._h, _ptr(mask), _ptr(goals), self.seed, self._stream()), "f16_reset")
         return self.obs
 
     def step(self, actions: Optional[torch.Tensor], auto_reset: bool = True):
@@ -149,7 +168,14 @@ class F16BatchedEnv:
             if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
                 actions = actions.to(device=self.device, dtype=torch.float32).contiguous()
             assert actions.shape == (self.num_envs, 4)
-        _lib.check(self.lib.f16_step(self._h, _ptr(actions), int(auto_reset), self._stream()), "f16_step")
+        mode = int(auto_reset)
+        if self.reset_mode == "carryover":
+            mode *= 2                      # F16_AUTO_RESET_CARRYOVER
+            if actions is not None:
+                if self._last_actions is None:
+                    self._last_actions = torch.zeros((self.num_envs, 4), dtype=torch.float32, device=self.device)
+                self._last_actions.copy_(actions)
+        _lib.check(self.lib.f16_step(self._h, _ptr(actions), mode, self._stream()), "f16_step")
         return self.obs, self.reward, self.done, self.truncated
 
     # ------------------------------------------------------------------ host-buffer API

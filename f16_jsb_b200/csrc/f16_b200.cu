@@ -378,6 +378,18 @@ __device__ __noinline__ void env_step_ground(const StatePtrs<R> sp, int64_t e, c
   store_env(es, sp, e);
 }
 
+// Carry-over reset of an env that finished in this step with auto_reset == 2 (veh_carryover_reset, f16_env.cuh): the
+// env's end-of-episode state is already back in HBM; run_ic()'s two zero-dt frames and set-running are applied to
+// it here. Cold (one lane of a warp, ~0.1 % of the envs per step under random actions) and not inlined.
+template <typename R>
+__device__ __noinline__ void env_carryover_bringup(const StatePtrs<R> sp, int64_t e, const Tables<R>* T, float4 action) {
+  Veh<R> s;
+  load_veh(s, sp, e);
+  const float act[4] = {action.x, action.y, action.z, action.w};
+  veh_carryover_reset<R>(s, *T, msets_for<R>(), c_snapshot, act, true);
+  store_veh(s, sp, e);
+}
+
 #ifndef F16_PERSISTENT
 #define F16_PERSISTENT 0
 #endif
@@ -464,6 +476,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
         store_veh(s, sp, e);
         store_env(es, sp, e);
       }
+      if (GROUND && a.auto_reset == 2 && (flags & STEP_RESET))
+        env_carryover_bringup<R>(sp, e, &T, make_float4(act[0], act[1], act[2], act[3]));
       a.reward[e] = reward;
       a.done[e] = (flags & STEP_DONE) ? 1 : 0;
       a.truncated[e] = (flags & STEP_TRUNCATED) ? 1 : 0;
@@ -514,10 +528,15 @@ struct ResetArgs {
   uint64_t seed;
   int64_t env_id_base;
   int obs_rows;      // 10 (stacked layout) or 20 (ring layout)
+  const void* tables;            // carry-over reset only: the table image of the context's precision
+  const float* last_actions;     // carry-over reset only: N x 4, the action of each env's last step (or NULL)
 };
 
-template <typename R>
+template <typename R, bool CARRY>
 __global__ void __launch_bounds__(BLOCK) f16_reset_kernel(const ResetArgs a) {
+  __shared__ __align__(16) unsigned char Tbuf[CARRY ? sizeof(Tables<R>) : 16];   // only the carry-over reset runs FDM frames
+  Tables<R>* const T = reinterpret_cast<Tables<R>*>(Tbuf);
+  if (CARRY) stage_tables(T, reinterpret_cast<const Tables<R>*>(a.tables));
   const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (e >= a.n) return;
   if (a.mask && !a.mask[e]) return;
@@ -525,12 +544,21 @@ __global__ void __launch_bounds__(BLOCK) f16_reset_kernel(const ResetArgs a) {
   Veh<R> s;
   EnvScalars es;
   load_env(es, sp, e);
-  es.episodes += 1;
   float g[3];
   if (a.goals) { g[0] = a.goals[e * 3 + 0]; g[1] = a.goals[e * 3 + 1]; g[2] = a.goals[e * 3 + 2]; }
-  else sample_goal(a.seed, (uint64_t)(a.env_id_base + e), es.episodes, g);
+  else sample_goal(a.seed, (uint64_t)(a.env_id_base + e), (es.episodes & ~kEpisodeUsedBit) + 1, g);
   float fr[16];
-  env_reset_one<R>(s, es, c_snapshot, c_snapshot_props, g, fr);
+  if (CARRY) {
+    // JSBSimEnv.reset on an env object that already exists: run_ic() + set-running on top of whatever the last
+    // episode left behind (env_carryover_reset_one, f16_env.cuh)
+    load_veh(s, sp, e);
+    float la[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (a.last_actions) { const float4 v = reinterpret_cast<const float4*>(a.last_actions)[e]; la[0] = v.x; la[1] = v.y; la[2] = v.z; la[3] = v.w; }
+    env_carryover_reset_one<R>(s, es, *T, msets_for<R>(), c_snapshot, c_snapshot_props, g, la, fr);
+  } else {
+    es.episodes = (es.episodes & ~kEpisodeUsedBit) + 1;
+    env_reset_one<R>(s, es, c_snapshot, c_snapshot_props, g, fr);
+  }
   store_veh(s, sp, e);
   store_env(es, sp, e);
   float* ob = a.obs + e * (a.obs_rows * F16_OBS_FEATURES);
@@ -782,9 +810,8 @@ int f16_set_env_id_base(f16_handle h, int64_t base) {
   return 0;
 }
 
-int f16_reset(f16_handle h, const uint8_t* mask, const float* goals, uint64_t seed, void* stream) {
-  if (!h) return fail("f16_reset: NULL handle");
-  if (!h->state) return fail("f16_reset: call f16_bind first");
+static int launch_reset(f16_handle h, const uint8_t* mask, const float* goals, uint64_t seed, bool carry, const float* last_actions,
+                        void* stream) {
   CUDA_OK(cudaSetDevice(h->device));
   h->seed = seed;
   ResetArgs a;
@@ -792,16 +819,39 @@ int f16_reset(f16_handle h, const uint8_t* mask, const float* goals, uint64_t se
   a.n = h->L.n; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
   a.seed = seed; a.env_id_base = h->env_id_base;
   a.obs_rows = h->ring == OBS_RING ? 2 * F16_OBS_FRAMES : h->ring == OBS_FRAME ? 1 : F16_OBS_FRAMES;
+  a.tables = h->tables_dev; a.last_actions = last_actions;
   unsigned grid = (unsigned)((h->L.n + BLOCK - 1) / BLOCK);
-  if (h->mode == F16_MODE_FP64) f16_reset_kernel<double><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
-  else f16_reset_kernel<float><<<grid, BLOCK, 0, (cudaStream_t)stream>>>(a);
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (h->mode == F16_MODE_FP64) {
+    if (carry) f16_reset_kernel<double, true><<<grid, BLOCK, 0, st>>>(a);
+    else f16_reset_kernel<double, false><<<grid, BLOCK, 0, st>>>(a);
+  } else {
+    if (carry) f16_reset_kernel<float, true><<<grid, BLOCK, 0, st>>>(a);
+    else f16_reset_kernel<float, false><<<grid, BLOCK, 0, st>>>(a);
+  }
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
+int f16_reset(f16_handle h, const uint8_t* mask, const float* goals, uint64_t seed, void* stream) {
+  if (!h) return fail("f16_reset: NULL handle");
+  if (!h->state) return fail("f16_reset: call f16_bind first");
+  return launch_reset(h, mask, goals, seed, false, nullptr, stream);
+}
+
+int f16_reset_carryover(f16_handle h, const uint8_t* mask, const float* goals, uint64_t seed, const float* last_actions, void* stream) {
+  if (!h) return fail("f16_reset_carryover: NULL handle");
+  if (!h->state) return fail("f16_reset_carryover: call f16_bind first");
+  return launch_reset(h, mask, goals, seed, true, last_actions, stream);
+}
+
 // One launch of the step kernel over envs [first, first + count); first is a multiple of 32.
 static int launch_step(f16_handle h, const float* actions, int auto_reset, int64_t first, int64_t count, uint32_t step_counter, void* stream) {
+  if (auto_reset < 0 || auto_reset > F16_AUTO_RESET_CARRYOVER) return fail("f16_step: auto_reset must be 0, 1 or 2 (got %d)", auto_reset);
+  if (auto_reset == F16_AUTO_RESET_CARRYOVER && !h->ground)
+    return fail("f16_step: the carry-over reset (auto_reset = 2) is part of the reference-detail build of the step kernel; "
+                "turn ground reactions on first (f16_set_ground_reactions)");
   StepArgs a;
   a.state = h->state; a.tables = h->tables_dev; a.actions = actions; a.obs = h->obs; a.reward = h->reward;
   a.done = h->done; a.truncated = h->truncated; a.terminal_obs = h->terminal_obs; a.ep_return = h->ep_return;

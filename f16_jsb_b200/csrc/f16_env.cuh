@@ -167,8 +167,11 @@ F16_HD void compute_snapshot(const Tables<double>& T, const MassSetT<double>* ms
 // the goal, build the reset frame (the caller replicates it into all ten rows).
 template <typename R>
 F16_HD void env_reset_one(Veh<R>& s, EnvScalars& es, const double* snapshot, const double* snapshot_props,
-                          const float* goal, float* frame16) {
-  veh_from_packed(s, snapshot);
+                          const float* goal, float* frame16, bool keep_state = false) {
+  // keep_state: carry-over reset in two parts - the flight-dynamics state is left as the episode ended and
+  // veh_carryover_reset() brings it up afterwards (the observation after reset is the same either way: its
+  // twelve properties only depend on the initial condition)
+  if (!keep_state) veh_from_packed(s, snapshot);
   es.gx = goal[0]; es.gy = goal[1]; es.gz = goal[2];
   float o[12];
   props_to_frame(snapshot_props, o);
@@ -178,6 +181,60 @@ F16_HD void env_reset_one(Veh<R>& s, EnvScalars& es, const double* snapshot, con
   es.step = 0;
   es.ep_ret = 0.0f;
   es.ep_len = 0;
+}
+
+// ------------------------------------------------------------------------------------ carry-over reset
+// What JSBSimEnv.reset really does to an env object that already exists (jsbsim_gym.py:305-306): run_ic()
+// re-initialises only FGPropagate's state from the initial condition and runs two frames with integration
+// suspended; propulsion/set-running restarts the engine. Everything else leaks from the episode that just
+// ended: the FCS actuator positions and PID memories (they even tick twice more, with dt = 1/120, on the last
+// action, whose fcs/*-cmd-norm properties stay set), the Auxiliary outputs the FCS reads one frame late, the
+// last accelerations (pilot load factors) and - unlike a fresh construct - the gear is already up and the tanks
+// already hold 1000 lb, so the mass properties are the in-flight ones from the very first frame.
+// The default reset restores the canonical fresh-env snapshot instead (deviation 1); this is the
+// opt-in alternative that reproduces the second and later episodes of one reference env object.
+// `used` = the env has been stepped since it was constructed (gear up, tanks refilled to 1000 lb); an env that
+// was only ever reset still has its gear down and 1500 lb in the tanks and is brought up like the constructor does.
+// Not modelled: the fuel burnt in the last frame of the previous episode (<= 0.13 lb of 19 630 lb), which
+// JSBSim's MassBalance would see during these two frames because reset() does not refill the tanks.
+constexpr uint32_t kEpisodeUsedBit = 0x80000000u;   // EnvScalars::episodes, top bit: the env was brought up by a carry-over reset
+template <typename R>
+F16_HD void veh_carryover_reset(Veh<R>& s, const Tables<R>& T, const MassSetT<R>* msets, const double* snapshot, const float* last_act,
+                                bool used) {
+  Veh<R> ic;
+  veh_from_packed(ic, snapshot);
+  for (int i = 0; i < 4; ++i) s.q[i] = ic.q[i];                     // FGPropagate::SetInitialState
+  for (int i = 0; i < 3; ++i) { s.ri[i] = ic.ri[i]; s.vi[i] = ic.vi[i]; s.wi[i] = ic.wi[i]; }
+  s.epa = ic.epa;
+  Cmd<R> cmd = {(R)last_act[0], (R)last_act[1], (R)last_act[2], (R)last_act[3]};
+  FrameObs<R> fo;
+  FrameCfg cfg;
+  cfg.dt = 0.0;
+  cfg.gear = used ? 0.0 : 1.0;
+  cfg.mass_set = used ? MS_FLIGHT : MS_IC;
+  for (int k = 0; k < 2; ++k) fdm_frame<R, true, false>(s, T, msets, cfg, cmd, false, fo);
+  for (int i = 0; i < 3; ++i) { s.vi1[i] = (R)s.vi[i]; s.vi2[i] = (R)s.vi[i]; }   // InitializeDerivatives
+  s.n2 = (R)(f16data::idlen2 + 1.0 * (f16data::maxn2 - f16data::idlen2));       // InitRunning + GetSteadyState
+  s.aug = R(0);
+}
+
+// Explicit reset() of one env in carry-over mode (f16_reset_carryover): what a second, third, ... call of
+// JSBSimEnv.reset does to the same env object. An env that was never reset has no constructor state yet and gets
+// the canonical bring-up. last_act: the action of the env's last step (ignored until it has been stepped).
+template <typename R>
+F16_HD void env_carryover_reset_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const MassSetT<R>* msets, const double* snapshot,
+                                    const double* snapshot_props, const float* goal, const float* last_act, float* frame16) {
+  const uint32_t ep = es.episodes & ~kEpisodeUsedBit;
+  if (ep == 0) {
+    es.episodes = 1;
+    env_reset_one<R>(s, es, snapshot, snapshot_props, goal, frame16);
+    return;
+  }
+  const bool used = (es.episodes & kEpisodeUsedBit) != 0 || es.step > 0;
+  const float none[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  veh_carryover_reset<R>(s, T, msets, snapshot, used ? last_act : none, used);
+  es.episodes = (ep + 1) | (used ? kEpisodeUsedBit : 0u);
+  env_reset_one<R>(s, es, snapshot, snapshot_props, goal, frame16, true);
 }
 
 enum { STEP_ACTIVE = 1, STEP_RESET = 2, STEP_TERMINAL = 4, STEP_DONE = 8, STEP_TRUNCATED = 16, STEP_CRASH = 32, STEP_GOAL = 64,
@@ -237,10 +294,11 @@ F16_HD int env_step_epilogue(Veh<R>& s, EnvScalars& es, const FrameObs<R>& fo, c
     if (auto_reset) {
       for (int i = 0; i < 16; ++i) tframe16[i] = frame16[i];
       flags |= STEP_RESET | STEP_TERMINAL;
-      es.episodes += 1;
+      const uint32_t ep = (es.episodes & ~kEpisodeUsedBit) + 1;
+      es.episodes = auto_reset == 2 ? (ep | kEpisodeUsedBit) : ep;
       float g[3];
-      sample_goal(seed, env_id, es.episodes, g);
-      env_reset_one<R>(s, es, snapshot, snapshot_props, g, frame16);
+      sample_goal(seed, env_id, ep, g);
+      env_reset_one<R>(s, es, snapshot, snapshot_props, g, frame16, auto_reset == 2);
     }
   }
   return flags;
@@ -275,7 +333,8 @@ F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const Mas
       for (int i = 0; i < pf.count; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf.ptr + (size_t)i * pf.stride));
     }
 #endif
-    const bool first = es.step == 1 && k == 0;
+    // the first flight frame after a fresh construct still carries the mass properties of the 1500-lb tanks' CG
+    const bool first = es.step == 1 && k == 0 && !(es.episodes & kEpisodeUsedBit);
     fdm_frame<R, false, GMODE != GROUND_OFF>(s, T, msets, cfg, cmd, first, fo);
     if (GROUND) {
       if (fo.may_touch) ground_fix<R>(s, fo, msets_d[first ? MS_FLIGHT_FIRST : MS_FLIGHT], gm);
@@ -286,7 +345,9 @@ F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const Mas
   }
   const int flags = env_step_epilogue<R>(s, es, fo, snapshot, snapshot_props, seed, env_id, auto_reset, frame16, tframe16,
                                          reward_out, ep_ret_out, ep_len_out);
-  if (GMODE == GROUND_DETECT && first_touch < 4 && !(first_touch == 3 && (flags & STEP_RESET))) return STEP_ACTIVE | STEP_NEAR_GROUND;
+  // (with the carry-over reset nothing is discarded: those accelerations feed the pilot load factors of the next episode)
+  if (GMODE == GROUND_DETECT && first_touch < 4 && !(first_touch == 3 && (flags & STEP_RESET) && auto_reset != 2))
+    return STEP_ACTIVE | STEP_NEAR_GROUND;
   return flags;
 }
 

@@ -20,12 +20,15 @@ _WrapperBase = _compat.gym.Wrapper if _compat.HAVE_GYMNASIUM else object
 class JSBSimEnv(_Base):
     metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 30}
 
-    def __init__(self, root: str = ".", device=None, mode: str = "fp64"):
+    def __init__(self, root: str = ".", device=None, mode: str = "fp64", reset_mode: str = "carryover"):
+        """reset_mode "carryover" (default here): a second reset() of this object does what the reference object
+        does - run_ic() + set-running on top of what the last episode left in the control laws, air data and
+        accelerations (jsbsim_gym.py:305-306). "snapshot": every episode starts like the first one of a new env."""
         if _compat.HAVE_GYMNASIUM:
             super().__init__()
         self.num_stacked_frames = NUM_STACKED_FRAMES
         self.observation_space, self.action_space = make_spaces()
-        self._env = F16BatchedEnv(1, device=device, mode=mode, with_terminal_obs=False)
+        self._env = F16BatchedEnv(1, device=device, mode=mode, with_terminal_obs=False, reset_mode=reset_mode)
         self.down_sample = 4
         self.current_step = 0
         self.max_episode_steps = 1200

@@ -91,6 +91,9 @@ class F16VecEnv(VecEnvBase):
     "copy" keeps the stacks on the device and copies all of them out every step into `host_ring`
     rotating pinned buffers. copy_obs=True returns fresh arrays (DummyVecEnv's behaviour) in either mode.
     `action_buffer()` hands out pinned staging arrays: actions written there go to the device by plain DMA.
+    reset_mode: "snapshot" (default) restarts a finished env from the state of a fresh reference env object;
+    "carryover" applies the reference's run_ic() + set-running to the env as the episode left it, which is what
+    DummyVecEnv's env objects go through from their second episode on (F16BatchedEnv, include/f16_b200.h).
     """
 
     metadata = {"render_modes": ["human", "rgb_array"], "render_fps": 30}   # jsbsim_gym.py:120
@@ -98,13 +101,16 @@ class F16VecEnv(VecEnvBase):
     def __init__(self, num_envs: int, device=None, mode: str = "fp32", seed: int = 0, host_ring: int = 2,
                  copy_obs: bool = False, lazy_infos: Optional[bool] = None, env_id_base: int = 0,
                  obs_layout: str = "stacked", host_obs: str = "window", host_rings: int = 2,
-                 host_dma_both: bool = False):
+                 host_dma_both: bool = False, reset_mode: str = "snapshot"):
         obs_space, act_space = make_spaces()
         if host_obs not in ("window", "copy"):
             raise ValueError("host_obs must be 'window' or 'copy'")
         self.host_obs = host_obs
         self.env = F16BatchedEnv(num_envs, device=device, mode=mode, seed=seed, env_id_base=env_id_base,
-                                 obs_layout="frame" if host_obs == "window" else obs_layout)
+                                 obs_layout="frame" if host_obs == "window" else obs_layout, reset_mode=reset_mode)
+        # what a finished env restarts from: F16_AUTO_RESET_SNAPSHOT (fresh-env state) or F16_AUTO_RESET_CARRYOVER
+        # (the reference's run_ic() on the used env object; include/f16_b200.h)
+        self._auto_reset = 2 if reset_mode == "carryover" else 1
         self.render_mode = None
         try:
             super().__init__(num_envs, obs_space, act_space)
@@ -146,6 +152,8 @@ class F16VecEnv(VecEnvBase):
             # reference semantics: goal drawn from np.random.default_rng(seed) per env (jsbsim_gym.py:312-323)
             g = np.stack([sample_goal_numpy(s) for s in self._seeds])
             goals = torch.from_numpy(g).to(self.env.device)
+        if self._auto_reset == 2 and self._actions is not None:
+            self.env._last_actions = torch.from_numpy(np.ascontiguousarray(self._actions)).to(self.env.device)
         obs = self.env.reset(goals=goals)
         if self._win is not None:
             out = self._win.reset(self.env, self.env._stream()).obs
@@ -176,7 +184,7 @@ class F16VecEnv(VecEnvBase):
         self._actions = b
 
     def _step_wait_window(self):
-        res = self._win.step(self.env, self._actions, self.env._stream(), auto_reset=True)
+        res = self._win.step(self.env, self._actions, self.env._stream(), auto_reset=self._auto_reset)
         dones = res.done.view(np.bool_)
         done_infos = _RecordInfos(res.records, res.terminal_obs, round(time.time() - self._t_start, 6))
         if self.lazy_infos:
@@ -194,7 +202,7 @@ class F16VecEnv(VecEnvBase):
         self._slot = (self._slot + 1) % len(self._h_obs)
         k = self._slot
         obs, rew, done, trunc = self._h_obs[k].numpy(), self._h_rew[k].numpy(), self._h_done[k].numpy(), self._h_trunc[k].numpy()
-        self.env.step_host(self._actions, obs, rew, done, trunc, auto_reset=True)
+        self.env.step_host(self._actions, obs, rew, done, trunc, auto_reset=self._auto_reset)
         dones = done.astype(bool)
         done_infos: dict = {}
         idx = np.flatnonzero(dones)

@@ -96,14 +96,33 @@ int f16_set_done_list(f16_handle h, f16_done_record* done_list, int32_t* done_co
  * every env (entries of unmasked envs are ignored), or NULL to sample distance~U[1000,10000) m,
  * bearing~U[0,2pi), altitude~U[1000,4000) m (jsbsim_gym.py:315-317) from Philox4x32-10 keyed by
  * (seed, global env id, episode counter). */
+enum { F16_AUTO_RESET_OFF = 0,
+       F16_AUTO_RESET_SNAPSHOT = 1,  /* finished envs restart from the canonical fresh-env state (f16_reset)        */
+       F16_AUTO_RESET_CARRYOVER = 2  /* finished envs restart as f16_reset_carryover does; needs ground reactions on */ };
 int f16_reset(f16_handle h, const uint8_t* mask, const float* goals, uint64_t seed, void* stream);
+
+/* The same call on an env object that ALREADY EXISTS, as the reference really executes it: JSBSimEnv.reset is
+ * run_ic() + propulsion/set-running (jsbsim_gym.py:305-306), and JSBSim's run_ic() re-initialises only the
+ * kinematic state (FGPropagate) before two frames with integration suspended. Actuator positions, PID memories,
+ * the one-frame-late Auxiliary outputs the control laws read, the last accelerations and the last action
+ * (fcs/ *-cmd-norm stay set; the FCS ticks twice more on it) carry over from the episode that just ended, and a
+ * stepped env keeps its gear up and 1000-lb tanks. f16_reset restores the canonical state of a FRESH env object
+ * instead (every episode like the first one of a new env); this entry point reproduces the second and later
+ * episodes of one reference env object. The returned observation is the same either way (its twelve properties
+ * depend on the initial condition only). last_actions: N x 4 float device pointer, the action of each env's last
+ * step (ignored for envs that have not been stepped since they were created), or NULL for zeros. An env that was
+ * never reset gets the canonical bring-up. */
+int f16_reset_carryover(f16_handle h, const uint8_t* mask, const float* goals, uint64_t seed, const float* last_actions,
+                        void* stream);
 
 /* One env-step for all N envs. actions: N x 4 float device pointer
  * [roll, pitch, yaw, throttle] -> fcs/{aileron,elevator,rudder,throttle}-cmd-norm, un-clipped
  * (jsbsim_gym.py:216-222); NULL samples action_space.sample()-like uniform actions in-kernel
  * (Philox, keyed by seed/env/step). auto_reset != 0: an env that finishes is reset in the same
  * launch (new Philox goal), its stacked terminal observation goes to terminal_obs, and obs holds
- * the reset observation, as DummyVecEnv does. */
+ * the reset observation, as DummyVecEnv does. auto_reset is one of F16_AUTO_RESET_*: 1 restarts a finished
+ * env from the canonical fresh-env state, 2 applies the reference's run_ic() + set-running to the state the
+ * episode ended in (see f16_reset_carryover), with this step's action as the last action. */
 int f16_step(f16_handle h, const float* actions, int auto_reset, void* stream);
 
 /* One env-step in pieces (frame layout only), so that a caller can pipeline it over several streams: upload of

@@ -62,6 +62,7 @@ class HostSim:
         L.hs_env_create.argtypes = [C.c_int]
         L.hs_env_destroy.argtypes = [C.c_void_p]
         L.hs_env_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_env_reset_carryover.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_env_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.POINTER(C.c_float), C.c_void_p]
         L.hs_env_get_state.argtypes = [C.c_void_p, C.c_void_p]
         L.hs_env_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -89,6 +90,13 @@ class HostSimEnv:
         g = np.ascontiguousarray(goal, dtype=np.float32)
         obs = np.zeros((10, 15), np.float32)
         self.L.hs_env_reset(self.h, g.ctypes.data, obs.ctypes.data)
+        return obs
+
+    def reset_carryover(self, goal, last_action):
+        g = np.ascontiguousarray(goal, dtype=np.float32)
+        a = np.ascontiguousarray(last_action, dtype=np.float32)
+        obs = np.zeros((10, 15), np.float32)
+        self.L.hs_env_reset_carryover(self.h, g.ctypes.data, a.ctypes.data, obs.ctypes.data)
         return obs
 
     def step(self, action, auto_reset=0, seed=0, env_id=0):

@@ -54,9 +54,19 @@ void hs_env_reset(void* h, const float* goal, float* obs_out) {
   HsEnv* e = (HsEnv*)h;
   const Consts& c = consts();
   float fr[16];
-  e->es.episodes += 1;
+  e->es.episodes = (e->es.episodes & ~kEpisodeUsedBit) + 1;
   if (e->mode == 0) env_reset_one<double>(e->sd, e->es, c.snap, c.snap + F16_NUM_STATE_FIELDS, goal, fr);
   else env_reset_one<float>(e->sf, e->es, c.snap, c.snap + F16_NUM_STATE_FIELDS, goal, fr);
+  for (int r = 0; r < 10; ++r) std::memcpy(e->obs[r], fr, 15 * sizeof(float));
+  if (obs_out) std::memcpy(obs_out, e->obs, sizeof(e->obs));
+}
+// JSBSimEnv.reset on the SAME env object (f16_reset_carryover of the C ABI)
+void hs_env_reset_carryover(void* h, const float* goal, const float* last_action, float* obs_out) {
+  HsEnv* e = (HsEnv*)h;
+  const Consts& c = consts();
+  float fr[16];
+  if (e->mode == 0) env_carryover_reset_one<double>(e->sd, e->es, c.Td, c.ms, c.snap, c.snap + F16_NUM_STATE_FIELDS, goal, last_action, fr);
+  else env_carryover_reset_one<float>(e->sf, e->es, c.Tf, c.msf, c.snap, c.snap + F16_NUM_STATE_FIELDS, goal, last_action, fr);
   for (int r = 0; r < 10; ++r) std::memcpy(e->obs[r], fr, 15 * sizeof(float));
   if (obs_out) std::memcpy(obs_out, e->obs, sizeof(e->obs));
 }
@@ -84,6 +94,12 @@ int hs_env_step(void* h, const float* action, int auto_reset, uint64_t seed, uin
       e->sf = s0; e->es = es0;
       flags = env_step_one<float, GROUND_FULL>(e->sf, e->es, c.Tf, c.msf, c.ms, c.snap, c.snap + F16_NUM_STATE_FIELDS, action, seed, env_id, auto_reset, fr, tfr, reward, &ep_ret, &ep_len);
     }
+  }
+  // auto_reset == 2: the finished env keeps its state and is brought up as run_ic() + set-running would (the kernel's
+  // env_carryover_bringup)
+  if (auto_reset == 2 && (flags & STEP_RESET)) {
+    if (e->mode == 0) veh_carryover_reset<double>(e->sd, c.Td, c.ms, c.snap, action, true);
+    else veh_carryover_reset<float>(e->sf, c.Tf, c.msf, c.snap, action, true);
   }
   // same stack update as warp_write_obs
   if (flags & STEP_TERMINAL) {

@@ -65,7 +65,57 @@ def run(seed, actions, with_states):
     return out
 
 
+def run_multi(seeds, action_fn, max_steps=1300):
+    """Several episodes on ONE env object, as train.py's DummyVecEnv drives it: reset() on a used env is run_ic() +
+    set-running on top of whatever the previous episode left in the FCS / Auxiliary / Accelerations models
+    (jsbsim_gym.py:305-306). The packed FDM state is recorded after every reset and every step."""
+    env = gym.make("JSBSim-v0", root=REF)
+    fdm = env.unwrapped.simulation._fdm
+    out = {}
+    for ep, seed in enumerate(seeds):
+        obs, _ = env.reset(seed=seed)
+        actions = action_fn(ep, max_steps)
+        frames, rewards, term_l, trunc_l, states = [], [], [], [], [fdm.pack_state()]
+        for a in actions:
+            o, r, term, trunc, _ = env.step(a)
+            frames.append(o[-1].copy()); rewards.append(np.float32(r)); term_l.append(term); trunc_l.append(trunc)
+            states.append(fdm.pack_state())
+            if term or trunc:
+                break
+        n = len(frames)
+        pre = "ep%d/" % ep
+        out[pre + "goal"] = env.unwrapped.goal.copy()
+        out[pre + "reset_obs"] = obs.copy()
+        out[pre + "actions"] = actions[:n]
+        out[pre + "frames"] = np.stack(frames)
+        out[pre + "rewards"] = np.array(rewards, dtype=np.float32)
+        out[pre + "terminated"] = np.array(term_l)
+        out[pre + "truncated"] = np.array(trunc_l)
+        out[pre + "states"] = np.stack(states)
+        print("one env object, episode", ep, "steps", n, "terminated", bool(term_l[-1]), "truncated", bool(trunc_l[-1]))
+    return out
+
+
+def multi_actions(ep, n):
+    """Episode 0 random, 1 a hard dive (ends in a crash within ~250 steps), 2 gentle, 3 random."""
+    if ep == 1:
+        rng = np.random.default_rng(3100)
+        a = np.stack([0.3 * rng.standard_normal(n), 0.9 + 0.05 * rng.standard_normal(n), 0.1 * rng.standard_normal(n),
+                      0.8 + 0.1 * rng.standard_normal(n)], axis=1)
+        return np.clip(a, LOW, HIGH).astype(np.float32)
+    if ep == 2:
+        return actions_gentle(7, n, 0.2, -0.1, 0.6)
+    return actions_random(40 + ep, n)
+
+
 def main():
+    if "--multi" in sys.argv:
+        flat = run_multi([100, 101, 102, 103], multi_actions)
+        flat["numpy_version"] = np.array(np.__version__)
+        path = os.path.join(ROOT, "tests", "golden", "ref_env_one_object_4_episodes.npz")
+        np.savez_compressed(path, **flat)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+        return
     traces = {}
     for seed in range(4):
         traces["random%d" % seed] = run(seed, actions_random(seed, 1300), with_states=(seed == 0))

@@ -226,6 +226,25 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     ground_other_ms = max_over_ranks(ev0.elapsed_time(ev1), device=dev) / g_steps
 
+    # ---- and with every reference detail on: ground reactions + the carry-over reset (F16_AUTO_RESET_CARRYOVER:
+    # a finished env restarts as the reference's run_ic() leaves a used env object, include/f16_b200.h)
+    import ctypes as _C
+    _f16lib.check(env.lib.f16_set_ground_reactions(env._h, 1), "f16_set_ground_reactions")
+
+    def step_carryover(a):
+        _f16lib.check(env.lib.f16_step(env._h, _C.c_void_p(a.data_ptr()), 2, env._stream()), "f16_step")
+
+    for w in range(3):
+        step_carryover(actions[w % ring])
+    barrier()
+    torch.cuda.synchronize(dev)
+    ev0.record()
+    for k in range(g_steps):
+        step_carryover(actions[k % ring])
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    carry_ms = max_over_ranks(ev0.elapsed_time(ev1), device=dev) / g_steps
+
     # ---- end to end through the public VecEnv API with host buffers
     env.close()
     del env
@@ -290,6 +309,9 @@ def run_ours(args):
                                         "note": "default of the mode (on in fp64, off in fp32); they only act inside the last env-step of a crash",
                                         "other_setting_ms_per_step": ground_other_ms,
                                         "other_setting_value": total_envs / (ground_other_ms * 1e-3)},
+                   "reset": {"timed": "snapshot (finished envs restart from the state of a fresh reference env object)",
+                             "carryover_with_ground_reactions_ms_per_step": carry_ms,
+                             "carryover_with_ground_reactions_value": total_envs / (carry_ms * 1e-3)},
                    "rollout_stats": {"episodes": stats[0], "mean_return": (stats[1] / stats[0]) if stats[0] else None,
                                      "mean_length": (stats[2] / stats[0]) if stats[0] else None, "crashes": stats[3], "goals": stats[4],
                                      "truncations": stats[5]}},

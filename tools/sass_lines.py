@@ -13,8 +13,12 @@ pat = sys.argv[1] if len(sys.argv) > 1 else "step_kernelIfE"
 topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 d = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=d, capture_output=True)
-cubin = [f for f in os.listdir(d) if f.endswith(".cubin")][0]
-txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cubin)], capture_output=True, text=True).stdout
+txt = ""
+for cubin in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):   # one cubin per .cu file of the library
+    t = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cubin)], capture_output=True, text=True).stdout
+    if pat in t:
+        txt = t
+        break
 in_fn, cur, counts, ops_by_line = False, None, collections.Counter(), collections.defaultdict(collections.Counter)
 for line in txt.splitlines():
     if line.startswith("//--------------------- .text."):

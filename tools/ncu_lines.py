@@ -14,7 +14,7 @@ import tempfile
 rep = sys.argv[1]
 pat = sys.argv[2] if len(sys.argv) > 2 else "step_kernelIfE"
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-lib = "f16_jsb_b200/libf16b200.so"
+lib = os.environ.get("F16_B200_LIB", "f16_jsb_b200/libf16b200.so")
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]

@@ -8,7 +8,7 @@ import subprocess
 import sys
 import tempfile
 
-lib = "f16_jsb_b200/libf16b200.so"
+lib = os.environ.get("F16_B200_LIB", "f16_jsb_b200/libf16b200.so")
 pat = sys.argv[1] if len(sys.argv) > 1 else "step_kernelIfE"
 topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 d = tempfile.mkdtemp()

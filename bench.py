@@ -251,7 +251,7 @@ def run_ours(args):
     torch.cuda.empty_cache()
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
 
-    phases, done_rate = {}, {}
+    phases, done_rate, numa = {}, {}, [-1]
 
     def e2e_run(host_obs, rings, dma_both=False):
         """F16VecEnv.step with actions in pinned host memory and NumPy results out, copies and sync inside."""
@@ -281,6 +281,7 @@ def run_ours(args):
         secs = max_over_ranks(time.perf_counter() - t0, device=dev)
         assert obs.shape == (hi - lo, 10, 15) and rew.shape == (hi - lo,) and dones.shape == (hi - lo,)
         if venv._win is not None:
+            numa[0] = venv._win.numa_node
             phases[(host_obs, rings, dma_both)] = {k: round(v, 4) for k, v in venv._win.timing().items() if k != "carry_over_duration" or v}
         venv.close()
         del venv
@@ -324,7 +325,7 @@ def run_ours(args):
                        "download); finished envs' records (144 B each, < 1 % of the envs per step) come through mapped host memory "
                        "and are not counted",
                 "variants": e2e_other, "host_ms_per_step_by_phase": phases.get(("window", 2, False)),
-                "warmup_steps": args.e2e_warmup, "episodes_finished_per_step": done_rate.get(("window", 2, False))},
+                "numa_node_rank0": numa[0], "warmup_steps": args.e2e_warmup, "episodes_finished_per_step": done_rate.get(("window", 2, False))},
         "gpu_launches": int(launches) * world,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic("f16_step_kernel<%s>" % ("float" if mode == "fp32" else "double"), hi - lo),

@@ -57,6 +57,7 @@ def load():
     L.f16_hostwin_reset.argtypes = [vp, vp, vp, C.POINTER(HostwinResult)]
     L.f16_hostwin_step.argtypes = [vp, vp, vp, i32, vp, C.POINTER(HostwinResult)]
     L.f16_hostwin_timing.argtypes = [vp, vp, i32]
+    L.f16_hostwin_numa_node.argtypes = [vp]
     L.f16_hostwin_fill.argtypes = [vp, vp, C.POINTER(HostwinResult)]
     L.f16_hostwin_push.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.POINTER(HostwinResult)]
     L.f16_reset.argtypes = [vp, vp, vp, u64, vp]
@@ -114,5 +115,5 @@ EXPORTED_SYMBOLS = (
     "f16_set_env_step", "f16_get_snapshot", "f16_get_stats", "f16_stats_device_ptr", "f16_launch_count", "f16_num_state_fields",
     "f16_last_error", "f16_version")
 HOSTWIN_SYMBOLS = ("f16_hostwin_create", "f16_hostwin_destroy", "f16_hostwin_layout", "f16_hostwin_action_buffer", "f16_hostwin_reset",
-                   "f16_hostwin_step", "f16_hostwin_timing", "f16_hostwin_fill", "f16_hostwin_push")
+                   "f16_hostwin_step", "f16_hostwin_timing", "f16_hostwin_numa_node", "f16_hostwin_fill", "f16_hostwin_push")
 ROLLOUT_SYMBOLS = ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather", "f16_features17")

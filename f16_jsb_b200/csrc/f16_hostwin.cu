@@ -6,6 +6,8 @@
 // (jsbsim_gym/jsbsim_gym.py:150,235,263) is a strided view of the ring and never has to be assembled.
 #include <cuda_runtime.h>
 #include <emmintrin.h>
+#include <pthread.h>
+#include <sched.h>
 #include <sys/mman.h>
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -54,6 +56,59 @@ int failf(const char* fmt, ...) {
   return f16_internal_fail(buf);
 }
 
+// ---- NUMA locality. On a multi-socket host every rank's frames arrive by DMA from ITS GPU's PCIe root and are then
+// touched by this rank's fix-up and carry-over threads; if the ring pages or those threads sit on the other socket,
+// every byte crosses the inter-socket link twice (measured on the 8-GPU box: the carry-over copy took 10 ms per step
+// instead of 2 ms on the one-GPU box). The ring is therefore first-touched, and the worker threads are kept, on the CPUs
+// of the NUMA node the GPU hangs off (/sys/bus/pci/devices/<bus id>/numa_node). F16_HOSTWIN_NUMA=0 turns it off, =2
+// also leaves the calling thread on that node. Only affinity calls are used (mbind / set_mempolicy are filtered in most
+// containers): memory follows the first touch.
+struct NumaPlace {
+  bool valid = false;
+  int node = -1;
+  cpu_set_t cpus;
+};
+NumaPlace numa_of_device(int device) {
+  NumaPlace p;
+  CPU_ZERO(&p.cpus);
+  const char* e = getenv("F16_HOSTWIN_NUMA");
+  if (e && atoi(e) == 0) return p;
+  char bus[64] = {0};
+  if (device < 0 || cudaDeviceGetPCIBusId(bus, (int)sizeof(bus) - 1, device) != cudaSuccess) { cudaGetLastError(); return p; }
+  for (char* c = bus; *c; ++c) *c = (char)tolower(*c);
+  char path[256];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE* f = fopen(path, "r");
+  if (!f) return p;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  if (node < 0) return p;                       // single-node machine or no affinity information
+  snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+  f = fopen(path, "r");
+  if (!f) return p;
+  char list[4096] = {0};
+  const size_t got = fread(list, 1, sizeof(list) - 1, f);
+  fclose(f);
+  list[got] = 0;
+  cpu_set_t allowed;
+  CPU_ZERO(&allowed);
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return p;
+  int n_set = 0;
+  for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {   // "0-31,64-95"
+    int a = 0, b = 0;
+    const int k = sscanf(tok, "%d-%d", &a, &b);
+    if (k < 1) continue;
+    if (k == 1) b = a;
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+      if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &p.cpus); ++n_set; }
+  }
+  if (n_set == 0) return p;                     // the cgroup gives this process none of that node's CPUs
+  p.valid = true;
+  p.node = node;
+  return p;
+}
+
 struct Ring {
   char* base = nullptr;      // 2 * bytes of address space
   size_t pitch = 0, bytes = 0;
@@ -72,8 +127,11 @@ struct Fix {
 // carry the newest slot over to the second ring in the background between two steps.
 class Pool {
  public:
-  explicit Pool(int n) {
-    for (int i = 0; i < n; ++i) th_.emplace_back([this, i] { worker(i); });
+  explicit Pool(int n, const NumaPlace* place = nullptr) {
+    for (int i = 0; i < n; ++i) {
+      th_.emplace_back([this, i] { worker(i); });
+      if (place && place->valid) pthread_setaffinity_np(th_.back().native_handle(), sizeof(place->cpus), &place->cpus);
+    }
   }
   ~Pool() {
     {
@@ -165,6 +223,7 @@ struct f16_hostwin {
   std::vector<float> term[2];
   std::vector<Fix> pending;              // finished envs of the previous step, still to be applied to the other ring
   int device = -1;
+  int numa_node = -1;                    // node the ring was first-touched on and the workers are kept on (-1: no placement)
   double phase_s[F16_HOSTWIN_PHASES] = {0, 0, 0, 0, 0, 0, 0, 0};   // accumulated wall time per phase of f16_hostwin_step
   int64_t phase_steps = 0;
   std::atomic<int64_t> copy_ns{0};   // duration of the last carry-over, launch to last worker done
@@ -393,11 +452,23 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
       return failf("f16_hostwin_create: F16_HOSTWIN_PIN needs a CUDA device; there is no CPU fallback for the env itself");
     }
   }
+  // NUMA placement (see NumaPlace): the calling thread moves to the GPU's node while the buffers are first touched
+  NumaPlace place;
+  cpu_set_t caller_cpus;
+  bool moved = false;
+  if (w->pin) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) == cudaSuccess) place = numa_of_device(dev);
+    else cudaGetLastError();
+    if (place.valid && sched_getaffinity(0, sizeof(caller_cpus), &caller_cpus) == 0)
+      moved = sched_setaffinity(0, sizeof(place.cpus), &place.cpus) == 0;
+  }
+  w->numa_node = place.valid ? place.node : -1;
   {
     const unsigned hw = std::thread::hardware_concurrency();
     const int nt = (int)std::max(1u, std::min(4u, hw > 2 ? (hw - 1) / 2 : 1u));
-    w->pool = new (std::nothrow) Pool(nt);
-    w->copier = new (std::nothrow) Pool(n_rings == 2 ? nt : 0);
+    w->pool = new (std::nothrow) Pool(nt, &place);
+    w->copier = new (std::nothrow) Pool(n_rings == 2 ? nt : 0, &place);
     if (!w->pool || !w->copier) { delete w->pool; delete w->copier; delete w; return failf("out of host memory"); }
   }
   int rc = 0;
@@ -426,10 +497,16 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
       if (c >= 1 && c <= F16_HOSTWIN_MAX_CHUNKS) w->n_chunks = c;
     }
   }
+  {
+    const char* e = getenv("F16_HOSTWIN_NUMA");
+    if (moved && !(e && atoi(e) == 2)) sched_setaffinity(0, sizeof(caller_cpus), &caller_cpus);
+  }
   if (rc) { f16_hostwin_destroy(w); return rc; }
   *out = w;
   return 0;
 }
+
+int f16_hostwin_numa_node(f16_hostwin_handle w) { return w ? w->numa_node : -1; }
 
 int f16_hostwin_destroy(f16_hostwin_handle w) {
   if (!w) return 0;

@@ -103,6 +103,11 @@ class HostWindow:
 
     PHASES = ("enqueue", "wait_upload_kernel", "fix_older_slots", "wait_d2h", "wait_carry_over", "fix_newest_slot", "hand_off", "carry_over_duration")
 
+    @property
+    def numa_node(self) -> int:
+        """NUMA node the ring lives on and the worker threads run on (-1: no placement); include/f16_hostwin.h."""
+        return int(self.lib.f16_hostwin_numa_node(self._h))
+
     def timing(self, reset: bool = False) -> dict:
         """Average milliseconds per step spent in each phase of f16_hostwin_step since the last reset."""
         out = (C.c_double * 8)()

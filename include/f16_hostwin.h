@@ -93,6 +93,12 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
 enum { F16_HOSTWIN_PHASES = 8 };
 int f16_hostwin_timing(f16_hostwin_handle w, double* seconds_per_step, int reset);
 
+/* NUMA node the pinned buffers were first touched on and the worker threads are kept on: the node of the current
+ * GPU's PCIe root (/sys/bus/pci/devices/<bus id>/numa_node), so that the frame DMA, the fix-ups and the carry-over of
+ * one rank stay on one socket. -1: no placement (single-node host, no information, F16_HOSTWIN_NUMA=0, or none of
+ * that node's CPUs are available to the process). */
+int f16_hostwin_numa_node(f16_hostwin_handle w);
+
 /* The same two operations for a producer that already has the data in host memory (tests, replay):
  * frames N x 15, reward N, done N, truncated N, records[n_done]. No CUDA calls. */
 int f16_hostwin_fill(f16_hostwin_handle w, const float* frames, f16_hostwin_result* out);

@@ -465,8 +465,12 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
   }
   w->numa_node = place.valid ? place.node : -1;
   {
+    // worker threads per pool: up to four (F16_HOSTWIN_THREADS overrides). Measured on the 8-GPU box (32 vCPUs, eight
+    // ranks): 1 / 2 / 4 threads per pool give 6.9e8 / 8.0e8 / 8.1e8 env-steps/s end to end - the carry-over there is bound
+    // by the host's memory system (~90 GB/s of DMA + copy writes over all ranks), not by thread count.
     const unsigned hw = std::thread::hardware_concurrency();
-    const int nt = (int)std::max(1u, std::min(4u, hw > 2 ? (hw - 1) / 2 : 1u));
+    int nt = (int)std::max(1u, std::min(4u, hw > 2 ? (hw - 1) / 2 : 1u));
+    if (const char* e = getenv("F16_HOSTWIN_THREADS")) { const int v = atoi(e); if (v >= 1 && v <= 16) nt = v; }
     w->pool = new (std::nothrow) Pool(nt, &place);
     w->copier = new (std::nothrow) Pool(n_rings == 2 ? nt : 0, &place);
     if (!w->pool || !w->copier) { delete w->pool; delete w->copier; delete w; return failf("out of host memory"); }

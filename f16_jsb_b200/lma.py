@@ -164,6 +164,55 @@ class _MLP(nn.Module):
         return F.dropout(self.c_proj(F.gelu(self.c_fc(x))), self.p, self.training)
 
 
+class _LayerNorm32Fn(torch.autograd.Function):
+    """LayerNorm over 32-channel rows by the kernels of csrc/f16_lma_norm.cu (include/f16_lma.h): statistics are
+    recomputed in the backward, which also reduces the weight / bias gradients."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float):
+        import ctypes as C
+
+        from . import _lib
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        rows = x.numel() // 32
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().f16_lma_layernorm_forward(rows, 32, C.c_void_p(x.data_ptr()), C.c_void_p(weight.data_ptr()),
+                                                             C.c_void_p(bias.data_ptr() if bias is not None else 0), float(eps),
+                                                             C.c_void_p(y.data_ptr()), stream), "f16_lma_layernorm_forward")
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (float(eps), bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        import ctypes as C
+
+        from . import _lib
+        x, weight = ctx.saved_tensors
+        eps, has_bias = ctx.meta
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dw = torch.empty_like(weight)
+        db = torch.empty_like(weight) if has_bias else None
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().f16_lma_layernorm_backward(x.numel() // 32, 32, C.c_void_p(x.data_ptr()), C.c_void_p(weight.data_ptr()),
+                                                              C.c_void_p(dy.data_ptr()), eps, C.c_void_p(dx.data_ptr()),
+                                                              C.c_void_p(dw.data_ptr()), C.c_void_p(db.data_ptr() if db is not None else 0),
+                                                              stream), "f16_lma_layernorm_backward")
+        return dx, dw, db, None
+
+
+def layer_norm32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
+    """LayerNorm over the last axis. CUDA float32 tensors with 32 channels (the reference's LMA shape) go through the
+    hand-written kernels; anything else through torch."""
+    if x.is_cuda and x.dtype == torch.float32 and x.shape[-1] == 32 and weight.dtype == torch.float32:
+        return _LayerNorm32Fn.apply(x, weight, bias, eps)
+    return F.layer_norm(x, weight.shape, weight, bias, eps)
+
+
 class _Norm(nn.Module):
     def __init__(self, dim: int, bias: bool):
         super().__init__()
@@ -171,7 +220,7 @@ class _Norm(nn.Module):
         self.bias = nn.Parameter(torch.zeros(dim)) if bias else None
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return F.layer_norm(x, self.weight.shape, self.weight, self.bias, 1e-5)
+        return layer_norm32(x, self.weight, self.bias, 1e-5)
 
 
 class _Block(nn.Module):

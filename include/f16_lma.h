@@ -27,6 +27,17 @@ int f16_lma_attention_backward(int64_t batch, int seq_len, int heads, int head_d
                                float* dqkv, float dropout_p, uint64_t seed, void* stream);
 /* The keep mask the two kernels use, as floats (0 or 1/(1-p')): [B][H][T][T]. For tests. */
 int f16_lma_attention_mask(int64_t batch, int seq_len, int heads, float* mask, float dropout_p, uint64_t seed, void* stream);
+
+/* LayerNorm over the last axis of the latent tokens (class LayerNorm, jsbsim_gym/LMA_features.py:172-185: weight,
+ * optional bias, eps 1e-5; used as ln_1 / ln_2 of every block, :398-400), rows x 32 float32, contiguous. torch's LayerNorm kernels spend a quarter of an AM-PPO
+ * update on these 128-byte rows (measured); here a warp normalises 32 rows per pass with coalesced
+ * 128-bit accesses and the statistics are recomputed in the backward instead of being stored.
+ * backward: dx (every element written), dweight[32] and dbias[32] (or NULL) are overwritten with the sums over rows.
+ * Only dim = 32 is built; pointers 16-byte aligned. */
+int f16_lma_layernorm_forward(int64_t rows, int dim, const float* x, const float* weight, const float* bias, float eps, float* y,
+                              void* stream);
+int f16_lma_layernorm_backward(int64_t rows, int dim, const float* x, const float* weight, const float* dy, float eps, float* dx,
+                               float* dweight, float* dbias, void* stream);
 #ifdef __cplusplus
 }
 #endif

@@ -103,3 +103,29 @@ def test_learn_two_iterations_with_ring_layout():
     assert algo.num_timesteps == 2 * 16 * 128 and algo.n_updates == 2
     assert np.isfinite(algo.last_stats["value_loss"])
     env.close()
+
+
+@pytest.mark.parametrize("rows,bias", [(5, True), (37, True), (4096 * 5, True), (131072 * 5, False)])
+def test_layernorm32_kernels_match_torch(rows, bias):
+    """csrc/f16_lma_norm.cu against F.layer_norm (the reference's LayerNorm, jsbsim_gym/LMA_features.py:172-185),
+    forward and all three gradients; ragged row counts exercise the tile tail."""
+    import torch.nn.functional as F
+
+    from f16_jsb_b200.lma import layer_norm32
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.randn((rows, 32), generator=g, device="cuda") * 3 + 0.7).requires_grad_(True)
+    w = (1 + 0.3 * torch.randn(32, generator=g, device="cuda")).requires_grad_(True)
+    b = (0.2 * torch.randn(32, generator=g, device="cuda")).requires_grad_(True) if bias else None
+    dy = torch.randn((rows, 32), generator=g, device="cuda")
+    y = layer_norm32(x, w, b)
+    y.backward(dy)
+    got = [y.detach(), x.grad.clone(), w.grad.clone()] + ([b.grad.clone()] if bias else [])
+    x.grad = w.grad = None
+    if bias:
+        b.grad = None
+    y_ref = F.layer_norm(x.double(), (32,), w.double(), b.double() if bias else None, 1e-5)
+    y_ref.backward(dy.double())
+    want = [y_ref.detach(), x.grad, w.grad] + ([b.grad] if bias else [])
+    for a, r, tol in zip(got, want, (2e-6, 1e-5, 1e-5, 1e-5)):
+        scale = float(r.abs().max())
+        assert torch.allclose(a.double(), r.double(), rtol=0, atol=tol * max(1.0, scale)), float((a.double() - r.double()).abs().max())

@@ -145,8 +145,8 @@ class _Attention(nn.Module):
     def __init__(self, dim: int, heads: int, dropout: float, bias: bool):
         super().__init__()
         self.heads, self.p = heads, dropout
-        self.c_attn = nn.Linear(dim, 3 * dim, bias=bias)
-        self.c_proj = nn.Linear(dim, dim, bias=bias)
+        self.c_attn = Linear(dim, 3 * dim, bias=bias)
+        self.c_proj = Linear(dim, dim, bias=bias)
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
         y = latent_attention(self.c_attn(z), self.heads, self.p if self.training else 0.0)
@@ -157,11 +157,57 @@ class _MLP(nn.Module):
     def __init__(self, dim: int, hidden: int, dropout: float, bias: bool):
         super().__init__()
         self.p = dropout
-        self.c_fc = nn.Linear(dim, hidden, bias=bias)
-        self.c_proj = nn.Linear(hidden, dim, bias=bias)
+        self.c_fc = Linear(dim, hidden, bias=bias)
+        self.c_proj = Linear(hidden, dim, bias=bias)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return F.dropout(self.c_proj(F.gelu(self.c_fc(x))), self.p, self.training)
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b with the weight / bias gradients from csrc/f16_lma_wgrad.cu (include/f16_lma.h): for these layers
+    (<= 160 features, 10^5..10^6 rows) the reduction over the batch is the expensive part of the backward and the
+    library GEMM gives it to a handful of CTAs. Forward and the input gradient stay torch matmuls."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        import ctypes as C
+
+        from . import _lib
+        x, weight = ctx.saved_tensors
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = dy.matmul(weight)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            x2 = x.reshape(-1, x.shape[-1]).contiguous()
+            dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+            dw = torch.empty_like(weight)
+            db = torch.empty(weight.shape[0], dtype=weight.dtype, device=weight.device) if ctx.has_bias else None
+            stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            with torch.cuda.device(x.device):
+                _lib.check(_lib.load().f16_lma_linear_wgrad(x2.shape[0], x2.shape[1], dy2.shape[1], C.c_void_p(x2.data_ptr()),
+                                                            C.c_void_p(dy2.data_ptr()), C.c_void_p(dw.data_ptr()),
+                                                            C.c_void_p(db.data_ptr() if db is not None else 0), stream), "f16_lma_linear_wgrad")
+        return dx, dw, db
+
+
+class Linear(nn.Linear):
+    """nn.Linear (same parameters, same state_dict keys) whose backward on CUDA float32 tensors with many rows uses
+    the hand-written weight-gradient kernel."""
+
+    min_rows = 4096      # below this the library GEMM is as good
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if (x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32 and torch.is_grad_enabled()
+                and self.weight.requires_grad and x.numel() // x.shape[-1] >= self.min_rows):
+            return _LinearFn.apply(x, self.weight, self.bias)
+        return F.linear(x, self.weight, self.bias)
 
 
 class _LayerNorm32Fn(torch.autograd.Function):
@@ -240,8 +286,8 @@ class _InitialTransform(nn.Module):
     def __init__(self, cfg: LMAConfig):
         super().__init__()
         self.cfg = cfg
-        self.input_embedding = nn.Linear(cfg.in_features, cfg.embed_dim, bias=cfg.bias)
-        self.embed_layer_2 = nn.Linear(cfg.c_new, cfg.d_new, bias=cfg.bias)
+        self.input_embedding = Linear(cfg.in_features, cfg.embed_dim, bias=cfg.bias)
+        self.embed_layer_2 = Linear(cfg.c_new, cfg.d_new, bias=cfg.bias)
         self.register_buffer("positions", sinusoidal_positions(cfg.seq_len, cfg.embed_dim), persistent=False)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -287,7 +333,7 @@ class LMAExtractor(nn.Module):
 def _mlp(sizes, act=nn.Tanh) -> nn.Sequential:
     layers = []
     for i in range(len(sizes) - 1):
-        layers += [nn.Linear(sizes[i], sizes[i + 1]), act()]
+        layers += [Linear(sizes[i], sizes[i + 1]), act()]
     return nn.Sequential(*layers)
 
 
@@ -310,8 +356,8 @@ class LMAActorCritic(nn.Module):
         self.features_extractor = LMAExtractor(cfg)
         d = self.features_extractor.features_dim
         self.mlp_extractor = _MlpExtractor(d, pi, vf)
-        self.action_net = nn.Linear(pi[-1], action_dim)
-        self.value_net = nn.Linear(vf[-1], 1)
+        self.action_net = Linear(pi[-1], action_dim)
+        self.value_net = Linear(vf[-1], 1)
         self.log_std = nn.Parameter(torch.full((action_dim,), float(log_std_init)))
         if ortho_init:
             for mod, gain in ((self.features_extractor, math.sqrt(2)), (self.mlp_extractor, math.sqrt(2)), (self.action_net, 0.01),

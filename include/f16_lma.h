@@ -38,6 +38,15 @@ int f16_lma_layernorm_forward(int64_t rows, int dim, const float* x, const float
                               void* stream);
 int f16_lma_layernorm_backward(int64_t rows, int dim, const float* x, const float* weight, const float* dy, float eps, float* dx,
                                float* dweight, float* dbias, void* stream);
+
+/* Weight and bias gradients of one of the policy's Linear layers (torch.nn.Linear of the LMA extractor,
+ * jsbsim_gym/LMA_features.py:221-279,315-385, and of SB3's MlpExtractor / action_net / value_net,
+ * stable_baselines3/common/torch_layers.py:MlpExtractor, common/policies.py:560-600):
+ * dweight[out][in] = sum over rows of dy[row][out] * x[row][in], dbias[out] = sum over rows of dy[row][out] (or NULL).
+ * x: rows x in_features, dy: rows x out_features, row-major float32; both outputs are overwritten. Any shape; built
+ * for in / out <= 160 and 10^5..10^6 rows, where the reduction runs over the batch. */
+int f16_lma_linear_wgrad(int64_t rows, int in_features, int out_features, const float* x, const float* dy, float* dweight,
+                         float* dbias, void* stream);
 #ifdef __cplusplus
 }
 #endif

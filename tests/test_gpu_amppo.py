@@ -129,3 +129,28 @@ def test_layernorm32_kernels_match_torch(rows, bias):
     for a, r, tol in zip(got, want, (2e-6, 1e-5, 1e-5, 1e-5)):
         scale = float(r.abs().max())
         assert torch.allclose(a.double(), r.double(), rtol=0, atol=tol * max(1.0, scale)), float((a.double() - r.double()).abs().max())
+
+
+@pytest.mark.parametrize("rows,fin,fout,bias", [(4096, 17, 64, True), (5 * 4099, 128, 32, True), (131072, 32, 96, True), (65536, 32, 128, False),
+                                                 (40000, 160, 64, True), (40000, 160, 128, True), (50000, 64, 4, True), (50001, 64, 1, True)])
+def test_linear_weight_gradient_kernel_matches_torch(rows, fin, fout, bias):
+    """csrc/f16_lma_wgrad.cu through the autograd wiring of lma.Linear, against a float64 torch reference: every
+    layer shape of the policy (train.py:21-32,84), ragged row counts."""
+    from f16_jsb_b200.lma import Linear
+    g = torch.Generator(device="cuda").manual_seed(5)
+    lin = Linear(fin, fout, bias=bias).cuda()
+    x = torch.randn((rows, fin), generator=g, device="cuda", requires_grad=True)
+    dy = torch.randn((rows, fout), generator=g, device="cuda")
+    y = lin(x)
+    assert y.grad_fn is not None and "LinearFn" in type(y.grad_fn).__name__
+    y.backward(dy)
+    got = [x.grad.clone(), lin.weight.grad.clone()] + ([lin.bias.grad.clone()] if bias else [])
+    xd = x.detach().double().requires_grad_(True)
+    wd = lin.weight.detach().double().requires_grad_(True)
+    bd = lin.bias.detach().double().requires_grad_(True) if bias else None
+    torch.nn.functional.linear(xd, wd, bd).backward(dy.double())
+    want = [xd.grad, wd.grad] + ([bd.grad] if bias else [])
+    for a, r in zip(got, want):
+        # sums of `rows` products of unit-variance numbers in float32: error ~ sqrt(rows) * 6e-8 * sqrt(rows)
+        tol = 2e-6 * max(1.0, float(r.abs().max()))
+        assert torch.allclose(a.double(), r, rtol=0, atol=tol), (float((a.double() - r).abs().max()), tol)

@@ -178,7 +178,7 @@ class AMPPO:
         if c.cuda_graph and self._graph is None:
             self._capture_act()
         self.buffer.reset()
-        for _ in range(c.n_steps):
+        for step in range(c.n_steps):
             if self._graph is not None:
                 self._g_obs.copy_(self._obs)            # the env shifts its observation tensor in place: keep this step's
                 self._graph.replay()
@@ -188,15 +188,46 @@ class AMPPO:
                 obs = self._obs.contiguous().clone()
                 actions, values, log_probs, clipped = self._act(obs)
             new_obs, rewards, dones, truncated = env.step(clipped, auto_reset=True)
-            rewards = rewards.clone()
-            tr = truncated.nonzero().flatten()          # time-limit bootstrap (:236-245); rare (step 1200 of an episode)
-            if tr.numel():
-                rewards[tr] += c.gamma * self.policy.predict_values(env.terminal_obs.index_select(0, tr))
+            self._note_truncations(step, truncated)
             self.buffer.add(obs, actions, rewards, self._episode_starts, values, log_probs)
             self._obs, self._episode_starts = new_obs, dones.clone()
             self.num_timesteps += env.num_envs
+        self._bootstrap_truncations()
         last_values = self.policy.predict_values(self._obs.contiguous())
         self.buffer.compute_returns_and_advantage(last_values, self._episode_starts)
+
+    # Time-limit bootstrap (on_policy_algorithm.py:236-245): reward += gamma * V(terminal observation) for episodes cut
+    # at step 1200. The reference does it inside the step loop; asking "was anybody truncated?" there costs one host
+    # synchronisation per env-step (it was 60 % of the rollout's host time). The policy does not change during a
+    # rollout, so the terminal observations of truncated envs are parked in a side buffer by index arithmetic on the
+    # device and all of them are valued once, after the last step - the same numbers, one synchronisation per rollout.
+    def _truncation_store(self):
+        if getattr(self, "_tr_obs", None) is None:
+            n, c = self.env.num_envs, self.cfg
+            cap = n * (c.n_steps // 1200 + 1)                       # an env is truncated at most once per 1200 steps
+            self._tr_cap = cap
+            self._tr_obs = torch.zeros((cap + 1,) + tuple(self.env.terminal_obs.shape[1:]), dtype=torch.float32, device=self.device)
+            self._tr_flat = torch.zeros(cap + 1, dtype=torch.int64, device=self.device)
+            self._tr_count = torch.zeros((), dtype=torch.int64, device=self.device)
+            self._tr_env = torch.arange(n, dtype=torch.int64, device=self.device)
+        return self._tr_obs
+
+    def _note_truncations(self, step: int, truncated: torch.Tensor) -> None:
+        self._truncation_store()
+        tr = truncated.to(torch.int64)
+        slot = torch.where(tr > 0, self._tr_count + torch.cumsum(tr, 0) - 1, self._tr_cap)      # non-truncated rows go to the spare slot
+        self._tr_obs.index_copy_(0, slot, self.env.terminal_obs)
+        self._tr_flat.index_copy_(0, slot, self._tr_env + step * self.env.num_envs)
+        self._tr_count += tr.sum()
+
+    def _bootstrap_truncations(self) -> None:
+        if getattr(self, "_tr_obs", None) is None:
+            return
+        n = int(self._tr_count.item())
+        if n:
+            v = self.policy.predict_values(self._tr_obs[:n])
+            self.buffer.rewards.view(-1).index_add_(0, self._tr_flat[:n], self.cfg.gamma * v)      # rewards are (step, env)
+        self._tr_count.zero_()
 
     # ------------------------------------------------------------------ update (ppo.py:271-455)
     def train(self) -> None:

@@ -94,6 +94,52 @@ def test_rollout_and_update_run_on_device(use_am_ppo, optimizer):
     env.close()
 
 
+def test_time_limit_bootstrap_is_deferred_without_changing_rewards():
+    """on_policy_algorithm.py:236-245 adds gamma * V(terminal_observation) to the reward of a truncated env inside the
+    step loop. AMPPO parks the terminal observations and values them after the last step (no host synchronisation per
+    env-step); the stored rewards must equal those of the in-loop form."""
+    from f16_jsb_b200 import F16BatchedEnv, _lib
+    from f16_jsb_b200.amppo import AMPPO, AMPPOConfig
+
+    class InLoop(AMPPO):
+        def _note_truncations(self, step, truncated):
+            self._pending = None
+            tr = truncated.nonzero().flatten()
+            if tr.numel():
+                self._pending = (tr, self.cfg.gamma * self.policy.predict_values(self.env.terminal_obs.index_select(0, tr)))
+                self._hits = getattr(self, "_hits", 0) + int(tr.numel())
+
+        def _bootstrap_truncations(self):
+            pass
+
+    results = []
+    for cls in (AMPPO, InLoop):
+        torch.manual_seed(11)
+        env = F16BatchedEnv(64, mode="fp32", seed=6)
+        algo = cls(env, AMPPOConfig(n_steps=10, batch_size=320, n_epochs=1, seed=9, cuda_graph=False))
+        algo._obs = env.reset()
+        algo._episode_starts = torch.ones(64, dtype=torch.uint8, device=env.device)
+        for i in range(12):                      # envs 0..11 reach step 1200 during this rollout
+            _lib.check(env.lib.f16_set_env_step(env._h, i, 1191 + (i % 9)), "f16_set_env_step")
+        if cls is InLoop:
+            orig_add = algo.buffer.add
+
+            def add(obs, actions, rewards, es, values, log_probs, _orig=orig_add, _a=algo):
+                rewards = rewards.clone()
+                if _a._pending is not None:
+                    rewards[_a._pending[0]] += _a._pending[1]
+                _orig(obs, actions, rewards, es, values, log_probs)
+            algo.buffer.add = add
+        torch.manual_seed(12)
+        algo.collect_rollouts()
+        results.append((algo.buffer.rewards.clone(), algo.buffer.returns.clone(), getattr(algo, "_hits", None)))
+        env.close()
+    assert results[1][2] == 12
+    assert torch.allclose(results[0][0], results[1][0], rtol=0, atol=1e-6), float((results[0][0] - results[1][0]).abs().max())
+    assert float((results[0][0] - results[1][0]).abs().max()) < 1e-6 and float(results[0][0].abs().max()) > 0.5
+    assert torch.allclose(results[0][1], results[1][1], rtol=0, atol=1e-5)
+
+
 def test_learn_two_iterations_with_ring_layout():
     from f16_jsb_b200 import F16BatchedEnv
     from f16_jsb_b200.amppo import AMPPO, AMPPOConfig

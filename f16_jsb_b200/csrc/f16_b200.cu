@@ -672,19 +672,7 @@ const char* f16_version(void) { return "f16_b200 0.1 (sm_100a)"; }
 int64_t f16_launch_count(void) { return g_launches; }
 int f16_num_state_fields(void) { return F16_NUM_STATE_FIELDS; }
 
-int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
-  if (!out) return fail("f16_create: out is NULL");
-  *out = nullptr;
-  if (n_envs <= 0) return fail("f16_create: n_envs must be positive (got %lld)", (long long)n_envs);
-  if (mode != F16_MODE_FP64 && mode != F16_MODE_FP32) return fail("f16_create: unknown mode %d", mode);
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0)
-    return fail("f16_create: no CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
-  if (device < 0 || device >= ndev) return fail("f16_create: device %d out of range [0,%d)", device, ndev);
-  CUDA_OK(cudaSetDevice(device));
-  f16_ctx* c = new (std::nothrow) f16_ctx;
-  if (!c) return fail("out of host memory");
+static int create_impl(f16_ctx* c, int64_t n_envs, int device, int mode) {
   c->device = device;
   c->mode = mode;
   c->L = make_layout(n_envs, mode);
@@ -697,14 +685,14 @@ int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
   CUDA_OK(cudaMemcpyToSymbol(c_msets, ms, sizeof(ms)));
   CUDA_OK(cudaMemcpyToSymbol(c_msets_f, msf, sizeof(msf)));
   int rc = mode == F16_MODE_FP64 ? upload_tables<double>(c) : upload_tables<float>(c);
-  if (rc) { delete c; return rc; }
+  if (rc) return rc;
   CUDA_OK(cudaMalloc(&c->stats_dev, F16_NUM_STATS * sizeof(double)));
   CUDA_OK(cudaMemset(c->stats_dev, 0, F16_NUM_STATS * sizeof(double)));
   CUDA_OK(cudaMalloc(&c->scratch_dev, 2 * (F16_NUM_STATE_FIELDS + 12) * sizeof(double)));
   // canonical snapshot: always computed in double, with a double table image
   {
     Tables<double>* hT = new (std::nothrow) Tables<double>;
-    if (!hT) { delete c; return fail("out of host memory"); }
+    if (!hT) return fail("out of host memory");
     host::build_tables<double>(hT);
     Tables<double>* dT = nullptr;
     CUDA_OK(cudaMalloc(&dT, sizeof(Tables<double>)));
@@ -730,6 +718,26 @@ int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
   if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, 1, OBS_STACKED, true>, BLOCK, 0));
   else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float, F16_MIN_BLOCKS_F32, OBS_STACKED, false>, BLOCK, 0));
   if (c->ctas_per_sm < 1) c->ctas_per_sm = 1;
+  return 0;
+}
+
+int f16_create(f16_handle* out, int64_t n_envs, int device, int mode) {
+  if (!out) return fail("f16_create: out is NULL");
+  *out = nullptr;
+  if (n_envs <= 0) return fail("f16_create: n_envs must be positive (got %lld)", (long long)n_envs);
+  if (mode != F16_MODE_FP64 && mode != F16_MODE_FP32) return fail("f16_create: unknown mode %d", mode);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("f16_create: no CUDA device (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return fail("f16_create: device %d out of range [0,%d)", device, ndev);
+  CUDA_OK(cudaSetDevice(device));
+  f16_ctx* c = new (std::nothrow) f16_ctx;
+  if (!c) return fail("out of host memory");
+  // everything that can fail after the context exists runs in create_impl, so that one f16_destroy releases whatever
+  // had been allocated by then
+  const int rc = create_impl(c, n_envs, device, mode);
+  if (rc) { f16_destroy(c); return rc; }
   *out = c;
   return 0;
 }

@@ -378,18 +378,6 @@ __device__ __noinline__ void env_step_ground(const StatePtrs<R> sp, int64_t e, c
   store_env(es, sp, e);
 }
 
-// Carry-over reset of an env that finished in this step with auto_reset == 2 (veh_carryover_reset, f16_env.cuh): the
-// env's end-of-episode state is already back in HBM; run_ic()'s two zero-dt frames and set-running are applied to
-// it here. Cold (one lane of a warp, ~0.1 % of the envs per step under random actions) and not inlined.
-template <typename R>
-__device__ __noinline__ void env_carryover_bringup(const StatePtrs<R> sp, int64_t e, const Tables<R>* T, float4 action) {
-  Veh<R> s;
-  load_veh(s, sp, e);
-  const float act[4] = {action.x, action.y, action.z, action.w};
-  veh_carryover_reset<R>(s, *T, msets_for<R>(), c_snapshot, act, true);
-  store_veh(s, sp, e);
-}
-
 #ifndef F16_PERSISTENT
 #define F16_PERSISTENT 0
 #endif
@@ -476,8 +464,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
         store_veh(s, sp, e);
         store_env(es, sp, e);
       }
-      if (GROUND && a.auto_reset == 2 && (flags & STEP_RESET))
-        env_carryover_bringup<R>(sp, e, &T, make_float4(act[0], act[1], act[2], act[3]));
       a.reward[e] = reward;
       a.done[e] = (flags & STEP_DONE) ? 1 : 0;
       a.truncated[e] = (flags & STEP_TRUNCATED) ? 1 : 0;

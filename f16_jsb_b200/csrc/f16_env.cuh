@@ -317,13 +317,18 @@ F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const Mas
   FrameObs<R> fo;
   FrameCfg cfg = {kDt, 0.0, MS_FLIGHT};
   constexpr bool GROUND = GMODE == GROUND_FULL;
+  // The reference-detail instantiations (ground reactions on) also carry the carry-over reset (auto_reset == 2): an env
+  // that finishes keeps its state, gets its kinematic state re-initialised and runs run_ic()'s two zero-dt frames
+  // as iterations 4 and 5 of this very loop (veh_carryover_reset spelled out; the frame takes dt at run time there).
+  constexpr bool CARRY = GMODE != GROUND_OFF;
   GroundMem gm;      // friction multipliers of the contacts (GROUND_FULL only; contact is confined to one env-step)
   if (GROUND) gm.started = 0;
   int first_touch = 4;
+  int n_frames = 4, flags = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < (CARRY ? n_frames : 4); ++k) {
 #ifdef __CUDA_ARCH__
 #ifndef F16_PREFETCH_AT_FRAME
 #define F16_PREFETCH_AT_FRAME 3
@@ -335,19 +340,40 @@ F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const Mas
 #endif
     // the first flight frame after a fresh construct still carries the mass properties of the 1500-lb tanks' CG
     const bool first = es.step == 1 && k == 0 && !(es.episodes & kEpisodeUsedBit);
-    fdm_frame<R, false, GMODE != GROUND_OFF>(s, T, msets, cfg, cmd, first, fo);
-    if (GROUND) {
-      if (fo.may_touch) ground_fix<R>(s, fo, msets_d[first ? MS_FLIGHT_FIRST : MS_FLIGHT], gm);
-      else if (gm.started) { for (int i = 0; i < 3 * kNumStructure; ++i) gm.lm[i] = 0.0; }   // FGLGear: not compressed
-    } else if (GMODE == GROUND_DETECT) {
-      if (fo.may_touch && first_touch == 4) first_touch = k;
+    fdm_frame<R, false, GMODE != GROUND_OFF, CARRY>(s, T, msets, cfg, cmd, first, fo);
+    if (!CARRY || k < 4) {
+      if (GROUND) {
+        if (fo.may_touch) ground_fix<R>(s, fo, msets_d[first ? MS_FLIGHT_FIRST : MS_FLIGHT], gm);
+        else if (gm.started) { for (int i = 0; i < 3 * kNumStructure; ++i) gm.lm[i] = 0.0; }   // FGLGear: not compressed
+      } else if (GMODE == GROUND_DETECT) {
+        if (fo.may_touch && first_touch == 4) first_touch = k;
+      }
+    }
+    if (CARRY && k == 3) {           // (the ground-less instantiation keeps its epilogue after the loop, below)
+      flags = env_step_epilogue<R>(s, es, fo, snapshot, snapshot_props, seed, env_id, auto_reset, frame16, tframe16, reward_out,
+                                   ep_ret_out, ep_len_out);
+      // (with the carry-over reset nothing is discarded: a last-frame contact's accelerations feed the next episode)
+      if (GMODE == GROUND_DETECT && first_touch < 4 && !(first_touch == 3 && (flags & STEP_RESET) && auto_reset != 2))
+        return STEP_ACTIVE | STEP_NEAR_GROUND;
+      if (CARRY && auto_reset == 2 && (flags & STEP_RESET)) {
+        Veh<R> ic;
+        veh_from_packed(ic, snapshot);
+        for (int i = 0; i < 4; ++i) s.q[i] = ic.q[i];                     // FGPropagate::SetInitialState
+        for (int i = 0; i < 3; ++i) { s.ri[i] = ic.ri[i]; s.vi[i] = ic.vi[i]; s.wi[i] = ic.wi[i]; }
+        s.epa = ic.epa;
+        cfg.dt = 0.0;
+        n_frames = 6;
+      }
     }
   }
-  const int flags = env_step_epilogue<R>(s, es, fo, snapshot, snapshot_props, seed, env_id, auto_reset, frame16, tframe16,
-                                         reward_out, ep_ret_out, ep_len_out);
-  // (with the carry-over reset nothing is discarded: those accelerations feed the pilot load factors of the next episode)
-  if (GMODE == GROUND_DETECT && first_touch < 4 && !(first_touch == 3 && (flags & STEP_RESET) && auto_reset != 2))
-    return STEP_ACTIVE | STEP_NEAR_GROUND;
+  if (!CARRY)
+    return env_step_epilogue<R>(s, es, fo, snapshot, snapshot_props, seed, env_id, auto_reset, frame16, tframe16, reward_out, ep_ret_out,
+                                ep_len_out);
+  if (CARRY && n_frames == 6) {
+    for (int i = 0; i < 3; ++i) { s.vi1[i] = (R)s.vi[i]; s.vi2[i] = (R)s.vi[i]; }   // InitializeDerivatives
+    s.n2 = (R)(f16data::idlen2 + 1.0 * (f16data::maxn2 - f16data::idlen2));       // InitRunning + GetSteadyState
+    s.aug = R(0);
+  }
   return flags;
 }
 

@@ -95,12 +95,7 @@ int hs_env_step(void* h, const float* action, int auto_reset, uint64_t seed, uin
       flags = env_step_one<float, GROUND_FULL>(e->sf, e->es, c.Tf, c.msf, c.ms, c.snap, c.snap + F16_NUM_STATE_FIELDS, action, seed, env_id, auto_reset, fr, tfr, reward, &ep_ret, &ep_len);
     }
   }
-  // auto_reset == 2: the finished env keeps its state and is brought up as run_ic() + set-running would (the kernel's
-  // env_carryover_bringup)
-  if (auto_reset == 2 && (flags & STEP_RESET)) {
-    if (e->mode == 0) veh_carryover_reset<double>(e->sd, c.Td, c.ms, c.snap, action, true);
-    else veh_carryover_reset<float>(e->sf, c.Tf, c.msf, c.snap, action, true);
-  }
+  // (auto_reset == 2: env_step_one itself runs the two zero-dt frames of the carry-over reset)
   // same stack update as warp_write_obs
   if (flags & STEP_TERMINAL) {
     std::memcpy(e->tobs[0], e->obs[1], 9 * 15 * sizeof(float));

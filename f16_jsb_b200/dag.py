@@ -106,7 +106,9 @@ class DAG(Optimizer):
             if group["maximize"]:
                 updates = torch._foreach_neg(updates)
             torch._foreach_add_(params, updates, alpha=-group["lr"])
-            sq = torch.stack([(u.double() * u.double()).sum() for u in updates]).sum()
+            # sum of squares of the whole update (sgd.py:318-322) from one multi-tensor norm instead of three launches
+            # per parameter tensor; the squares are added in float64
+            sq = (torch.stack(torch._foreach_norm(updates, 2)).double() ** 2).sum()
             total_sq = sq if total_sq is None else total_sq + sq
             total_n += sum(p.numel() for p in params)
         if total_n:

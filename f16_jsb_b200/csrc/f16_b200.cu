@@ -160,21 +160,7 @@ struct StepArgs {
   f16_done_record* done_list;   // frame layout only: one record per env that finished this step (may be mapped host memory)
   int32_t* done_count;          // frame layout only: device counter of appended records
   int64_t tile0;                // first 32-env tile of this launch (f16_step_range); n is the end of the range
-  // Low tiles first (ground-reaction instantiations, whole-batch launches): a lane that redoes its step with the
-  // contact forces runs alone for two to three ordinary step times, and if its tile is scheduled late that is the
-  // tail of the launch. Every warp therefore reports at the end of a step whether one of its envs is below
-  // kLowAltitudeM and still flying; the next launch starts with `prio_ctas` CTAs that walk that list, and the regular
-  // CTAs skip the listed tiles. Ordering only: every tile is still stepped exactly once.
-  const int32_t* prio_list;     // tiles listed by the previous launch (NULL: plain order)
-  const int32_t* prio_count;    // how many
-  const uint8_t* prio_flag;     // 1 for listed tiles
-  int32_t* next_list;           // what this launch reports for the next one
-  int32_t* next_count;
-  uint8_t* next_flag;
-  int prio_cap;                 // capacity of the lists
-  int prio_ctas;                // CTAs at the head of the grid that take their tiles from prio_list
 };
-constexpr float kLowAltitudeM = 25.0f;   // an env can only reach the ground within one env-step from below ~20 m
 
 template <typename R>
 __device__ __forceinline__ StatePtrs<R> state_ptrs(void* state, size_t r_off, size_t e_off, int64_t np) {
@@ -426,20 +412,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
   for (int64_t tile = a.tile0 + (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += warps_total) {
 #else
   (void)warps_total;
-  int64_t tile;
-  bool listed = false;
-  if (GROUND && a.prio_list) {
-    if ((int)blockIdx.x < a.prio_ctas) {
-      const int idx = (int)blockIdx.x * WARPS + warp;
-      const int cnt = min(*a.prio_count, a.prio_cap);
-      tile = idx < cnt ? (int64_t)a.prio_list[idx] : n_tiles;
-    } else {
-      tile = a.tile0 + (int64_t)((int)blockIdx.x - a.prio_ctas) * WARPS + warp;
-      if (tile < n_tiles) listed = a.prio_flag[tile] != 0;     // checked after the state loads have been issued
-    }
-  } else {
-    tile = a.tile0 + (int64_t)blockIdx.x * WARPS + warp;
-  }
+  const int64_t tile = a.tile0 + (int64_t)blockIdx.x * WARPS + warp;
   if (tile < n_tiles) {
 #endif
     const int64_t env0 = tile << 5;
@@ -450,11 +423,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
       EnvScalars es;
       load_veh(s, sp, e);
       load_env(es, sp, e);
-#if !F16_PERSISTENT
-      // this tile was taken by one of the CTAs at the head of the grid (warp-uniform; tested only now so that the
-      // flag's round trip hides behind the state loads; lanes past the end of the batch leave right after this block)
-      if (GROUND && listed) return;
-#endif
       const uint64_t gid = (uint64_t)(a.env_id_base + e);
       float act[4];
       if (a.actions) {
@@ -527,24 +495,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
         }
       }
     }
-#if !F16_PERSISTENT
-    if (GROUND && listed) return;
-#endif
     flags_s[warp][lane] = (uint8_t)(flags & (STEP_ACTIVE | STEP_RESET | STEP_TERMINAL));
     __syncwarp();
-    if (GROUND && a.next_list) {
-      // report for the next launch: an env of this tile is low and still flying (frame column 2 = altitude in metres)
-      const bool low = (flags & STEP_ACTIVE) && !(flags & STEP_RESET) && !(flags & STEP_DONE) && frame_s[warp][lane][2] < kLowAltitudeM;
-      const unsigned any_low = __ballot_sync(0xffffffffu, low);
-      if (lane == 0) {
-        uint8_t f = 0;
-        if (any_low) {
-          const int idx = atomicAdd(a.next_count, 1);
-          if (idx < a.prio_cap) { a.next_list[idx] = (int32_t)tile; f = 1; }
-        }
-        a.next_flag[tile] = f;
-      }
-    }
     if (OBS == OBS_FRAME) warp_write_frames(a.obs, env0, a.n, frame_s[warp]);
     else if (OBS == OBS_RING) warp_write_ring(a.obs, a.terminal_obs, env0, a.ring_slot, frame_s[warp], tframe_s[warp], flags_s[warp]);
     else warp_write_obs(a.obs, a.terminal_obs, env0, frame_s[warp], tframe_s[warp], flags_s[warp]);
@@ -671,13 +623,6 @@ struct f16_ctx {
   f16_done_record* done_list = nullptr;   // frame layout: where the step kernel appends finished envs
   int32_t* done_count = nullptr;
   int ground = 1;                         // ground reactions (f16_set_ground_reactions); default: on in FP64 mode, off in FP32 mode
-  // low-tiles-first ordering (StepArgs): two generations of {list, count, flag}, written by one launch, read by the next
-  int32_t* prio_list[2] = {nullptr, nullptr};
-  int32_t* prio_count = nullptr;          // 2 counters
-  uint8_t* prio_flag[2] = {nullptr, nullptr};
-  int prio_cap = 0, prio_gen = 0;
-  bool prio_valid = false;                // the current generation was written by the previous whole-batch launch
-  int prio_enabled = 1;                   // F16_PRIORITY=0 turns the ordering off
 };
 
 template <typename R>
@@ -754,18 +699,6 @@ static int create_impl(f16_ctx* c, int64_t n_envs, int device, int mode) {
     CUDA_OK(cudaMemcpyToSymbol(c_snapshot_props, c->snapshot + F16_NUM_STATE_FIELDS, 12 * sizeof(double)));
   }
   CUDA_OK(cudaMalloc(&c->actions_stage, (size_t)n_envs * F16_ACTION_DIM * sizeof(float)));
-  {
-    const int64_t n_tiles = c->L.np / 32;
-    c->prio_cap = (int)std::min<int64_t>(n_tiles, std::max<int64_t>(WARPS, (n_tiles / 8 + WARPS - 1) / WARPS * WARPS));   // 1/8 of the tiles
-    for (int g = 0; g < 2; ++g) {
-      CUDA_OK(cudaMalloc(&c->prio_list[g], (size_t)c->prio_cap * sizeof(int32_t)));
-      CUDA_OK(cudaMalloc(&c->prio_flag[g], (size_t)n_tiles));
-      CUDA_OK(cudaMemset(c->prio_flag[g], 0, (size_t)n_tiles));
-    }
-    CUDA_OK(cudaMalloc(&c->prio_count, 2 * sizeof(int32_t)));
-    CUDA_OK(cudaMemset(c->prio_count, 0, 2 * sizeof(int32_t)));
-    if (const char* e = getenv("F16_PRIORITY")) c->prio_enabled = atoi(e) != 0;
-  }
 
   CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, 1, OBS_STACKED, true>, BLOCK, 0));
@@ -802,8 +735,6 @@ int f16_destroy(f16_handle h) {
   cudaFree(h->stats_dev);
   cudaFree(h->scratch_dev);
   cudaFree(h->actions_stage);
-  for (int g = 0; g < 2; ++g) { cudaFree(h->prio_list[g]); cudaFree(h->prio_flag[g]); }
-  cudaFree(h->prio_count);
   delete h;
   return 0;
 }
@@ -928,26 +859,6 @@ static int launch_step(f16_handle h, const float* actions, int auto_reset, int64
   int64_t want = (int64_t)h->num_sms * h->ctas_per_sm;
   const int64_t need = (tiles + WARPS - 1) / WARPS;
   unsigned grid = (unsigned)((F16_PERSISTENT && want < need) ? want : need);
-  // low tiles first: whole-batch launches of the ground-reaction instantiations (a piece of f16_step_range neither
-  // reads nor writes the lists; ordering information that skipped a step is merely older)
-  a.prio_list = nullptr; a.prio_count = nullptr; a.prio_flag = nullptr;
-  a.next_list = nullptr; a.next_count = nullptr; a.next_flag = nullptr;
-  a.prio_cap = h->prio_cap; a.prio_ctas = 0;
-  const bool whole = first == 0 && count == h->L.n;
-  if (!F16_PERSISTENT && h->ground && h->prio_enabled && whole) {
-    const int cur = h->prio_gen, nxt = cur ^ 1;
-    CUDA_OK(cudaMemsetAsync(h->prio_count + nxt, 0, sizeof(int32_t), (cudaStream_t)stream));
-    a.next_list = h->prio_list[nxt]; a.next_count = h->prio_count + nxt; a.next_flag = h->prio_flag[nxt];
-    if (h->prio_valid) {
-      a.prio_list = h->prio_list[cur]; a.prio_count = h->prio_count + cur; a.prio_flag = h->prio_flag[cur];
-      a.prio_ctas = (h->prio_cap + WARPS - 1) / WARPS;
-      grid += (unsigned)a.prio_ctas;
-    }
-    h->prio_gen = nxt;
-    h->prio_valid = true;
-  } else if (!whole) {
-    h->prio_valid = false;        // the lists describe the batch as of an older step: start over at the next whole-batch launch
-  }
 
   const cudaStream_t st = (cudaStream_t)stream;
 #define F16_LAUNCH_STEP_G(R, MINB, G)                                                                      \

@@ -206,7 +206,7 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = total_envs * args.steps / (ms_total * 1e-3)
     st = env.stats()
-    stats_t = torch.tensor([st[k] for k in ("episodes", "return_sum", "length_sum", "crashes", "goals", "truncations", "env_steps", "reserved")],
+    stats_t = torch.tensor([st[k] for k in ("episodes", "return_sum", "length_sum", "crashes", "goals", "truncations", "env_steps", "ground_redos")],
                            dtype=torch.float64, device=dev)
     allreduce_stats(stats_t)                        # the only collective: rollout statistics over NVLink
     stats = stats_t.cpu().tolist()
@@ -315,7 +315,7 @@ def run_ours(args):
                              "carryover_with_ground_reactions_value": total_envs / (carry_ms * 1e-3)},
                    "rollout_stats": {"episodes": stats[0], "mean_return": (stats[1] / stats[0]) if stats[0] else None,
                                      "mean_length": (stats[2] / stats[0]) if stats[0] else None, "crashes": stats[3], "goals": stats[4],
-                                     "truncations": stats[5]}},
+                                     "truncations": stats[5], "ground_redos": stats[7]}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total_envs * 16, "d2h_bytes_per_step": total_envs * (60 + 4 + 1 + 1),
                 "steps": e2e_steps,

@@ -15,7 +15,7 @@ from .constants import NUM_FEATURES, NUM_STACKED_FRAMES
 
 MODE_FP64, MODE_FP32 = 0, 1
 NUM_STATS = 8
-STAT_NAMES = ("episodes", "return_sum", "length_sum", "crashes", "goals", "truncations", "env_steps", "reserved")
+STAT_NAMES = ("episodes", "return_sum", "length_sum", "crashes", "goals", "truncations", "env_steps", "ground_redos")
 
 
 def _ptr(t: Optional[torch.Tensor]):

@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
         // a contact point reached the ground (last env-step of a crash): redo the step with the contact forces
         // from the state still in HBM; the cold copy stores the new state itself
         GroundStepOut go;
+        if (a.stats) atomicAdd(a.stats + 7, 1.0);
         env_step_ground<R>(sp, e, &T, make_float4(act[0], act[1], act[2], act[3]), a.seed, gid, a.auto_reset,
                            frame_s[warp][lane], tframe_s[warp][lane], &go);
         flags = go.flags; reward = go.reward; ep_ret = go.ep_ret; ep_len = go.ep_len;

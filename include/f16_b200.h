@@ -159,7 +159,8 @@ int f16_get_snapshot(f16_handle h, double* state_out, double* props12_out);
 
 /* Rollout statistics accumulated on the device since the last call with reset != 0:
  * [0] episodes finished, [1] sum of episode returns, [2] sum of episode lengths, [3] crashes,
- * [4] goals reached, [5] truncations, [6] env-steps, [7] reserved. Synchronises `stream`. */
+ * [4] goals reached, [5] truncations, [6] env-steps, [7] env-steps redone with ground-contact forces (ground
+ * reactions on). Synchronises `stream`. */
 int f16_get_stats(f16_handle h, double* out8, int reset, void* stream);
 /* Device pointer to those 8 doubles (for an NCCL all-reduce by the caller). */
 int f16_stats_device_ptr(f16_handle h, double** out);

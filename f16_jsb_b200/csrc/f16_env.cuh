@@ -324,56 +324,63 @@ F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const Mas
   GroundMem gm;      // friction multipliers of the contacts (GROUND_FULL only; contact is confined to one env-step)
   if (GROUND) gm.started = 0;
   int first_touch = 4;
-  int n_frames = 4, flags = 0;
+  int flags = 0;
+  // Two passes over ONE copy of the frame loop: the four frames of the step, then - carry-over reset only - run_ic()'s
+  // two zero-dt frames. The epilogue sits between the passes, outside the inner loop, so the loop body the warps
+  // spend their time in stays as small as in the ground-less instantiation (instruction cache).
 #ifdef __CUDA_ARCH__
 #pragma unroll 1
 #endif
-  for (int k = 0; k < (CARRY ? n_frames : 4); ++k) {
+  for (int pass = 0; pass < (CARRY ? 2 : 1); ++pass) {
+    const int k_end = pass == 0 ? 4 : 2;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (int k = 0; k < k_end; ++k) {
 #ifdef __CUDA_ARCH__
 #ifndef F16_PREFETCH_AT_FRAME
 #define F16_PREFETCH_AT_FRAME 3
 #endif
-    if (k == F16_PREFETCH_AT_FRAME) {
-      if (pf.count < 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.ptr), "r"(pf.stride) : "memory");
-      for (int i = 0; i < pf.count; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf.ptr + (size_t)i * pf.stride));
-    }
+      if (pass == 0 && k == F16_PREFETCH_AT_FRAME) {
+        if (pf.count < 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.ptr), "r"(pf.stride) : "memory");
+        for (int i = 0; i < pf.count; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf.ptr + (size_t)i * pf.stride));
+      }
 #endif
-    // the first flight frame after a fresh construct still carries the mass properties of the 1500-lb tanks' CG
-    const bool first = es.step == 1 && k == 0 && !(es.episodes & kEpisodeUsedBit);
-    fdm_frame<R, false, GMODE != GROUND_OFF, CARRY>(s, T, msets, cfg, cmd, first, fo);
-    if (!CARRY || k < 4) {
-      if (GROUND) {
-        if (fo.may_touch) ground_fix<R>(s, fo, msets_d[first ? MS_FLIGHT_FIRST : MS_FLIGHT], gm);
-        else if (gm.started) { for (int i = 0; i < 3 * kNumStructure; ++i) gm.lm[i] = 0.0; }   // FGLGear: not compressed
-      } else if (GMODE == GROUND_DETECT) {
-        if (fo.may_touch && first_touch == 4) first_touch = k;
+      // the first flight frame after a fresh construct still carries the mass properties of the 1500-lb tanks' CG
+      const bool first = es.step == 1 && k == 0 && pass == 0 && !(es.episodes & kEpisodeUsedBit);
+      fdm_frame<R, false, GMODE != GROUND_OFF, CARRY>(s, T, msets, cfg, cmd, first, fo);
+      if (pass == 0) {
+        if (GROUND) {
+          if (fo.may_touch) ground_fix<R>(s, fo, msets_d[first ? MS_FLIGHT_FIRST : MS_FLIGHT], gm);
+          else if (gm.started) { for (int i = 0; i < 3 * kNumStructure; ++i) gm.lm[i] = 0.0; }   // FGLGear: not compressed
+        } else if (GMODE == GROUND_DETECT) {
+          if (fo.may_touch && first_touch == 4) first_touch = k;
+        }
       }
     }
-    if (CARRY && k == 3) {           // (the ground-less instantiation keeps its epilogue after the loop, below)
-      flags = env_step_epilogue<R>(s, es, fo, snapshot, snapshot_props, seed, env_id, auto_reset, frame16, tframe16, reward_out,
-                                   ep_ret_out, ep_len_out);
-      // (with the carry-over reset nothing is discarded: a last-frame contact's accelerations feed the next episode)
-      if (GMODE == GROUND_DETECT && first_touch < 4 && !(first_touch == 3 && (flags & STEP_RESET) && auto_reset != 2))
-        return STEP_ACTIVE | STEP_NEAR_GROUND;
-      if (CARRY && auto_reset == 2 && (flags & STEP_RESET)) {
-        Veh<R> ic;
-        veh_from_packed(ic, snapshot);
-        for (int i = 0; i < 4; ++i) s.q[i] = ic.q[i];                     // FGPropagate::SetInitialState
-        for (int i = 0; i < 3; ++i) { s.ri[i] = ic.ri[i]; s.vi[i] = ic.vi[i]; s.wi[i] = ic.wi[i]; }
-        s.epa = ic.epa;
-        cfg.dt = 0.0;
-        n_frames = 6;
-      }
+    if (!CARRY) break;
+    if (pass == 1) {
+      for (int i = 0; i < 3; ++i) { s.vi1[i] = (R)s.vi[i]; s.vi2[i] = (R)s.vi[i]; }   // InitializeDerivatives
+      s.n2 = (R)(f16data::idlen2 + 1.0 * (f16data::maxn2 - f16data::idlen2));       // InitRunning + GetSteadyState
+      s.aug = R(0);
+      break;
     }
+    flags = env_step_epilogue<R>(s, es, fo, snapshot, snapshot_props, seed, env_id, auto_reset, frame16, tframe16, reward_out,
+                                 ep_ret_out, ep_len_out);
+    // (with the carry-over reset nothing is discarded: a last-frame contact's accelerations feed the next episode)
+    if (GMODE == GROUND_DETECT && first_touch < 4 && !(first_touch == 3 && (flags & STEP_RESET) && auto_reset != 2))
+      return STEP_ACTIVE | STEP_NEAR_GROUND;
+    if (!(auto_reset == 2 && (flags & STEP_RESET))) break;
+    Veh<R> ic;
+    veh_from_packed(ic, snapshot);
+    for (int i = 0; i < 4; ++i) s.q[i] = ic.q[i];                     // FGPropagate::SetInitialState
+    for (int i = 0; i < 3; ++i) { s.ri[i] = ic.ri[i]; s.vi[i] = ic.vi[i]; s.wi[i] = ic.wi[i]; }
+    s.epa = ic.epa;
+    cfg.dt = 0.0;
   }
   if (!CARRY)
     return env_step_epilogue<R>(s, es, fo, snapshot, snapshot_props, seed, env_id, auto_reset, frame16, tframe16, reward_out, ep_ret_out,
                                 ep_len_out);
-  if (CARRY && n_frames == 6) {
-    for (int i = 0; i < 3; ++i) { s.vi1[i] = (R)s.vi[i]; s.vi2[i] = (R)s.vi[i]; }   // InitializeDerivatives
-    s.n2 = (R)(f16data::idlen2 + 1.0 * (f16data::maxn2 - f16data::idlen2));       // InitRunning + GetSteadyState
-    s.aug = R(0);
-  }
   return flags;
 }
 

@@ -117,6 +117,7 @@ void build_tables(Tables<R>* T) {
   memset(T, 0, sizeof(*T));
   for (int i = 0; i < NA; ++i) {
     for (int k = 0; k < A1_N; ++k) T->A1[i][k] = (R)A1[i][k];
+    for (int k = A1_N; k < A1_N + 4; ++k) T->A1[i][k] = (R)0;        // row padding (bank spreading, f16_model.cuh)
     for (int j = 0; j < NDE; ++j)
       for (int k = 0; k < 4; ++k) T->AE[i][j][k] = (R)AE[i][j][k];
     for (int j = 0; j < NB7; ++j)

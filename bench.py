@@ -315,7 +315,8 @@ def run_ours(args):
                              "carryover_with_ground_reactions_value": total_envs / (carry_ms * 1e-3)},
                    "rollout_stats": {"episodes": stats[0], "mean_return": (stats[1] / stats[0]) if stats[0] else None,
                                      "mean_length": (stats[2] / stats[0]) if stats[0] else None, "crashes": stats[3], "goals": stats[4],
-                                     "truncations": stats[5], "ground_redos": stats[7]}},
+                                     "truncations": stats[5], "ground_redos": stats[7],
+                                     "note": "episodes that ENDED inside the timed steps: with all envs reset together shortly before, long episodes are under-represented (an unbiased 6 000-step run gives a mean length of ~855, tools/soak.py)"}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total_envs * 16, "d2h_bytes_per_step": total_envs * (60 + 4 + 1 + 1),
                 "steps": e2e_steps,

@@ -304,7 +304,8 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if mode == "fp32" else "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": n_env, "total_envs": total_envs, "mode": mode,
-                   "frames_per_env_step": 4, "fdm_frames_per_s": value * 4, "l2": "inputs larger than L2 (state+obs %.0f MB per GPU); no flush" % ((hi - lo) * (bpe - 22) / 2e6),
+                   "frames_per_env_step": 4,
+                   "actions": "uniform over the action Box, 8 distinct (N,4) batches resident in HBM before the timed region and used in turn (the 16 B per env-step of the roofline's action read); in-kernel Philox actions (f16_step(actions=NULL)) give the same rate", "fdm_frames_per_s": value * 4, "l2": "inputs larger than L2 (state+obs %.0f MB per GPU); no flush" % ((hi - lo) * (bpe - 22) / 2e6),
                    "parallelism": "env-sharded x%d, no data-path collective" % world,
                    "ground_reactions": {"timed": "on" if ground_main else "off",
                                         "note": "default of the mode (on in fp64, off in fp32); they only act inside the last env-step of a crash",

@@ -165,28 +165,15 @@ class _MLP(nn.Module):
 
 
 class _LinearFn(torch.autograd.Function):
-    """y = x W^T + b by csrc/f16_lma_linear.cu (bias fused) with the weight / bias gradients from csrc/f16_lma_wgrad.cu
-    (include/f16_lma.h): for these layers (<= 160 features, 10^5..10^6 rows) the reduction over the batch is the expensive
-    part of the backward and the library GEMM gives it to a handful of CTAs. The input gradient stays a torch matmul."""
+    """y = x W^T + b with the weight / bias gradients from csrc/f16_lma_wgrad.cu (include/f16_lma.h): for these layers
+    (<= 160 features, 10^5..10^6 rows) the reduction over the batch is the expensive part of the backward and the
+    library GEMM gives it to a handful of CTAs. Forward and the input gradient stay torch matmuls."""
 
     @staticmethod
     def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]):
-        import ctypes as C
-
-        from . import _lib
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        if torch.backends.cuda.matmul.allow_tf32:      # the caller asked for tensor-core matmuls: leave it to the library
-            return F.linear(x, weight, bias)
-        x2 = x.reshape(-1, x.shape[-1]).contiguous()
-        w = weight.contiguous()
-        y = torch.empty(x.shape[:-1] + (weight.shape[0],), dtype=torch.float32, device=x.device)
-        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-        with torch.cuda.device(x.device):
-            _lib.check(_lib.load().f16_lma_linear_forward(x2.shape[0], x2.shape[1], w.shape[0], C.c_void_p(x2.data_ptr()), C.c_void_p(w.data_ptr()),
-                                                          C.c_void_p(bias.data_ptr() if bias is not None else 0), C.c_void_p(y.data_ptr()),
-                                                          stream), "f16_lma_linear_forward")
-        return y
+        return F.linear(x, weight, bias)
 
     @staticmethod
     def backward(ctx, dy: torch.Tensor):

@@ -45,11 +45,6 @@ int f16_lma_layernorm_backward(int64_t rows, int dim, const float* x, const floa
  * dweight[out][in] = sum over rows of dy[row][out] * x[row][in], dbias[out] = sum over rows of dy[row][out] (or NULL).
  * x: rows x in_features, dy: rows x out_features, row-major float32; both outputs are overwritten. Any shape; built
  * for in / out <= 160 and 10^5..10^6 rows, where the reduction runs over the batch. */
-/* Forward of the same layers with the bias fused: y[row][o] = sum_k x[row][k] * weight[o][k] + bias[o] (bias may be
- * NULL). x: rows x in_features, weight: out_features x in_features (torch.nn.Linear layout), y: rows x out_features,
- * row-major float32. FP32 FMA. */
-int f16_lma_linear_forward(int64_t rows, int in_features, int out_features, const float* x, const float* weight, const float* bias,
-                           float* y, void* stream);
 int f16_lma_linear_wgrad(int64_t rows, int in_features, int out_features, const float* x, const float* dy, float* dweight,
                          float* dbias, void* stream);
 #ifdef __cplusplus

@@ -231,6 +231,36 @@ def test_random_action_rollout_full_size_properties(F16BatchedEnv):
     assert s["crashes"] + s["goals"] + s["truncations"] == s["episodes"]
 
 
+def test_results_do_not_depend_on_how_the_envs_are_sharded(F16BatchedEnv):
+    """env ids are partitioned contiguously over the ranks and every random draw (goals on reset and
+    auto-reset, in-kernel actions) is keyed by the GLOBAL env id, so one batch of N envs and two shards of it (env_id_base
+    = 0 and N/2, as distributed.shard_range hands them out) produce bit-identical observations, rewards and flags."""
+    from f16_jsb_b200 import _lib
+    n, half, steps = 4096 + 64, 2048 + 32, 40
+    whole = F16BatchedEnv(n, mode="fp32", seed=21)
+    parts = [F16BatchedEnv(half, mode="fp32", seed=21, env_id_base=0), F16BatchedEnv(half, mode="fp32", seed=21, env_id_base=half)]
+    for e in [whole] + parts:
+        e.reset()
+    # some envs are about to hit the time limit: their auto-reset goals must come out the same in either arrangement
+    for i in range(0, n, 97):
+        _lib.check(whole.lib.f16_set_env_step(whole._h, i, 1190 + i % 9), "f16_set_env_step")
+        p, j = divmod(i, half)
+        _lib.check(parts[p].lib.f16_set_env_step(parts[p]._h, j, 1190 + i % 9), "f16_set_env_step")
+    finished = 0
+    for k in range(steps):
+        o, r, d, t = whole.step(None, auto_reset=True)
+        outs = [e.step(None, auto_reset=True) for e in parts]
+        assert torch.equal(o, torch.cat([x[0] for x in outs])), k
+        assert torch.equal(r, torch.cat([x[1] for x in outs])) and torch.equal(d, torch.cat([x[2] for x in outs]))
+        assert torch.equal(t, torch.cat([x[3] for x in outs]))
+        finished += int(d.sum().item())
+    assert finished >= n // 97
+    assert torch.equal(whole.pack_states(), torch.cat([e.pack_states() for e in parts]))
+    sw, sp = whole.stats(), [e.stats() for e in parts]
+    for key in ("episodes", "truncations", "crashes", "length_sum", "env_steps"):
+        assert sw[key] == sp[0][key] + sp[1][key], key
+
+
 @pytest.mark.parametrize("mode", ["fp32", "fp64"])
 def test_ring_layout_is_value_identical_to_stacked(F16BatchedEnv, mode):
     """obs_layout='ring' (frame written twice, zero-copy window view) must return the stacks, rewards,

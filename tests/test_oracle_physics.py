@@ -26,7 +26,8 @@ NAMES = ["attitude/phi-rad", "attitude/theta-rad", "attitude/psi-rad", "velociti
          "position/long-gc-rad", "forces/fbx-aero-lbs", "forces/fby-aero-lbs", "forces/fbz-aero-lbs", "forces/fbx-prop-lbs",
          "moments/l-aero-lbsft", "moments/m-aero-lbsft", "moments/n-aero-lbsft", "moments/m-prop-lbsft", "inertia/mass-slugs",
          "inertia/ixx-slugs_ft2", "inertia/iyy-slugs_ft2", "inertia/izz-slugs_ft2", "inertia/ixz-slugs_ft2",
-         "accelerations/gravity-ft_sec2"]
+         "accelerations/gravity-ft_sec2", "aero/alpha-rad", "aero/beta-rad", "velocities/mach", "velocities/vt-fps", "atmosphere/a-fps",
+         "atmosphere/rho-slugs_ft3", "aero/qbar-psf", "atmosphere/T-R", "atmosphere/P-psf"]
 
 
 @pytest.fixture(scope="module")
@@ -125,3 +126,19 @@ def test_translational_dynamics(flight):
         worst = max(worst, np.abs(fd - pred).max())
         biggest = max(biggest, np.abs(pred).max())
     assert biggest > 60.0 and worst < 0.5, (worst, biggest)       # ft/s2; measured 0.15: Coriolis + centrifugal + transport terms
+
+
+def test_air_data_identities(flight):
+    """alpha = atan2(w, u), beta = atan2(v, sqrt(u2 + w2)), Vt = |uvw| (no wind), Mach = Vt / a, qbar = rho Vt2 / 2,
+    a = sqrt(gamma R T), rho = P / (R T) - the Auxiliary and atmosphere outputs agree with the state they are made from."""
+    R_AIR = 1716.5574933  # ft lbf / (slug R): 8.31432 J/(mol K) / 28.9645 g/mol in engineering units
+    for h in flight[1:]:
+        u, v, w = _uvw(h)
+        vt = np.sqrt(u * u + v * v + w * w)
+        assert h["aero/alpha-rad"] == pytest.approx(np.arctan2(w, u), abs=1e-12)
+        assert h["aero/beta-rad"] == pytest.approx(np.arctan2(v, np.hypot(u, w)), abs=1e-12)
+        assert h["velocities/vt-fps"] == pytest.approx(vt, rel=1e-12)
+        assert h["velocities/mach"] == pytest.approx(vt / h["atmosphere/a-fps"], rel=1e-12)
+        assert h["aero/qbar-psf"] == pytest.approx(0.5 * h["atmosphere/rho-slugs_ft3"] * vt * vt, rel=1e-12)
+        assert h["atmosphere/a-fps"] == pytest.approx(np.sqrt(1.4 * R_AIR * h["atmosphere/T-R"]), rel=1e-6)
+        assert h["atmosphere/rho-slugs_ft3"] == pytest.approx(h["atmosphere/P-psf"] / (R_AIR * h["atmosphere/T-R"]), rel=1e-6)

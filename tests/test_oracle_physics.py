@@ -142,3 +142,14 @@ def test_air_data_identities(flight):
         assert h["aero/qbar-psf"] == pytest.approx(0.5 * h["atmosphere/rho-slugs_ft3"] * vt * vt, rel=1e-12)
         assert h["atmosphere/a-fps"] == pytest.approx(np.sqrt(1.4 * R_AIR * h["atmosphere/T-R"]), rel=1e-6)
         assert h["atmosphere/rho-slugs_ft3"] == pytest.approx(h["atmosphere/P-psf"] / (R_AIR * h["atmosphere/T-R"]), rel=1e-6)
+
+
+def test_gravity_at_the_initial_condition(oracle):
+    """J2 gravity on the equator, 5 000 ft above the WGS84 ellipsoid: GM / r2 * (1 + 1.5 J2 (a / r)2), evaluated here from the
+    published constants (GM = 3.986004418e14 m3/s2, a = 6 378 137 m, J2 = 1.08262982e-3)."""
+    env = oracle.OracleEnv()
+    env.reset(np.array([5000.0, 0.0, 2000.0], np.float32))
+    ft = 0.3048
+    gm, a, j2 = 3.986004418e14 / ft ** 3, 6378137.0 / ft, 1.08262982e-3
+    r = a + 5000.0
+    assert env.fdm["accelerations/gravity-ft_sec2"] == pytest.approx(gm / r ** 2 * (1 + 1.5 * j2 * (a / r) ** 2), rel=1e-9)

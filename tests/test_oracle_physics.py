@@ -27,7 +27,8 @@ NAMES = ["attitude/phi-rad", "attitude/theta-rad", "attitude/psi-rad", "velociti
          "moments/l-aero-lbsft", "moments/m-aero-lbsft", "moments/n-aero-lbsft", "moments/m-prop-lbsft", "inertia/mass-slugs",
          "inertia/ixx-slugs_ft2", "inertia/iyy-slugs_ft2", "inertia/izz-slugs_ft2", "inertia/ixz-slugs_ft2",
          "accelerations/gravity-ft_sec2", "aero/alpha-rad", "aero/beta-rad", "velocities/mach", "velocities/vt-fps", "atmosphere/a-fps",
-         "atmosphere/rho-slugs_ft3", "aero/qbar-psf", "atmosphere/T-R", "atmosphere/P-psf"]
+         "atmosphere/rho-slugs_ft3", "aero/qbar-psf", "atmosphere/T-R", "atmosphere/P-psf",
+         "accelerations/n-pilot-y-norm", "accelerations/n-pilot-z-norm", "inertia/cg-x-in", "inertia/cg-y-in", "inertia/cg-z-in"]
 
 
 @pytest.fixture(scope="module")
@@ -153,3 +154,27 @@ def test_gravity_at_the_initial_condition(oracle):
     gm, a, j2 = 3.986004418e14 / ft ** 3, 6378137.0 / ft, 1.08262982e-3
     r = a + 5000.0
     assert env.fdm["accelerations/gravity-ft_sec2"] == pytest.approx(gm / r ** 2 * (1 + 1.5 * j2 * (a / r) ** 2), rel=1e-9)
+
+
+def test_pilot_accelerations(flight):
+    """The load factors the pitch and yaw control laws feed on (aircraft/f16/f16.xml:502-761) are the specific force at the
+    eyepoint (f16.xml:50-54): n = [F / m + wdot x r + w x (w x r)] / g0 with r from the CG to the eyepoint in body axes -
+    formed, as FGAuxiliary does, from the forces and moments of the PREVIOUS frame and this frame's rates. In level flight
+    n-pilot-z is -1 (z points down)."""
+    eye = np.array([-336.2, 0.0, 29.5])                           # structural frame, inches
+    g0 = 9.80665 / 0.3048
+    worst = 0.0
+    for z, a in zip(flight[2:-1], flight[3:]):
+        cg = np.array([z["inertia/cg-x-in"], z["inertia/cg-y-in"], z["inertia/cg-z-in"]])
+        r = (eye - cg) / 12.0 * np.array([-1.0, 1.0, -1.0])       # structural -> body axes, feet
+        ixz = z["inertia/ixz-slugs_ft2"]
+        J = np.array([[z["inertia/ixx-slugs_ft2"], 0, -ixz], [0, z["inertia/iyy-slugs_ft2"], 0], [-ixz, 0, z["inertia/izz-slugs_ft2"]]])
+        M = np.array([z["moments/l-aero-lbsft"], z["moments/m-aero-lbsft"] + z["moments/m-prop-lbsft"], z["moments/n-aero-lbsft"]])
+        wz = _pqr(z)
+        wdot = np.linalg.solve(J, M - np.cross(wz, J @ wz))
+        F = np.array([z["forces/fbx-aero-lbs"] + z["forces/fbx-prop-lbs"], z["forces/fby-aero-lbs"], z["forces/fbz-aero-lbs"]]) / z["inertia/mass-slugs"]
+        w = _pqr(a)
+        n = (F + np.cross(wdot, r) + np.cross(w, np.cross(w, r))) / g0
+        worst = max(worst, abs(a["accelerations/n-pilot-z-norm"] - n[2]), abs(a["accelerations/n-pilot-y-norm"] - n[1]))
+    assert worst < 1e-4, worst                                    # g; measured 2e-5 (inertial against earth-relative rates)
+    assert -1.5 < flight[1]["accelerations/n-pilot-z-norm"] < -0.5

@@ -223,12 +223,13 @@ def test_gpu_auto_reset_carryover_free_run_vs_one_oracle_object_per_env(oracle, 
 
 
 @pytest.mark.gpu
-def test_gpu_vecenv_carryover_through_host_windows(oracle, state_fields):
+@pytest.mark.parametrize("host_obs", ["window", "copy"])
+def test_gpu_vecenv_carryover_through_host_windows(oracle, state_fields, host_obs):
     """F16VecEnv(reset_mode="carryover") - NumPy in / NumPy out through the host-resident windows - against one
     oracle env object per env: terminal observations, reset observations and everything after them."""
     from f16_jsb_b200 import F16VecEnv
     n, steps = 96, 420
-    venv = F16VecEnv(n, mode="fp64", reset_mode="carryover", seed=2)
+    venv = F16VecEnv(n, mode="fp64", reset_mode="carryover", seed=2, host_obs=host_obs)
     venv.seed(500)
     obs = venv.reset()
     refs = [oracle.OracleEnv() for _ in range(n)]

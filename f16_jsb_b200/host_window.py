@@ -54,11 +54,22 @@ class HostWindow:
             self._rings.append((flat, pitch.value))
             self.aliased.append(bool(aliased.value))
         self.action_buffers = [_as_array(self.lib.f16_hostwin_action_buffer(h, k), (self.num_envs, 4), np.float32) for k in (0, 1)]
+        self._action_addr = [(b, b.ctypes.data) for b in self.action_buffers]
         self._res = _lib.HostwinResult()
+        # the library hands out the same few buffers over and over (22 window positions, two sets of scalars): build each
+        # NumPy view once - at a few thousand envs constructing them was a third of a step's wall time
+        self._views = {}
+
+    def _view(self, ptr: int, shape, dtype) -> np.ndarray:
+        key = (ptr, shape)
+        v = self._views.get(key)
+        if v is None:
+            v = self._views[key] = _as_array(ptr, shape, dtype)
+        return v
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
-            self._rings, self.action_buffers = [], []
+            self._rings, self.action_buffers, self._views, self._action_addr = [], [], {}, []
             self.lib.f16_hostwin_destroy(self._h)
             self._h = C.c_void_p(0)
 
@@ -71,9 +82,13 @@ class HostWindow:
     # ------------------------------------------------------------------ views
     def window(self, ring: int, first_slot: int) -> np.ndarray:
         """(N,10,15) float32 strided view: row k of env n lives in slot first_slot + k."""
-        flat, pitch = self._rings[ring]
-        v = np.lib.stride_tricks.as_strided(flat[first_slot * (pitch // 4):], shape=(self.num_envs, NUM_STACKED_FRAMES, NUM_FEATURES),
-                                            strides=(NUM_FEATURES * 4, pitch, 4))
+        key = ("window", ring, first_slot)
+        v = self._views.get(key)
+        if v is None:
+            flat, pitch = self._rings[ring]
+            v = self._views[key] = np.lib.stride_tricks.as_strided(flat[first_slot * (pitch // 4):],
+                                                                   shape=(self.num_envs, NUM_STACKED_FRAMES, NUM_FEATURES),
+                                                                   strides=(NUM_FEATURES * 4, pitch, 4))
         return v
 
     def _result(self) -> StepResult:
@@ -81,9 +96,9 @@ class HostWindow:
         out = StepResult()
         out.ring, out.first_slot = int(r.ring), int(r.first_slot)
         out.obs = self.window(out.ring, out.first_slot)
-        out.reward = _as_array(r.reward, (n,), np.float32)
-        out.done = _as_array(r.done, (n,), np.uint8)
-        out.truncated = _as_array(r.truncated, (n,), np.uint8)
+        out.reward = self._view(r.reward, (n,), np.float32)
+        out.done = self._view(r.done, (n,), np.uint8)
+        out.truncated = self._view(r.truncated, (n,), np.uint8)
         k = int(r.n_done)
         out.records = _as_array(r.records, (k,), RECORD_DTYPE).copy() if (k and r.records) else np.empty(0, dtype=RECORD_DTYPE)
         out.terminal_obs = (_as_array(r.terminal_obs, (k, NUM_STACKED_FRAMES, NUM_FEATURES), np.float32) if (k and r.terminal_obs)
@@ -97,7 +112,13 @@ class HostWindow:
 
     def step(self, env, actions: np.ndarray, stream_ptr, auto_reset: bool = True) -> StepResult:
         assert actions.dtype == np.float32 and actions.flags.c_contiguous and actions.shape == (self.num_envs, 4)
-        _lib.check(self.lib.f16_hostwin_step(self._h, env._h, C.c_void_p(actions.ctypes.data), int(auto_reset), stream_ptr,
+        addr = None
+        for b, a in self._action_addr:                     # the pinned staging buffers come back every other step
+            if actions is b:
+                addr = a
+        if addr is None:
+            addr = actions.ctypes.data
+        _lib.check(self.lib.f16_hostwin_step(self._h, env._h, C.c_void_p(addr), int(auto_reset), stream_ptr,
                                              C.byref(self._res)), "f16_hostwin_step")
         return self._result()
 

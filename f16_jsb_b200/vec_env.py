@@ -174,6 +174,10 @@ class F16VecEnv(VecEnvBase):
         return self._act_bufs[self._act_next]
 
     def step_async(self, actions: np.ndarray) -> None:
+        for b in self._act_bufs:                      # the caller filled one of our pinned staging buffers
+            if actions is b:
+                self._actions = b
+                return
         a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 4)
         for b in self._act_bufs:
             if a.ctypes.data == b.ctypes.data:

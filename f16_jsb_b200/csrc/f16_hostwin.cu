@@ -398,7 +398,7 @@ void carry_over(f16_hostwin* w, int ring_src) {
   const char* src = (const char*)w->row(ring_src, w->head, 0);
   char* dst = (char*)w->row(ring_dst, w->head, 0);
   char* dst2 = w->ring[ring_dst].aliased ? nullptr : (char*)w->row(ring_dst, w->head + SLOTS, 0);
-  if (bytes < ((size_t)1 << 20) || w->copier->size() == 0) {
+  if (bytes < ((size_t)1 << 16) || w->copier->size() == 0) {    // below 64 KB the copy is cheaper than waking a thread
     memcpy(dst, src, bytes);
     if (dst2) memcpy(dst2, src, bytes);
     return;

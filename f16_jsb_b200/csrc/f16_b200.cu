@@ -654,6 +654,15 @@ int f16_internal_frame_buffers(f16_handle h, int64_t* n, int* device, float** ob
   return 0;
 }
 
+// shared with f16_hostwin.cu: where the frame layout's step kernel stores the newest frames (device memory, or pinned
+// host memory mapped into the device's address space)
+int f16_internal_set_obs_frame(f16_handle h, float* obs_frame) {
+  if (!h || !h->state || h->ring != OBS_FRAME) return fail("the env is not bound in the frame layout (f16_bind_frames)");
+  if (!obs_frame) return fail("obs_frame is NULL");
+  h->obs = obs_frame;
+  return 0;
+}
+
 const char* f16_last_error(void) { return g_err.c_str(); }
 const char* f16_version(void) { return "f16_b200 0.1 (sm_100a)"; }
 int64_t f16_launch_count(void) { return g_launches; }

@@ -30,6 +30,7 @@
 #include "../../include/f16_hostwin.h"
 
 extern "C" int f16_internal_fail(const char* msg);
+extern "C" int f16_internal_set_obs_frame(f16_handle h, float* obs_frame);
 extern "C" int f16_internal_frame_buffers(f16_handle h, int64_t* n, int* device, float** obs_frame, float** reward, uint8_t** done,
                                           uint8_t** truncated, float** actions_stage);
 
@@ -116,6 +117,7 @@ struct Ring {
   bool registered = false;   // cudaHostRegister-ed (aliased) / cudaHostAlloc-ed (mirror)
   bool pinned_alloc = false;
   int fd = -1;
+  char* dev_base = nullptr;  // device address of `base` when the ring is mapped into the GPU's address space (zero-copy frames)
 };
 
 struct Fix {
@@ -218,6 +220,7 @@ struct f16_hostwin {
   int32_t* count_host = nullptr;
   cudaEvent_t ev = nullptr, fork = nullptr;
   int n_chunks = 1;                      // pieces one step is pipelined in (upload | kernel | download)
+  int zero_copy = 1;                     // 1: single-piece steps let the kernel write its frames straight into the ring; 2: every step; 0: never
   cudaStream_t cs[F16_HOSTWIN_MAX_CHUNKS] = {};
   cudaEvent_t kdone[F16_HOSTWIN_MAX_CHUNKS] = {};
   std::vector<float> term[2];
@@ -262,13 +265,16 @@ bool make_aliased(Ring& g, bool pin) {
   if (a == MAP_FAILED || b == MAP_FAILED) { munmap(span, 2 * g.bytes); close(fd); return false; }
   if (pin) {
     // DMA only ever targets the first mapping; the second is read by the CPU alone
-    if (cudaHostRegister(span, g.bytes, cudaHostRegisterPortable) != cudaSuccess) {
+    if (cudaHostRegister(span, g.bytes, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
       cudaGetLastError();
       munmap(span, 2 * g.bytes);
       close(fd);
       return false;
     }
     g.registered = true;
+    void* dev = nullptr;
+    if (cudaHostGetDevicePointer(&dev, span, 0) == cudaSuccess) g.dev_base = (char*)dev;
+    else cudaGetLastError();
   }
   g.base = (char*)span;
   g.fd = fd;
@@ -496,6 +502,7 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
     }
     // a step is worth cutting in pieces once a piece still fills the GPU for a wave or two
     w->n_chunks = n_envs >= 524288 ? 4 : n_envs >= 131072 ? 2 : 1;
+    if (const char* e = getenv("F16_HOSTWIN_ZEROCOPY")) w->zero_copy = atoi(e);
     if (const char* e = getenv("F16_HOSTWIN_CHUNKS")) {
       const int c = atoi(e);
       if (c >= 1 && c <= F16_HOSTWIN_MAX_CHUNKS) w->n_chunks = c;
@@ -668,6 +675,17 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
   const int64_t per = ((w->n + C - 1) / C + 127) / 128 * 128;
   rc = f16_step_begin(env, stream);
   if (rc) return rc;
+  // Zero-copy frames: the ring is mapped into the GPU's address space, so the step kernel can store its newest frames
+  // (one contiguous 1 920-byte span per warp) straight into this step's slot over PCIe while it runs, instead of writing
+  // them to HBM and handing them to the copy engine afterwards. That removes the copy's launch latency and the
+  // kernel -> copy serialisation, which is what a step of a few thousand envs consists of; large batches are bound by the
+  // link either way and keep the copy engine (its 256-byte transactions use the link better than a warp's stores).
+  const bool zc = w->pin && w->ring[ring_now].aliased && w->ring[ring_now].dev_base && !(w->flags & F16_HOSTWIN_DMA_BOTH) &&
+                  (w->zero_copy == 2 || (w->zero_copy == 1 && C == 1));
+  if (zc) {
+    rc = f16_internal_set_obs_frame(env, (float*)(w->ring[ring_now].dev_base + (size_t)w->head * w->ring[ring_now].pitch));
+    if (rc) return rc;
+  }
   if (C > 1) CUDA_OK(cudaEventRecord(w->fork, st));
   for (int c = 0; c < C; ++c) {
     const int64_t first = (int64_t)c * per;
@@ -691,6 +709,7 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
     for (int r = 0; r < w->n_rings; ++r) {
       const int rr = (r == 0) ? ring_now : 1 - ring_now;      // the returned ring first
       if (rr != ring_now && !(w->flags & F16_HOSTWIN_DMA_BOTH)) continue;     // carried over by host threads after the sync
+      if (zc) continue;                                                        // the kernel wrote them there itself
       CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head, first), obs_frame + first * FEAT, cnt * ROW_BYTES, cudaMemcpyDeviceToHost, s));
       if (!w->ring[rr].aliased)
         CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head + SLOTS, first), obs_frame + first * FEAT, cnt * ROW_BYTES, cudaMemcpyDeviceToHost, s));
@@ -702,6 +721,10 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
     f16_publish_count_kernel<<<1, 1, 0, st>>>(w->count_dev, count_host_dev);
     f16_internal_count_launch();
     CUDA_OK(cudaEventRecord(w->ev, st));
+  }
+  if (zc) {
+    rc = f16_internal_set_obs_frame(env, obs_frame);      // launches have their arguments: back to the device buffer
+    if (rc) return rc;
   }
   lap();                                    // [0] enqueue: copies and the kernel launch
   CUDA_OK(cudaEventSynchronize(w->ev));     // kernel finished: the records it wrote to mapped host memory are complete

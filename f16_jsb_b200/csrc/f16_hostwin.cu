@@ -220,7 +220,7 @@ struct f16_hostwin {
   int32_t* count_host = nullptr;
   cudaEvent_t ev = nullptr, fork = nullptr;
   int n_chunks = 1;                      // pieces one step is pipelined in (upload | kernel | download)
-  int zero_copy = 1;                     // 1: single-piece steps let the kernel write its frames straight into the ring; 2: every step; 0: never
+  int zero_copy = 1;                     // 1: steps of up to 32 768 envs let the kernel write its frames straight into the ring; 2: every step; 0: never
   cudaStream_t cs[F16_HOSTWIN_MAX_CHUNKS] = {};
   cudaEvent_t kdone[F16_HOSTWIN_MAX_CHUNKS] = {};
   std::vector<float> term[2];
@@ -681,7 +681,7 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
   // kernel -> copy serialisation, which is what a step of a few thousand envs consists of; large batches are bound by the
   // link either way and keep the copy engine (its 256-byte transactions use the link better than a warp's stores).
   const bool zc = w->pin && w->ring[ring_now].aliased && w->ring[ring_now].dev_base && !(w->flags & F16_HOSTWIN_DMA_BOTH) &&
-                  (w->zero_copy == 2 || (w->zero_copy == 1 && C == 1));
+                  (w->zero_copy == 2 || (w->zero_copy == 1 && C == 1 && w->n <= 32768));   // measured: +9 % at 4 096 envs, +4 % at 16 384, -2 % at 65 536, -9 % at 1M
   if (zc) {
     rc = f16_internal_set_obs_frame(env, (float*)(w->ring[ring_now].dev_base + (size_t)w->head * w->ring[ring_now].pitch));
     if (rc) return rc;

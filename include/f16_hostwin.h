@@ -33,7 +33,7 @@
  * F16_HOSTWIN_CHUNKS (1..8 pieces per step; default 4 from 524 288 envs, 2 from 131 072, else 1),
  * F16_HOSTWIN_THREADS (1..16 worker threads per pool; default up to 4), F16_HOSTWIN_NUMA (0 off, 1 place buffers
  * and worker threads on the GPU's NUMA node, 2 also leave the calling thread there; default 1), F16_HOSTWIN_ZEROCOPY
- * (1: steps that run in one piece have the kernel store its frames straight into the ring, which is mapped into the
+ * (1: steps of up to 32 768 envs have the kernel store its frames straight into the ring, which is mapped into the
  * GPU's address space, instead of copying them afterwards; 2: every step; 0: never; default 1).
  */
 #ifndef F16_HOSTWIN_H

@@ -64,14 +64,16 @@ def test_vecenv_done_infos_match_dummy_vec_env_conventions(golden, host_obs, rin
     env.close()
 
 
-@pytest.mark.parametrize("rings,dma_both", [(1, False), (2, False), (2, True)])
-def test_window_mode_returns_what_copy_mode_returns(rings, dma_both):
+@pytest.mark.parametrize("rings,dma_both,zero_copy", [(1, False, 1), (2, False, 1), (2, True, 1), (1, False, 0), (2, False, 0)])
+def test_window_mode_returns_what_copy_mode_returns(rings, dma_both, zero_copy, monkeypatch):
     """Host-resident windows (60 B per env-step over PCIe) against the device-side stacks copied out whole
     (600 B): identical observations, rewards, flags, terminal observations and episode statistics across
     crashes and auto-resets. FP64 mode: there the two layouts' kernel instantiations agree bit for bit (the
     float instantiations contract a few multiply-adds differently, see test_ring_layout_is_value_identical_to_stacked)."""
     from f16_jsb_b200 import F16VecEnv
     n, steps = 2048, 120
+    # zero_copy 1: the kernel stores its frames straight into the mapped ring (default up to 32 768 envs); 0: copy engine
+    monkeypatch.setenv("F16_HOSTWIN_ZEROCOPY", str(zero_copy))
     a_env = F16VecEnv(n, mode="fp64", seed=3, host_obs="window", host_rings=rings, host_dma_both=dma_both)
     b_env = F16VecEnv(n, mode="fp64", seed=3, host_obs="copy")
     oa, ob = _reset_with_near_goals(a_env, n, 5), _reset_with_near_goals(b_env, n, 5)

@@ -663,13 +663,6 @@ int f16_internal_set_obs_frame(f16_handle h, float* obs_frame) {
   return 0;
 }
 
-int f16_internal_set_scalar_outputs(f16_handle h, float* reward, uint8_t* done, uint8_t* truncated) {
-  if (!h || !h->state || h->ring != OBS_FRAME) return fail("the env is not bound in the frame layout (f16_bind_frames)");
-  if (!reward || !done || !truncated) return fail("reward, done and truncated are required");
-  h->reward = reward; h->done = done; h->truncated = truncated;
-  return 0;
-}
-
 const char* f16_last_error(void) { return g_err.c_str(); }
 const char* f16_version(void) { return "f16_b200 0.1 (sm_100a)"; }
 int64_t f16_launch_count(void) { return g_launches; }

@@ -31,7 +31,6 @@
 
 extern "C" int f16_internal_fail(const char* msg);
 extern "C" int f16_internal_set_obs_frame(f16_handle h, float* obs_frame);
-extern "C" int f16_internal_set_scalar_outputs(f16_handle h, float* reward, uint8_t* done, uint8_t* truncated);
 extern "C" int f16_internal_frame_buffers(f16_handle h, int64_t* n, int* device, float** obs_frame, float** reward, uint8_t** done,
                                           uint8_t** truncated, float** actions_stage);
 
@@ -485,10 +484,9 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
   int rc = 0;
   for (int r = 0; r < n_rings && !rc; ++r) rc = make_ring(w->ring[r], n_envs, w->pin, !(flags & F16_HOSTWIN_NO_ALIAS));
   for (int b = 0; b < 2 && !rc; ++b) {
-    // mapped as well: zero-copy steps have the kernel write rewards and flags here directly
-    rc = host_array(&w->reward[b], (size_t)n_envs, w->pin, cudaHostAllocPortable | cudaHostAllocMapped);
-    if (!rc) rc = host_array(&w->done[b], (size_t)n_envs, w->pin, cudaHostAllocPortable | cudaHostAllocMapped);
-    if (!rc) rc = host_array(&w->trunc[b], (size_t)n_envs, w->pin, cudaHostAllocPortable | cudaHostAllocMapped);
+    rc = host_array(&w->reward[b], (size_t)n_envs, w->pin);
+    if (!rc) rc = host_array(&w->done[b], (size_t)n_envs, w->pin);
+    if (!rc) rc = host_array(&w->trunc[b], (size_t)n_envs, w->pin);
     if (!rc) rc = host_array(&w->actions[b], (size_t)n_envs * F16_ACTION_DIM, w->pin);
   }
   if (!rc && w->pin) {
@@ -687,14 +685,6 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
   if (zc) {
     rc = f16_internal_set_obs_frame(env, (float*)(w->ring[ring_now].dev_base + (size_t)w->head * w->ring[ring_now].pitch));
     if (rc) return rc;
-    // rewards and flags the same way (6 B per env-step; three copies less to launch and to wait for)
-    float* r_dev = nullptr;
-    uint8_t *d_dev = nullptr, *t_dev = nullptr;
-    CUDA_OK(cudaHostGetDevicePointer((void**)&r_dev, w->reward[cur], 0));
-    CUDA_OK(cudaHostGetDevicePointer((void**)&d_dev, w->done[cur], 0));
-    CUDA_OK(cudaHostGetDevicePointer((void**)&t_dev, w->trunc[cur], 0));
-    rc = f16_internal_set_scalar_outputs(env, r_dev, d_dev, t_dev);
-    if (rc) return rc;
   }
   if (C > 1) CUDA_OK(cudaEventRecord(w->fork, st));
   for (int c = 0; c < C; ++c) {
@@ -713,11 +703,9 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
       f16_internal_count_launch();
       CUDA_OK(cudaEventRecord(w->ev, st));
     }
-    if (!zc) {
-      CUDA_OK(cudaMemcpyAsync(w->done[cur] + first, done + first, cnt, cudaMemcpyDeviceToHost, s));
-      CUDA_OK(cudaMemcpyAsync(w->trunc[cur] + first, trunc + first, cnt, cudaMemcpyDeviceToHost, s));
-      CUDA_OK(cudaMemcpyAsync(w->reward[cur] + first, reward + first, cnt * sizeof(float), cudaMemcpyDeviceToHost, s));
-    }
+    CUDA_OK(cudaMemcpyAsync(w->done[cur] + first, done + first, cnt, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(w->trunc[cur] + first, trunc + first, cnt, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(w->reward[cur] + first, reward + first, cnt * sizeof(float), cudaMemcpyDeviceToHost, s));
     for (int r = 0; r < w->n_rings; ++r) {
       const int rr = (r == 0) ? ring_now : 1 - ring_now;      // the returned ring first
       if (rr != ring_now && !(w->flags & F16_HOSTWIN_DMA_BOTH)) continue;     // carried over by host threads after the sync
@@ -735,8 +723,7 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
     CUDA_OK(cudaEventRecord(w->ev, st));
   }
   if (zc) {
-    rc = f16_internal_set_obs_frame(env, obs_frame);      // launches have their arguments: back to the device buffers
-    if (!rc) rc = f16_internal_set_scalar_outputs(env, reward, done, trunc);
+    rc = f16_internal_set_obs_frame(env, obs_frame);      // launches have their arguments: back to the device buffer
     if (rc) return rc;
   }
   lap();                                    // [0] enqueue: copies and the kernel launch

@@ -4,17 +4,25 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K --warmup W   # CPU arm (oracle port, host threads)
 
-One "step" = one env-step (4 FDM frames + observation stack + reward/termination, auto-reset on) of
-every env of the job. Workload (BASELINE.json configs[3]): 1 048 576 F-16 envs per GPU, FP32
-throughput mode, stacked (10,15) observations and goal reward, random actions. Per-GPU work is fixed
-as N grows (weak scaling, no data-path collective; only the rollout statistics are all-reduced).
-The per-GPU working set (state + observations, ~0.9 GB) is far larger than the 126 MB L2, so every
-step streams from HBM without an explicit flush.
+One "step" = one env-step (4 FDM frames + observation window + reward/termination, auto-reset on) of every
+env of the job. Workload (BASELINE.json configs[3]): 1 048 576 F-16 envs per GPU, FP32 throughput mode, random
+actions, goal reward, ten-frame observation windows kept in the device-resident ring buffer the step kernel
+writes (F16BatchedEnv's default layout). Per-GPU work is fixed as N grows (weak scaling, no data-path
+collective; only the rollout statistics are all-reduced). The per-GPU working set (state + ring, ~1.5 GB) is
+far larger than the 126 MB L2, so every step streams from HBM without an explicit flush.
 
-`value`  : device-resident throughput - actions already in HBM, CUDA-event timing, max over ranks.
-`e2e`    : the same metric through the public SB3 VecEnv call (NumPy actions in, NumPy obs/reward/done
-           out, pinned host buffers, copies and sync inside the timed region).
-`roofline`: achieved algorithmic bytes/s of the step kernel vs the measured HBM copy bandwidth.
+Every device-resident leg is timed at STEADY STATE: after reset all envs are rolled for `--preroll` (600)
+untimed env-steps, so that episodes end, auto-reset and draw new goals all along the timed region (random
+actions: the first crashes come after ~300 env-steps).
+
+`value`   : device-resident throughput of the headline leg - actions already in HBM, CUDA-event timing, max over ranks.
+`legs`    : the same rollout in the other settings, each with its own `roofline` block: the materialised
+            (N,10,15) stack shifted in place ("stacked", the reference's array), the newest-frame-only layout
+            ("frame"), FP64 parity mode, and every reference detail on (ground reactions + carry-over reset).
+`e2e`     : the same metric through the public SB3 VecEnv call (NumPy actions in, NumPy obs/reward/done out,
+            pinned host buffers, copies and sync inside the timed region).
+`roofline`: achieved algorithmic bytes/s of the step kernel vs the measured HBM copy bandwidth, plus the issue-slot
+            accounting that actually bounds it.
 `cpu_baseline`: the oracle (a C++ port of the reference path, not JSBSim itself) on the host cores.
 """
 import argparse
@@ -33,23 +41,30 @@ ENVS_PER_GPU = 1_048_576
 METRIC = "F-16 env-steps/sec"
 UNIT = "env-steps/s"
 WORKLOAD = ("BASELINE configs[3]: 1M F-16 envs per GPU (aircraft/f16, 4 FDM frames per env-step), FP32 mode, "
-            "stacked (10,15) observations + goal reward, random actions, auto-reset")
-# algorithmic bytes per env-step, FP32 mode with the materialised stack (DESIGN.md "Roofline"):
-# state read+write 2*(11*8 + 42*4 + 8*4) = 576, action 16, previous 9 frames read 540, stack write 600,
-# reward 4 + done 1 + truncated 1
-BYTES_PER_ENV_STEP_FP32 = 576 + 16 + 540 + 600 + 6
-BYTES_PER_ENV_STEP_FP64 = 2 * (11 * 8 + 42 * 8 + 8 * 4) + 16 + 540 + 600 + 6
+            "ten-frame (10,15) observation windows + goal reward, random actions, auto-reset, steady state")
+
+# ---- algorithmic bytes per env-step (DESIGN.md "Roofline")
+# state read + write: 11 kinematic doubles + 42 model scalars (float / double) + 8 env words
+STATE_BYTES = {"fp32": 2 * (11 * 8 + 42 * 4 + 8 * 4), "fp64": 2 * (11 * 8 + 42 * 8 + 8 * 4)}
+# observation traffic: stacked = read the nine surviving rows (540) + write the whole stack (600);
+# ring = the newest 60-byte frame written to its slot and to the mirror slot; frame = the newest frame once
+OBS_BYTES = {"stacked": 540 + 600, "ring": 2 * 60, "frame": 60}
+MISC_BYTES = 16 + 4 + 1 + 1          # action read, reward, done, truncated
 
 
-def ncu_traffic(kernel, envs):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+def bytes_per_env_step(mode, layout):
+    return STATE_BYTES[mode] + OBS_BYTES[layout] + MISC_BYTES
+
+
+def profile_entry(kernel_key, envs):
+    """Per-launch counters of `kernel_key` from the committed ncu capture (profiles/traffic.json), or {}."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel_key)
         if t and int(t["envs"]) == int(envs):
-            return float(t["dram_bytes_per_launch"])
+            return t
     except Exception:
         pass
-    return None
+    return {}
 
 
 def measured_peaks():
@@ -109,51 +124,90 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(seconds=12.0, threads=None):
+# ------------------------------------------------------------------------------------ CPU arm
+CPU_SAMPLE_ENVS = 64          # the same sample on every box and at every N, so the driver's ratio is comparable across N
+CPU_SAMPLE_STEPS = 4000       # env-steps per env per sample: ~0.1 s of work on 16 threads
+
+
+def cpu_threads():
+    return max(1, min(os.cpu_count() or 1, CPU_SAMPLE_ENVS))
+
+
+def cpu_baseline(seconds=12.0):
     """The oracle's env (CPU restatement of the reference path) on host threads, bounded sample."""
     from oracle import f16_oracle
-    threads = threads or (os.cpu_count() or 1)
-    f16_oracle.rollout(threads, 50, 1, threads)                      # warm-up / page-in
+    threads = cpu_threads()
+    f16_oracle.rollout(CPU_SAMPLE_ENVS, 50, 1, threads)                      # warm-up / page-in
     t0 = time.perf_counter()
-    n, _ = f16_oracle.rollout(threads * 4, 250, 2, threads)
+    n, _ = f16_oracle.rollout(CPU_SAMPLE_ENVS, 250, 2, threads)
     rate = n / (time.perf_counter() - t0)
-    per_thread_steps = max(250, int(rate * seconds / (threads * 4)))
+    per_env_steps = max(250, int(rate * seconds / CPU_SAMPLE_ENVS))
     t0 = time.perf_counter()
-    n, cs = f16_oracle.rollout(threads * 4, per_thread_steps, 3, threads)
+    n, cs = f16_oracle.rollout(CPU_SAMPLE_ENVS, per_env_steps, 3, threads)
     dt = time.perf_counter() - t0
     return {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d envs x %d env-steps, random actions, auto-reset, %d host threads, %.1f s (oracle/libf16oracle.so: C++ restatement of the reference path, not JSBSim itself)"
-                      % (threads * 4, per_thread_steps, threads, dt)}
+            "sample": "%d envs x %d env-steps, random actions, auto-reset, ground reactions on, %d host threads, %.1f s "
+                      "(oracle/libf16oracle.so: C++ restatement of the reference path, not JSBSim itself)"
+                      % (CPU_SAMPLE_ENVS, per_env_steps, threads, dt)}
 
 
 def run_reference(args):
     """--impl reference: the reference path's CPU implementation (oracle port; real JSBSim is not
-    installable offline) on all host threads; a 'step' is a bounded sample of the same workload."""
+    installable offline) on the host threads; a 'step' is a bounded sample of the same workload. The sample
+    (64 envs x 4 000 env-steps) does not depend on N; rank 0 runs it after the other ranks have left."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        time.sleep(3.0)          # let the idle ranks' interpreters exit before timing host threads
     from oracle import f16_oracle
-    threads = os.cpu_count() or 1
-    envs = threads * 4
-    steps_per_sample = 4000          # ~0.1-0.3 s of host work per 'step'
-    for _ in range(max(1, args.warmup)):
-        f16_oracle.rollout(envs, 50, 0, threads)
+    threads = cpu_threads()
+    for _ in range(max(3, args.warmup)):
+        f16_oracle.rollout(CPU_SAMPLE_ENVS, 200, 0, threads)
     t0 = time.perf_counter()
     total = 0
     for k in range(args.steps):
-        n, _ = f16_oracle.rollout(envs, steps_per_sample, k + 1, threads)
+        n, _ = f16_oracle.rollout(CPU_SAMPLE_ENVS, CPU_SAMPLE_STEPS, k + 1, threads)
         total += n
     dt = time.perf_counter() - t0
     value = total / dt
-    sample = "%d samples of %d envs x %d env-steps on %d host threads (oracle port of the reference path)" % (args.steps, envs, steps_per_sample, threads)
+    sample = "%d samples of %d envs x %d env-steps on %d host threads (oracle port of the reference path)" % (
+        args.steps, CPU_SAMPLE_ENVS, CPU_SAMPLE_STEPS, threads)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "warmup": max(3, args.warmup), "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reference_arm": "CPU restatement of JSBSim F-16 env-step (jsbsim PyPI package unavailable offline)"},
+        "config": {"workload": WORKLOAD, "reference_arm": "CPU restatement of JSBSim F-16 env-step (jsbsim PyPI package unavailable offline; "
+                   "profiles/r2_jsbsim_probe_gpu_box.txt), all reference details on (ground reactions, one FDM object per env)",
+                   "sample_envs": CPU_SAMPLE_ENVS, "sample_env_steps": CPU_SAMPLE_STEPS},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+LEGS = {
+    # name: (mode, obs layout, ground reactions (None = the mode's default), reset mode)
+    "fp32_ring": ("fp32", "ring", None, "snapshot"),
+    "fp32_stacked": ("fp32", "stacked", None, "snapshot"),
+    "fp32_frame": ("fp32", "frame", None, "snapshot"),
+    "fp32_all_reference_details": ("fp32", "ring", True, "carryover"),
+    "fp64_parity": ("fp64", "ring", None, "snapshot"),
+    "fp64_parity_stacked": ("fp64", "stacked", None, "snapshot"),
+}
+LEG_NOTES = {
+    "fp32_ring": "headline: FP32 throughput mode, device-resident ring of ten-frame windows (zero-copy strided (N,10,15) view)",
+    "fp32_stacked": "the reference's materialised (N,10,15) array, shifted in place every step (round 1's headline layout)",
+    "fp32_frame": "newest frame only (N,15): what crosses PCIe in the host-window path and what the rollout store keeps",
+    "fp32_all_reference_details": "ground reactions on + carry-over reset (auto_reset = 2: the reference's run_ic() on a used env object)",
+    "fp64_parity": "FP64 parity mode (all model math in double, ground reactions on), ring layout",
+    "fp64_parity_stacked": "FP64 parity mode with the materialised stack",
+}
+
+
+def kernel_name(mode, layout, ground):
+    return "f16_step_kernel<%s,%s,%s>" % ("float" if mode == "fp32" else "double", layout, "ground" if ground else "noground")
 
 
 def run_ours(args):
@@ -168,103 +222,126 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    n_env = args.envs
-    total_envs = n_env * world
-    lo, hi = shard_range(total_envs, rank, world)
-    mode = args.mode
-    env = F16BatchedEnv(hi - lo, device=dev, mode=mode, seed=args.seed, env_id_base=lo,
-                        ground_reactions={"default": None, "on": True, "off": False}[args.ground])
-    ground_main = env.ground_reactions
-    env.reset()
-    # actions resident in HBM before the timed region: a ring of distinct uniform action batches
-    ring = 8
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
+    peak, peak_src = measured_peaks()
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+
+    # actions resident in HBM before any timed region: a ring of distinct uniform action batches
+    n_ring = 8
     lo_a = torch.tensor([-1, -1, -1, 0], dtype=torch.float32, device=dev)
     hi_a = torch.tensor([1, 1, 1, 1], dtype=torch.float32, device=dev)
-    actions = [lo_a + (hi_a - lo_a) * torch.rand((hi - lo, 4), generator=gen, device=dev) for _ in range(ring)]
-    for w in range(max(3, args.warmup)):
-        env.step(actions[w % ring], auto_reset=True)
-    torch.cuda.synchronize(dev)
-    env.stats(reset=True)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
-    torch.cuda.synchronize(dev)
-    if sampler:
-        sampler.start()
-    launches0 = env.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for k in range(args.steps):
-        env.step(actions[k % ring], auto_reset=True)
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    barrier()
-    launches = env.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1), device=dev)
-    ms_step = ms_total / args.steps
-    value = total_envs * args.steps / (ms_total * 1e-3)
-    st = env.stats()
-    stats_t = torch.tensor([st[k] for k in ("episodes", "return_sum", "length_sum", "crashes", "goals", "truncations", "env_steps", "ground_redos")],
-                           dtype=torch.float64, device=dev)
-    allreduce_stats(stats_t)                        # the only collective: rollout statistics over NVLink
-    stats = stats_t.cpu().tolist()
 
-    # ---- the same rollout, continued with the other setting of the ground reactions (include/f16_b200.h)
-    from f16_jsb_b200 import _lib as _f16lib
-    _f16lib.check(env.lib.f16_set_ground_reactions(env._h, 0 if ground_main else 1), "f16_set_ground_reactions")
-    for w in range(3):
-        env.step(actions[w % ring], auto_reset=True)
-    g_steps = max(10, args.steps // 4)
-    barrier()
-    torch.cuda.synchronize(dev)
-    ev0.record()
-    for k in range(g_steps):
-        env.step(actions[k % ring], auto_reset=True)
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    ground_other_ms = max_over_ranks(ev0.elapsed_time(ev1), device=dev) / g_steps
+    def make_actions(n):
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1234 + rank)
+        return [lo_a + (hi_a - lo_a) * torch.rand((n, 4), generator=gen, device=dev) for _ in range(n_ring)]
 
-    # ---- and with every reference detail on: ground reactions + the carry-over reset (F16_AUTO_RESET_CARRYOVER:
-    # a finished env restarts as the reference's run_ic() leaves a used env object, include/f16_b200.h)
-    import ctypes as _C
-    _f16lib.check(env.lib.f16_set_ground_reactions(env._h, 1), "f16_set_ground_reactions")
+    def device_leg(name, envs_per_gpu, steps, warmup, sample_clocks=False):
+        """One device-resident rollout: reset, `--preroll` untimed env-steps to reach the steady-state population,
+        `warmup` more, then `steps` timed launches between CUDA events; max over ranks."""
+        mode, layout, ground, reset_mode = LEGS[name]
+        total_envs = envs_per_gpu * world
+        lo, hi = shard_range(total_envs, rank, world)
+        n = hi - lo
+        env = F16BatchedEnv(n, device=dev, mode=mode, seed=args.seed, env_id_base=lo, obs_layout=layout,
+                            ground_reactions=ground, reset_mode=reset_mode, with_terminal_obs=(layout != "frame"))
+        actions = make_actions(n)
+        env.reset()
+        for w in range(args.preroll + max(3, warmup)):
+            env.step(actions[w % n_ring], auto_reset=True)
+        torch.cuda.synchronize(dev)
+        env.stats(reset=True)
+        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
+        barrier()
+        torch.cuda.synchronize(dev)
+        if sampler:
+            sampler.start()
+        launches0 = env.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for k in range(steps):
+            env.step(actions[k % n_ring], auto_reset=True)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+        barrier()
+        launches = env.launch_count() - launches0
+        clocks = sampler.stop() if sampler else None
+        ms_step = max_over_ranks(ev0.elapsed_time(ev1), device=dev) / steps
+        st = env.stats()
+        stats_t = torch.tensor([st[k] for k in ("episodes", "return_sum", "length_sum", "crashes", "goals", "truncations", "env_steps", "ground_redos")],
+                               dtype=torch.float64, device=dev)
+        allreduce_stats(stats_t)                        # the only collective: rollout statistics over NVLink
+        stats = stats_t.cpu().tolist()
+        ground_on = env.ground_reactions
+        env.close()
+        del env, actions
+        torch.cuda.empty_cache()
+        bpe = bytes_per_env_step(mode, layout)
+        achieved = n * bpe / (ms_step * 1e-3) / 1e9          # per GPU: one launch processes one rank's envs
+        prof = profile_entry(kernel_name(mode, layout, ground_on), n)
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": prof.get("dram_bytes_per_launch"), "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/)",
+                "algorithmic_bytes_per_launch": n * bpe, "algorithmic_bytes_per_env_step": bpe,
+                "bytes_breakdown": {"state_read_write": STATE_BYTES[mode], "observations": OBS_BYTES[layout], "action_reward_flags": MISC_BYTES},
+                "peak_source": peak_src, "kernel": kernel_name(mode, layout, ground_on), "per": "GPU"}
+        if prof.get("warp_instructions_per_launch"):
+            # what really bounds the kernel: instruction issue. 4 schedulers per SM, one warp-instruction per cycle each
+            wi = float(prof["warp_instructions_per_launch"])
+            clk = (clocks or {}).get("sm_mhz") or prof.get("sm_mhz") or 1965.0
+            roof["issue"] = {"warp_instructions_per_launch": wi, "warp_instructions_per_warp_env_step": wi / (n / 32.0),
+                             "issue_slots_per_s_peak": sm_count * 4 * clk * 1e6,
+                             "achieved_frac_of_issue_peak": wi / (ms_step * 1e-3) / (sm_count * 4 * clk * 1e6),
+                             "sm_mhz_used": clk, "source": prof.get("source")}
+        return {"name": name, "note": LEG_NOTES[name], "mode": mode, "obs_layout": layout, "ground_reactions": "on" if ground_on else "off",
+                "reset": reset_mode, "envs_per_gpu": envs_per_gpu, "steps": steps, "ms_per_step": ms_step,
+                "value": total_envs * 1e3 / ms_step, "unit": UNIT, "gpu_launches": int(launches) * world, "roofline": roof,
+                "rollout_stats": {"episodes": stats[0], "mean_return": (stats[1] / stats[0]) if stats[0] else None,
+                                  "mean_length": (stats[2] / stats[0]) if stats[0] else None, "crashes": stats[3], "goals": stats[4],
+                                  "truncations": stats[5], "ground_redos": stats[7]},
+                "clocks": clocks}
 
-    def step_carryover(a):
-        _f16lib.check(env.lib.f16_step(env._h, _C.c_void_p(a.data_ptr()), 2, env._stream()), "f16_step")
-
-    for w in range(3):
-        step_carryover(actions[w % ring])
-    barrier()
-    torch.cuda.synchronize(dev)
-    ev0.record()
-    for k in range(g_steps):
-        step_carryover(actions[k % ring])
-    ev1.record()
-    torch.cuda.synchronize(dev)
-    carry_ms = max_over_ranks(ev0.elapsed_time(ev1), device=dev) / g_steps
+    n_env = args.envs
+    total_envs = n_env * world
+    head_name = {"fp32": "fp32_" + args.layout, "fp64": "fp64_parity" if args.layout == "ring" else "fp64_parity_stacked"}[args.mode]
+    if head_name not in LEGS:
+        raise SystemExit("no such leg: %s" % head_name)
+    head = device_leg(head_name, n_env, args.steps, args.warmup, sample_clocks=True)
+    leg_steps = max(10, min(args.steps, args.leg_steps))
+    legs = {}
+    if args.legs:
+        for name in LEGS:
+            if name == head_name or (name == "fp64_parity_stacked" and not args.all_legs):
+                continue
+            legs[name] = device_leg(name, n_env, leg_steps, args.warmup)
+        for v in legs.values():
+            v.pop("clocks", None)
+    # BASELINE configs[3] read literally: 1M envs in TOTAL, sharded over the N GPUs (strong scaling; at N = 8 the
+    # 131 072 envs of a GPU - 38 MB of state, 157 MB of ring - are partly L2-resident, which is stated, not hidden)
+    strong = None
+    if world > 1 and args.legs:
+        s = device_leg(head_name, max(32, ENVS_PER_GPU // world), leg_steps, args.warmup)
+        strong = {"total_envs": s["envs_per_gpu"] * world, "envs_per_gpu": s["envs_per_gpu"], "ms_per_step": s["ms_per_step"], "value": s["value"],
+                  "unit": UNIT, "scaling": "strong", "roofline_frac": s["roofline"]["frac"],
+                  "l2": "per-GPU working set %.0f MB against a 126 MB L2: partly cache-resident, no flush" % (
+                      s["envs_per_gpu"] * (bytes_per_env_step(args.mode, args.layout)) / 2e6)}
 
     # ---- end to end through the public VecEnv API with host buffers
-    env.close()
-    del env
-    torch.cuda.empty_cache()
     e2e_steps = max(3, min(args.steps, args.e2e_steps))
-
+    lo, hi = shard_range(total_envs, rank, world)
     phases, done_rate, numa = {}, {}, [-1]
 
-    def e2e_run(host_obs, rings, dma_both=False):
-        """F16VecEnv.step with actions in pinned host memory and NumPy results out, copies and sync inside."""
-        venv = F16VecEnv(hi - lo, device=dev, mode=mode, seed=args.seed, env_id_base=lo, host_obs=host_obs, host_rings=rings,
-                         host_dma_both=dma_both)
+    def e2e_run(host_obs, rings, dma_both=False, copy_obs=False, touch=False, steps=None, tag=None):
+        """F16VecEnv.step with actions in pinned host memory and NumPy results out, copies and sync inside.
+        touch: the consumer reads every byte of the returned observation (np.add.reduce over the float32 view)."""
+        steps = steps or e2e_steps
+        venv = F16VecEnv(hi - lo, device=dev, mode=args.mode, seed=args.seed, env_id_base=lo, host_obs=host_obs, host_rings=rings,
+                         host_dma_both=dma_both, copy_obs=copy_obs)
         venv.reset()
         rng = np.random.default_rng(99 + rank)
         bufs = [venv.action_buffer(), venv.action_buffer()]
         for b in bufs:
             b[...] = rng.uniform([-1, -1, -1, 0], [1, 1, 1, 1], size=(hi - lo, 4)).astype(np.float32)
-        # warm-up through the same call, long enough for episodes to be ending all along the timed steps
-        # (random actions: the first crashes come after ~300 env-steps), so the timed region pays for the
-        # terminal observations and reset fix-ups of finished envs too
+        # warm-up through the same call, long enough for episodes to be ending all along the timed steps, so the
+        # timed region pays for the terminal observations and reset fix-ups of finished envs too
         for w in range(args.e2e_warmup if host_obs == "window" else min(args.e2e_warmup, 50)):
             venv.step(bufs[w % 2])
         if venv._win is not None:
@@ -273,52 +350,61 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         finished = 0
-        for k in range(e2e_steps):
+        sink = 0.0
+        for k in range(steps):
             obs, rew, dones, infos = venv.step(bufs[k % 2])
             finished += int(np.count_nonzero(dones))
+            if touch:
+                sink += float(np.add.reduce(obs, axis=None, dtype=np.float32))
         torch.cuda.synchronize(dev)
         barrier()
         secs = max_over_ranks(time.perf_counter() - t0, device=dev)
         assert obs.shape == (hi - lo, 10, 15) and rew.shape == (hi - lo,) and dones.shape == (hi - lo,)
+        key = tag or (host_obs, rings, dma_both)
         if venv._win is not None:
             numa[0] = venv._win.numa_node
-            phases[(host_obs, rings, dma_both)] = {k: round(v, 4) for k, v in venv._win.timing().items() if k != "carry_over_duration" or v}
+            phases[key] = {k: round(v, 4) for k, v in venv._win.timing().items() if k != "carry_over_duration" or v}
         venv.close()
         del venv
         torch.cuda.empty_cache()
-        done_rate[(host_obs, rings, dma_both)] = finished / float(e2e_steps)
-        return total_envs * e2e_steps / secs
+        done_rate[key] = finished / float(steps)
+        return total_envs * steps / secs
 
     e2e_value = e2e_run("window", 2)
-    e2e_other = ({"window_1ring": e2e_run("window", 1), "window_2rings_dma_both": e2e_run("window", 2, True),
-                  "copy_whole_stacks": e2e_run("copy", 2)} if args.e2e_variants else {})
+    e2e_other = {}
+    if args.e2e_variants:
+        few = max(3, min(e2e_steps, 10))
+        e2e_other = {"window_1ring": e2e_run("window", 1), "window_2rings_dma_both": e2e_run("window", 2, True),
+                     "window_2rings_consumer_reads_obs": e2e_run("window", 2, touch=True, steps=few, tag="touch"),
+                     "window_2rings_copy_obs_true": e2e_run("window", 2, copy_obs=True, steps=few, tag="copy_obs"),
+                     "copy_whole_stacks": e2e_run("copy", 2, steps=few),
+                     "note": "consumer_reads_obs adds one single-threaded NumPy pass over the returned (N,10,15) view per step; copy_obs_true is "
+                             "DummyVecEnv's behaviour (a fresh 600-byte stack per env per step); both are host-CPU work of the caller, "
+                             "timed over %d steps" % few}
 
     if rank != 0:
         return
-    peak, peak_src = measured_peaks()
-    bpe = BYTES_PER_ENV_STEP_FP32 if mode == "fp32" else BYTES_PER_ENV_STEP_FP64
-    achieved = (hi - lo) * bpe / (ms_step * 1e-3) / 1e9          # per GPU: one launch processes one rank's envs
     cpu = cpu_baseline(seconds=args.cpu_seconds) if (not args.no_cpu_baseline and world == 1) else None   # rank 0, N=1 only
+    mode, layout = args.mode, args.layout
+    bpe = bytes_per_env_step(mode, layout)
     out = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if mode == "fp32" else "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": n_env, "total_envs": total_envs, "mode": mode,
-                   "frames_per_env_step": 4,
-                   "actions": "uniform over the action Box, 8 distinct (N,4) batches resident in HBM before the timed region and used in turn (the 16 B per env-step of the roofline's action read); in-kernel Philox actions (f16_step(actions=NULL)) give the same rate", "fdm_frames_per_s": value * 4, "l2": "inputs larger than L2 (state+obs %.0f MB per GPU); no flush" % ((hi - lo) * (bpe - 22) / 2e6),
+        "config": {"workload": WORKLOAD, "envs_per_gpu": n_env, "total_envs": total_envs, "mode": mode, "obs_layout": layout,
+                   "frames_per_env_step": 4, "preroll_steps": args.preroll,
+                   "steady_state": "all envs are reset together and rolled %d untimed env-steps before the timed region, so episodes end, "
+                                   "auto-reset and draw new goals inside it (rollout_stats counts only the timed steps)" % args.preroll,
+                   "actions": "uniform over the action Box, 8 distinct (N,4) batches resident in HBM before the timed region and used in turn "
+                              "(the 16 B per env-step of the roofline's action read)",
+                   "fdm_frames_per_s": head["value"] * 4,
+                   "l2": "inputs larger than L2 (state + observation ring %.0f MB per GPU); no flush" % (
+                       n_env * (STATE_BYTES[mode] / 2 + {"ring": 1200, "stacked": 600, "frame": 60}[layout]) / 1e6),
                    "parallelism": "env-sharded x%d, no data-path collective" % world,
-                   "ground_reactions": {"timed": "on" if ground_main else "off",
-                                        "note": "default of the mode (on in fp64, off in fp32); they only act inside the last env-step of a crash",
-                                        "other_setting_ms_per_step": ground_other_ms,
-                                        "other_setting_value": total_envs / (ground_other_ms * 1e-3)},
-                   "reset": {"timed": "snapshot (finished envs restart from the state of a fresh reference env object)",
-                             "carryover_with_ground_reactions_ms_per_step": carry_ms,
-                             "carryover_with_ground_reactions_value": total_envs / (carry_ms * 1e-3)},
-                   "rollout_stats": {"episodes": stats[0], "mean_return": (stats[1] / stats[0]) if stats[0] else None,
-                                     "mean_length": (stats[2] / stats[0]) if stats[0] else None, "crashes": stats[3], "goals": stats[4],
-                                     "truncations": stats[5], "ground_redos": stats[7],
-                                     "note": "episodes that ENDED inside the timed steps: with all envs reset together shortly before, long episodes are under-represented (an unbiased 6 000-step run gives a mean length of ~855, tools/soak.py)"}},
-        "clocks": clocks,
+                   "ground_reactions": head["ground_reactions"], "reset": head["reset"],
+                   "rollout_stats": head["rollout_stats"],
+                   "strong_scaling_1M_total": strong if strong else ("identical to the headline at one GPU" if world == 1 else None)},
+        "clocks": head["clocks"],
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": total_envs * 16, "d2h_bytes_per_step": total_envs * (60 + 4 + 1 + 1),
                 "steps": e2e_steps,
                 "api": "F16VecEnv.step(actions in pinned host memory) -> NumPy obs (N,10,15), rewards, dones, infos; host-resident "
@@ -328,12 +414,9 @@ def run_ours(args):
                        "and are not counted",
                 "variants": e2e_other, "host_ms_per_step_by_phase": phases.get(("window", 2, False)),
                 "numa_node_rank0": numa[0], "warmup_steps": args.e2e_warmup, "episodes_finished_per_step": done_rate.get(("window", 2, False))},
-        "gpu_launches": int(launches) * world,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic("f16_step_kernel<%s>" % ("float" if mode == "fp32" else "double"), hi - lo),
-                     "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/)", "algorithmic_bytes_per_launch": (hi - lo) * bpe,
-                     "peak_source": peak_src, "kernel": "f16_step_kernel<%s>" % ("float" if mode == "fp32" else "double"),
-                     "algorithmic_bytes_per_env_step": bpe, "per": "GPU"},
+        "gpu_launches": head["gpu_launches"],
+        "roofline": head["roofline"],
+        "legs": legs,
     }
     if cpu:
         out["cpu_baseline"] = cpu
@@ -347,18 +430,21 @@ def main():
     sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU, help="envs per GPU")
     ap.add_argument("--mode", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--layout", default="ring", choices=["ring", "stacked", "frame"], help="observation layout of the headline leg")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--ground", default="default", choices=["default", "on", "off"],
-                    help="ground reactions of the device-resident run (default: on in fp64, off in fp32)")
+    ap.add_argument("--preroll", type=int, default=600, help="untimed env-steps after reset, before every device-resident leg (steady state)")
+    ap.add_argument("--leg-steps", type=int, default=200, help="timed steps of the secondary legs (capped by --steps)")
+    ap.add_argument("--no-legs", dest="legs", action="store_false", help="time the headline leg only")
+    ap.add_argument("--all-legs", action="store_true", help="also time FP64 with the materialised stack")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--e2e-warmup", type=int, default=600)
     ap.add_argument("--no-e2e-variants", dest="e2e_variants", action="store_false",
-                    help="skip the one-ring and whole-stack-copy variants of the end-to-end measurement")
+                    help="skip the one-ring, consumer-reads, copy_obs and whole-stack-copy variants of the end-to-end measurement")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

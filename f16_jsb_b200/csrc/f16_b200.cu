@@ -25,33 +25,53 @@
 
 using namespace f16;
 
-// ------------------------------------------------------------------------------------ SoA layout
-// [K fields: NKF x np doubles][R fields: NRF x np R][E fields: NEF x np 4-byte], np = n rounded up to
-// 32; field lists and order in f16_env.cuh. Field-major, so a warp's accesses are one 128/256-byte row.
+// ------------------------------------------------------------------------------------ state layout
+// Tiles of 32 envs (one warp), field-major inside the tile:
+//   tile t: [K fields: NKF x 32 doubles][R fields: NRF x 32 R][E fields: NEF x 32 4-byte words]     (field lists: f16_env.cuh)
+// A warp's access to one field is one contiguous 128-byte (float) / 256-byte (double) row, exactly as with a global
+// field-major array, but every field now sits at a COMPILE-TIME offset from the lane's tile pointer: the 122 loads and
+// stores of a step take their address from one base register + an immediate instead of a 64-bit multiply-add each
+// (round 1: 133 IADD3 + 34 IMAD around the 41 loads of the R fields alone), and a tile's state is one contiguous
+// 9 216-byte (FP32 mode) / 14 592-byte (FP64 mode) span of HBM.
+template <typename R>
+struct TileLayout {
+  static constexpr size_t K_OFF = 0;
+  static constexpr size_t R_OFF = K_OFF + (size_t)NKF * 32 * sizeof(K);
+  static constexpr size_t E_OFF = R_OFF + (size_t)NRF * 32 * sizeof(R);
+  static constexpr size_t TILE_BYTES = E_OFF + (size_t)NEF * 32 * 4;
+};
+static_assert(TileLayout<float>::TILE_BYTES % 256 == 0 && TileLayout<double>::TILE_BYTES % 256 == 0, "tiles stay 256-byte aligned");
 struct Layout {
-  int64_t n, np;
-  size_t k_off, r_off, e_off, total;
-  int rsize;
+  int64_t n, tiles;
+  size_t tile_bytes, e_off, total;
 };
 static Layout make_layout(int64_t n, int mode) {
   Layout L;
   L.n = n;
-  L.np = (n + 31) / 32 * 32;
-  L.rsize = mode == F16_MODE_FP64 ? 8 : 4;
-  L.k_off = 0;
-  L.r_off = L.k_off + (size_t)NKF * L.np * 8;
-  L.e_off = L.r_off + (size_t)NRF * L.np * L.rsize;
-  L.total = L.e_off + (size_t)NEF * L.np * 4;
+  L.tiles = (n + 31) / 32;
+  L.tile_bytes = mode == F16_MODE_FP64 ? TileLayout<double>::TILE_BYTES : TileLayout<float>::TILE_BYTES;
+  L.e_off = mode == F16_MODE_FP64 ? TileLayout<double>::E_OFF : TileLayout<float>::E_OFF;
+  L.total = (size_t)L.tiles * L.tile_bytes;
   return L;
 }
 
+// the lane's view of its tile: field f of the env is k[f * 32], r[f * 32], e[f * 32]
 template <typename R>
 struct StatePtrs {
   K* k;
   R* r;
   uint32_t* e;
-  int64_t np;
 };
+template <typename R>
+__device__ __forceinline__ StatePtrs<R> state_ptrs(void* state, int64_t env) {
+  char* b = (char*)state + (size_t)(env >> 5) * TileLayout<R>::TILE_BYTES;
+  const int lane = (int)(env & 31);
+  StatePtrs<R> p;
+  p.k = (K*)(b + TileLayout<R>::K_OFF) + lane;
+  p.r = (R*)(b + TileLayout<R>::R_OFF) + lane;
+  p.e = (uint32_t*)(b + TileLayout<R>::E_OFF) + lane;
+  return p;
+}
 
 // state and observations are touched exactly once per step: streaming (evict-first) accesses keep them
 // from displacing the prefetched observation rows in L2 (F16_STREAMING)
@@ -66,48 +86,48 @@ struct StatePtrs {
 #define F16_ST(ptr, v) (*(ptr) = (v))
 #endif
 template <typename R>
-__device__ __forceinline__ void load_veh(Veh<R>& s, const StatePtrs<R>& p, int64_t e) {
+__device__ __forceinline__ void load_veh(Veh<R>& s, const StatePtrs<R>& p) {
   int f = 0;
-#define X(m) s.m = F16_LD(&p.k[(size_t)(f++) * p.np + e]);
+#define X(m) s.m = F16_LD(&p.k[(f++) * 32]);
   F16_KFIELDS(X)
 #undef X
   f = 0;
-#define X(m) s.m = F16_LD(&p.r[(size_t)(f++) * p.np + e]);
+#define X(m) s.m = F16_LD(&p.r[(f++) * 32]);
   F16_RFIELDS(X)
 #undef X
 }
 template <typename R>
-__device__ __forceinline__ void store_veh(const Veh<R>& s, const StatePtrs<R>& p, int64_t e) {
+__device__ __forceinline__ void store_veh(const Veh<R>& s, const StatePtrs<R>& p) {
   int f = 0;
-#define X(m) F16_ST(&p.k[(size_t)(f++) * p.np + e], s.m);
+#define X(m) F16_ST(&p.k[(f++) * 32], s.m);
   F16_KFIELDS(X)
 #undef X
   f = 0;
-#define X(m) F16_ST(&p.r[(size_t)(f++) * p.np + e], s.m);
+#define X(m) F16_ST(&p.r[(f++) * 32], s.m);
   F16_RFIELDS(X)
 #undef X
 }
 template <typename R>
-__device__ __forceinline__ void load_env(EnvScalars& es, const StatePtrs<R>& p, int64_t e) {
-  es.gx = __uint_as_float(p.e[(size_t)EF_GOAL_X * p.np + e]);
-  es.gy = __uint_as_float(p.e[(size_t)EF_GOAL_Y * p.np + e]);
-  es.gz = __uint_as_float(p.e[(size_t)EF_GOAL_Z * p.np + e]);
-  es.last_d = __uint_as_float(p.e[(size_t)EF_LAST_DIST * p.np + e]);
-  es.step = (int32_t)p.e[(size_t)EF_STEP * p.np + e];
-  es.ep_ret = __uint_as_float(p.e[(size_t)EF_EP_RET * p.np + e]);
-  es.ep_len = (int32_t)p.e[(size_t)EF_EP_LEN * p.np + e];
-  es.episodes = p.e[(size_t)EF_EPISODES * p.np + e];
+__device__ __forceinline__ void load_env(EnvScalars& es, const StatePtrs<R>& p) {
+  es.gx = __uint_as_float(p.e[EF_GOAL_X * 32]);
+  es.gy = __uint_as_float(p.e[EF_GOAL_Y * 32]);
+  es.gz = __uint_as_float(p.e[EF_GOAL_Z * 32]);
+  es.last_d = __uint_as_float(p.e[EF_LAST_DIST * 32]);
+  es.step = (int32_t)p.e[EF_STEP * 32];
+  es.ep_ret = __uint_as_float(p.e[EF_EP_RET * 32]);
+  es.ep_len = (int32_t)p.e[EF_EP_LEN * 32];
+  es.episodes = p.e[EF_EPISODES * 32];
 }
 template <typename R>
-__device__ __forceinline__ void store_env(const EnvScalars& es, const StatePtrs<R>& p, int64_t e) {
-  p.e[(size_t)EF_GOAL_X * p.np + e] = __float_as_uint(es.gx);
-  p.e[(size_t)EF_GOAL_Y * p.np + e] = __float_as_uint(es.gy);
-  p.e[(size_t)EF_GOAL_Z * p.np + e] = __float_as_uint(es.gz);
-  p.e[(size_t)EF_LAST_DIST * p.np + e] = __float_as_uint(es.last_d);
-  p.e[(size_t)EF_STEP * p.np + e] = (uint32_t)es.step;
-  p.e[(size_t)EF_EP_RET * p.np + e] = __float_as_uint(es.ep_ret);
-  p.e[(size_t)EF_EP_LEN * p.np + e] = (uint32_t)es.ep_len;
-  p.e[(size_t)EF_EPISODES * p.np + e] = es.episodes;
+__device__ __forceinline__ void store_env(const EnvScalars& es, const StatePtrs<R>& p) {
+  p.e[EF_GOAL_X * 32] = __float_as_uint(es.gx);
+  p.e[EF_GOAL_Y * 32] = __float_as_uint(es.gy);
+  p.e[EF_GOAL_Z * 32] = __float_as_uint(es.gz);
+  p.e[EF_LAST_DIST * 32] = __float_as_uint(es.last_d);
+  p.e[EF_STEP * 32] = (uint32_t)es.step;
+  p.e[EF_EP_RET * 32] = __float_as_uint(es.ep_ret);
+  p.e[EF_EP_LEN * 32] = (uint32_t)es.ep_len;
+  p.e[EF_EPISODES * 32] = es.episodes;
 }
 
 // ------------------------------------------------------------------------------------ constant memory
@@ -150,8 +170,7 @@ struct StepArgs {
   float* ep_return;
   int32_t* ep_len;
   double* stats;
-  int64_t n, np;
-  size_t r_off, e_off;
+  int64_t n;
   uint64_t seed;
   int64_t env_id_base;
   uint32_t step_counter;
@@ -161,17 +180,6 @@ struct StepArgs {
   int32_t* done_count;          // frame layout only: device counter of appended records
   int64_t tile0;                // first 32-env tile of this launch (f16_step_range); n is the end of the range
 };
-
-template <typename R>
-__device__ __forceinline__ StatePtrs<R> state_ptrs(void* state, size_t r_off, size_t e_off, int64_t np) {
-  StatePtrs<R> p;
-  char* b = (char*)state;
-  p.k = (K*)b;
-  p.r = (R*)(b + r_off);
-  p.e = (uint32_t*)(b + e_off);
-  p.np = np;
-  return p;
-}
 
 // Canonical post-reset snapshot (f16_env.cuh: compute_snapshot), one thread, always in double.
 __global__ void f16_init_snapshot_kernel(const Tables<double>* __restrict__ gT, const double* __restrict__ ic_state, double* out) {
@@ -362,20 +370,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // contact and friction code (double precision, ~4 kB of stack) costs the hot path one compare per frame.
 struct GroundStepOut { int flags; float reward, ep_ret; int32_t ep_len; };
 template <typename R>
-__device__ __noinline__ void env_step_ground(const StatePtrs<R> sp, int64_t e, const Tables<R>* T, float4 action, uint64_t seed,
+__device__ __noinline__ void env_step_ground(const StatePtrs<R> sp, const Tables<R>* T, float4 action, uint64_t seed,
                                              uint64_t gid, int auto_reset, float* frame16, float* tframe16, GroundStepOut* out) {
   Veh<R> s;
   EnvScalars es;
-  load_veh(s, sp, e);
-  load_env(es, sp, e);
+  load_veh(s, sp);
+  load_env(es, sp);
   const float act[4] = {action.x, action.y, action.z, action.w};
   float reward = 0.0f, ep_ret = 0.0f;
   int32_t ep_len = 0;
   out->flags = env_step_one<R, GROUND_FULL>(s, es, *T, msets_for<R>(), c_msets, c_snapshot, c_snapshot_props, act, seed, gid, auto_reset,
                                      frame16, tframe16, &reward, &ep_ret, &ep_len);
   out->reward = reward; out->ep_ret = ep_ret; out->ep_len = ep_len;
-  store_veh(s, sp, e);
-  store_env(es, sp, e);
+  store_veh(s, sp);
+  store_env(es, sp);
 }
 
 #ifndef F16_PERSISTENT
@@ -406,7 +414,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
   const int64_t n_tiles = (a.n + 31) >> 5;
   const int64_t warps_total = (int64_t)gridDim.x * WARPS;
   bool tables_ready = false;
-  const StatePtrs<R> sp = state_ptrs<R>(a.state, a.r_off, a.e_off, a.np);
 #if F16_PERSISTENT
 #pragma unroll 1
   for (int64_t tile = a.tile0 + (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += warps_total) {
@@ -419,10 +426,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
     const int64_t e = env0 + lane;
     int flags = 0;
     if (e < a.n) {
+      const StatePtrs<R> sp = state_ptrs<R>(a.state, e);
       Veh<R> s;
       EnvScalars es;
-      load_veh(s, sp, e);
-      load_env(es, sp, e);
+      load_veh(s, sp);
+      load_env(es, sp);
       const uint64_t gid = (uint64_t)(a.env_id_base + e);
       float act[4];
       if (a.actions) {
@@ -458,12 +466,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
         // from the state still in HBM; the cold copy stores the new state itself
         GroundStepOut go;
         if (a.stats) atomicAdd(a.stats + 7, 1.0);
-        env_step_ground<R>(sp, e, &T, make_float4(act[0], act[1], act[2], act[3]), a.seed, gid, a.auto_reset,
+        env_step_ground<R>(sp, &T, make_float4(act[0], act[1], act[2], act[3]), a.seed, gid, a.auto_reset,
                            frame_s[warp][lane], tframe_s[warp][lane], &go);
         flags = go.flags; reward = go.reward; ep_ret = go.ep_ret; ep_len = go.ep_len;
       } else {
-        store_veh(s, sp, e);
-        store_env(es, sp, e);
+        store_veh(s, sp);
+        store_env(es, sp);
       }
       a.reward[e] = reward;
       a.done[e] = (flags & STEP_DONE) ? 1 : 0;
@@ -510,8 +518,7 @@ struct ResetArgs {
   const uint8_t* mask;
   const float* goals;
   float* obs;
-  int64_t n, np;
-  size_t r_off, e_off;
+  int64_t n;
   uint64_t seed;
   int64_t env_id_base;
   int obs_rows;      // 10 (stacked layout) or 20 (ring layout)
@@ -527,10 +534,10 @@ __global__ void __launch_bounds__(BLOCK) f16_reset_kernel(const ResetArgs a) {
   const int64_t e = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   if (e >= a.n) return;
   if (a.mask && !a.mask[e]) return;
-  StatePtrs<R> sp = state_ptrs<R>(a.state, a.r_off, a.e_off, a.np);
+  StatePtrs<R> sp = state_ptrs<R>(a.state, e);
   Veh<R> s;
   EnvScalars es;
-  load_env(es, sp, e);
+  load_env(es, sp);
   float g[3];
   if (a.goals) { g[0] = a.goals[e * 3 + 0]; g[1] = a.goals[e * 3 + 1]; g[2] = a.goals[e * 3 + 2]; }
   else sample_goal(a.seed, (uint64_t)(a.env_id_base + e), (es.episodes & ~kEpisodeUsedBit) + 1, g);
@@ -538,7 +545,7 @@ __global__ void __launch_bounds__(BLOCK) f16_reset_kernel(const ResetArgs a) {
   if (CARRY) {
     // JSBSimEnv.reset on an env object that already exists: run_ic() + set-running on top of whatever the last
     // episode left behind (env_carryover_reset_one, f16_env.cuh)
-    load_veh(s, sp, e);
+    load_veh(s, sp);
     float la[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (a.last_actions) { const float4 v = reinterpret_cast<const float4*>(a.last_actions)[e]; la[0] = v.x; la[1] = v.y; la[2] = v.z; la[3] = v.w; }
     env_carryover_reset_one<R>(s, es, *T, msets_for<R>(), c_snapshot, c_snapshot_props, g, la, fr);
@@ -546,34 +553,34 @@ __global__ void __launch_bounds__(BLOCK) f16_reset_kernel(const ResetArgs a) {
     es.episodes = (es.episodes & ~kEpisodeUsedBit) + 1;
     env_reset_one<R>(s, es, c_snapshot, c_snapshot_props, g, fr);
   }
-  store_veh(s, sp, e);
-  store_env(es, sp, e);
+  store_veh(s, sp);
+  store_env(es, sp);
   float* ob = a.obs + e * (a.obs_rows * F16_OBS_FEATURES);
   for (int r = 0; r < a.obs_rows; ++r)
     for (int c = 0; c < F16_OBS_FEATURES; ++c) ob[r * F16_OBS_FEATURES + c] = fr[c];
 }
 
 template <typename R>
-__global__ void f16_pack_kernel(void* state, size_t r_off, size_t e_off, int64_t n, int64_t np, int64_t first, double* out) {
+__global__ void f16_pack_kernel(void* state, int64_t n, int64_t first, double* out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  StatePtrs<R> sp = state_ptrs<R>(state, r_off, e_off, np);
+  StatePtrs<R> sp = state_ptrs<R>(state, first + i);
   Veh<R> s;
-  load_veh(s, sp, first + i);
+  load_veh(s, sp);
   double a[F16_NUM_STATE_FIELDS];
   veh_to_packed(s, a);
   for (int f = 0; f < F16_NUM_STATE_FIELDS; ++f) out[i * F16_NUM_STATE_FIELDS + f] = a[f];
 }
 template <typename R>
-__global__ void f16_unpack_kernel(void* state, size_t r_off, size_t e_off, int64_t n, int64_t np, int64_t first, const double* in) {
+__global__ void f16_unpack_kernel(void* state, int64_t n, int64_t first, const double* in) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  StatePtrs<R> sp = state_ptrs<R>(state, r_off, e_off, np);
+  StatePtrs<R> sp = state_ptrs<R>(state, first + i);
   double a[F16_NUM_STATE_FIELDS];
   for (int f = 0; f < F16_NUM_STATE_FIELDS; ++f) a[f] = in[i * F16_NUM_STATE_FIELDS + f];
   Veh<R> s;
   veh_from_packed(s, a);
-  store_veh(s, sp, first + i);
+  store_veh(s, sp);
 }
 
 // ==================================================================================== host side
@@ -820,7 +827,7 @@ static int launch_reset(f16_handle h, const uint8_t* mask, const float* goals, u
   h->seed = seed;
   ResetArgs a;
   a.state = h->state; a.mask = mask; a.goals = goals; a.obs = h->obs;
-  a.n = h->L.n; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
+  a.n = h->L.n;
   a.seed = seed; a.env_id_base = h->env_id_base;
   a.obs_rows = h->ring == OBS_RING ? 2 * F16_OBS_FRAMES : h->ring == OBS_FRAME ? 1 : F16_OBS_FRAMES;
   a.tables = h->tables_dev; a.last_actions = last_actions;
@@ -859,7 +866,7 @@ static int launch_step(f16_handle h, const float* actions, int auto_reset, int64
   StepArgs a;
   a.state = h->state; a.tables = h->tables_dev; a.actions = actions; a.obs = h->obs; a.reward = h->reward;
   a.done = h->done; a.truncated = h->truncated; a.terminal_obs = h->terminal_obs; a.ep_return = h->ep_return;
-  a.ep_len = h->ep_len; a.stats = h->stats_dev; a.n = first + count; a.np = h->L.np; a.r_off = h->L.r_off; a.e_off = h->L.e_off;
+  a.ep_len = h->ep_len; a.stats = h->stats_dev; a.n = first + count;
   a.seed = h->seed; a.env_id_base = h->env_id_base; a.step_counter = step_counter; a.auto_reset = auto_reset;
   a.ring_slot = h->ring_head;
   a.done_list = h->done_list; a.done_count = h->done_count;
@@ -965,16 +972,16 @@ int f16_step_host(f16_handle h, const float* actions_host, int auto_reset, float
 
 static int pack_range(f16_handle h, int64_t first, int64_t count, double* dev_out, cudaStream_t st) {
   unsigned grid = (unsigned)((count + 127) / 128);
-  if (h->mode == F16_MODE_FP64) f16_pack_kernel<double><<<grid, 128, 0, st>>>(h->state, h->L.r_off, h->L.e_off, count, h->L.np, first, dev_out);
-  else f16_pack_kernel<float><<<grid, 128, 0, st>>>(h->state, h->L.r_off, h->L.e_off, count, h->L.np, first, dev_out);
+  if (h->mode == F16_MODE_FP64) f16_pack_kernel<double><<<grid, 128, 0, st>>>(h->state, count, first, dev_out);
+  else f16_pack_kernel<float><<<grid, 128, 0, st>>>(h->state, count, first, dev_out);
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 static int unpack_range(f16_handle h, int64_t first, int64_t count, const double* dev_in, cudaStream_t st) {
   unsigned grid = (unsigned)((count + 127) / 128);
-  if (h->mode == F16_MODE_FP64) f16_unpack_kernel<double><<<grid, 128, 0, st>>>(h->state, h->L.r_off, h->L.e_off, count, h->L.np, first, dev_in);
-  else f16_unpack_kernel<float><<<grid, 128, 0, st>>>(h->state, h->L.r_off, h->L.e_off, count, h->L.np, first, dev_in);
+  if (h->mode == F16_MODE_FP64) f16_unpack_kernel<double><<<grid, 128, 0, st>>>(h->state, count, first, dev_in);
+  else f16_unpack_kernel<float><<<grid, 128, 0, st>>>(h->state, count, first, dev_in);
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -1018,7 +1025,7 @@ int f16_set_env_step(f16_handle h, int64_t env, int32_t current_step) {
   if (env < 0 || env >= h->L.n) return fail("f16_set_env_step: env out of range");
   CUDA_OK(cudaSetDevice(h->device));
   CUDA_OK(cudaDeviceSynchronize());
-  char* p = (char*)h->state + h->L.e_off + ((size_t)EF_STEP * h->L.np + env) * 4;
+  char* p = (char*)h->state + (size_t)(env >> 5) * h->L.tile_bytes + h->L.e_off + ((size_t)EF_STEP * 32 + (size_t)(env & 31)) * 4;
   CUDA_OK(cudaMemcpy(p, &current_step, 4, cudaMemcpyHostToDevice));
   return 0;
 }

@@ -33,12 +33,16 @@ class F16BatchedEnv:
     with them on, such a step is redone by a cold copy of the step that includes the contact and friction
     forces (one crash in fifteen under random actions; see DESIGN.md for what it costs).
 
-    obs_layout: "frame" keeps no observation history on the device: `obs` is the (N, 15) tensor of newest
-    frames, 60 B written per env-step; the ten-frame windows then live in host memory (host_window.py,
-    F16VecEnv's default) or in the frame-only rollout store (rollout.py). "stacked" (default) keeps a contiguous (N, 10, 15) tensor that the step kernel shifts in
-    place, exactly the reference's array. "ring" keeps (N, 20, 15) and writes each new frame twice, so
-    `obs` is a zero-copy strided view (N, 10, 15) of the current window - same values, 2.4x less HBM
-    traffic per step; each env's 150 floats stay contiguous (obs.view(N, 150) is a valid strided matrix).
+    obs_layout: where the ten-frame window of each env lives.
+    "ring" (default) keeps a slot-major ring buffer (20, N, 15) that the step kernel writes: the newest frames go into
+    their slot and into the mirror slot ten further on as two contiguous (N, 15) planes, so `obs` is always a zero-copy
+    strided (N, 10, 15) view of the current window (row 0 oldest, row 9 newest; strides (15, N*15, 1)) - the reference's
+    values with 120 B written per env-step instead of 540 B read + 600 B written. obs[:, k, :] is contiguous over the
+    envs (what a GPU consumer wants); obs.reshape(N, 150) copies. Like the reference's array the view is only valid
+    until the next step. "stacked" keeps the reference's contiguous (N, 10, 15)
+    tensor and shifts it in place every step. "frame" keeps no history on the device: `obs` is the (N, 15) tensor of
+    newest frames, 60 B written per env-step; the windows then live in host memory (host_window.py, F16VecEnv's
+    default) or in the frame-only rollout store (rollout.py).
 
     reset_mode: "snapshot" (default) starts every episode from the canonical state of a FRESH reference env
     object. "carryover" does what JSBSimEnv.reset does to an env object that already exists
@@ -49,7 +53,7 @@ class F16BatchedEnv:
     """
 
     def __init__(self, num_envs: int, device=None, mode: str = "fp32", seed: int = 0,
-                 with_terminal_obs: bool = True, env_id_base: int = 0, obs_layout: str = "stacked",
+                 with_terminal_obs: bool = True, env_id_base: int = 0, obs_layout: str = "ring",
                  done_list: bool = False, ground_reactions=None, reset_mode: str = "snapshot"):
         if not torch.cuda.is_available():
             raise _lib.F16Error("F16BatchedEnv needs a CUDA device: the F-16 env has no CPU fallback")
@@ -86,9 +90,10 @@ class F16BatchedEnv:
             if obs_layout == "frame":
                 self._obs_buf = torch.zeros((n, NUM_FEATURES), dtype=torch.float32, device=self.device)
                 with_terminal_obs = False
+            elif obs_layout == "ring":
+                self._obs_buf = torch.zeros((2 * NUM_STACKED_FRAMES, n, NUM_FEATURES), dtype=torch.float32, device=self.device)   # [slot][env][15]
             else:
-                rows = NUM_STACKED_FRAMES * (2 if obs_layout == "ring" else 1)
-                self._obs_buf = torch.zeros((n, rows, NUM_FEATURES), dtype=torch.float32, device=self.device)
+                self._obs_buf = torch.zeros((n, NUM_STACKED_FRAMES, NUM_FEATURES), dtype=torch.float32, device=self.device)
             self.reward = torch.zeros(n, dtype=torch.float32, device=self.device)
             self.done = torch.zeros(n, dtype=torch.uint8, device=self.device)
             self.truncated = torch.zeros(n, dtype=torch.uint8, device=self.device)
@@ -125,7 +130,7 @@ class F16BatchedEnv:
             return self._obs_buf
         first = C.c_int()
         _lib.check(self.lib.f16_obs_window(self._h, C.byref(first)), "f16_obs_window")
-        return self._obs_buf[:, first.value:first.value + NUM_STACKED_FRAMES, :]
+        return self._obs_buf[first.value:first.value + NUM_STACKED_FRAMES].permute(1, 0, 2)
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):

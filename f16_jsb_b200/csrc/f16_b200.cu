@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -141,13 +142,33 @@ __constant__ double c_snapshot_props[12];               // the 12 STATE_FORMAT p
 
 // ------------------------------------------------------------------------------------ kernels
 #ifndef F16_BLOCK
-#define F16_BLOCK 128            // measured on B200 (1M envs): 128 x 3 CTAs/SM best; 64x6 -1 %, 96x4 -2 %, 256x2 -10 %
+#define F16_BLOCK 128            // reset / pack kernels, and the step kernels unless overridden below
+#endif
+// Step-kernel launch shapes (profiles/r2_*: A/B runs at 1M envs, steady state).
+#ifndef F16_BLOCK_F32
+#define F16_BLOCK_F32 128
 #endif
 #ifndef F16_MIN_BLOCKS_F32
-#define F16_MIN_BLOCKS_F32 3   // CTAs per SM of the float step kernel: 3 x 128 threads -> 168 registers, 72 B of spills
+#define F16_MIN_BLOCKS_F32 4   // CTAs per SM of the float step kernel: 4 x 128 threads -> 128 registers
+#endif
+#ifndef F16_BLOCK_F64
+#define F16_BLOCK_F64 256
+#endif
+#ifndef F16_MIN_BLOCKS_F64
+#define F16_MIN_BLOCKS_F64 1   // 255 registers
+#endif
+// All warps of a CTA start every FDM frame together (one CTA barrier per frame): they then run the same ~25 KB of
+// straight-line code within a few hundred cycles of each other and share their instruction-cache fills.
+#ifndef F16_FRAME_SYNC_F32
+#define F16_FRAME_SYNC_F32 1
+#endif
+#ifndef F16_FRAME_SYNC_F64
+#define F16_FRAME_SYNC_F64 1
 #endif
 constexpr int BLOCK = F16_BLOCK;
-constexpr int WARPS = BLOCK / 32;
+template <typename R> struct StepShape;
+template <> struct StepShape<float> { static constexpr int BLK = F16_BLOCK_F32, MINB = F16_MIN_BLOCKS_F32; static constexpr bool SYNC = F16_FRAME_SYNC_F32 != 0; };
+template <> struct StepShape<double> { static constexpr int BLK = F16_BLOCK_F64, MINB = F16_MIN_BLOCKS_F64; static constexpr bool SYNC = F16_FRAME_SYNC_F64 != 0; };
 
 template <typename R>
 __device__ __forceinline__ void stage_tables(Tables<R>* dst, const Tables<R>* __restrict__ src) {
@@ -175,7 +196,8 @@ struct StepArgs {
   int64_t env_id_base;
   uint32_t step_counter;
   int auto_reset;
-  int ring_slot;     // ring layout only: slot (0..9) this step writes; the window is rows slot+1 .. slot+10
+  int ring_slot;     // ring layout only: slot (0..9) this step writes; the window is slots slot+1 .. slot+10
+  size_t ring_pitch; // ring layout only: floats between consecutive slots (= N x 15)
   f16_done_record* done_list;   // frame layout only: one record per env that finished this step (may be mapped host memory)
   int32_t* done_count;          // frame layout only: device counter of appended records
   int64_t tile0;                // first 32-env tile of this launch (f16_step_range); n is the end of the range
@@ -273,51 +295,62 @@ __device__ __forceinline__ void warp_write_obs(float* __restrict__ obs, float* _
   }
 }
 
-// Ring layout of the observations (opt-in, f16_bind_ring): per env 20 rows of 15 floats; each step writes
-// the newest frame into row `slot` and its mirror `slot + 10`, so the chronological stack is always the
-// contiguous window of rows slot+1 .. slot+10 and nothing is ever shifted: 120 B written per env-step
-// instead of 540 B read + 600 B written. A reset fills all 20 rows with the reset frame. The warp writes
-// cooperatively: lanes run over the 32 x 15 floats of one row set, so a store touches ~2 envs' 60-byte rows.
-__device__ __forceinline__ void warp_write_ring(float* __restrict__ ring, float* __restrict__ term_obs, int64_t env0, int slot,
-                                                const float (*frame_s)[16], const float (*tframe_s)[16],
+// Ring layout of the observations (f16_bind_ring; F16BatchedEnv's default): 20 slots of one frame per env, slot-major
+// ring[slot][env][15]. Each step writes the newest frame of every env into slot `slot` and into the mirror slot
+// `slot + 10`, so the chronological ten-frame window is always the contiguous slot range slot+1 .. slot+10 and the
+// stacked observation is the strided view obs[n][k][f] = ring[slot + 1 + k][n][f] - nothing is ever shifted or read:
+// 120 B written per env-step instead of 540 B read + 600 B written. Slot-major makes each of the two writes what the
+// frame layout's single write is: one contiguous, fully coalesced 1 920-byte span per warp (an env-major ring put
+// 60-byte rows at a 1 200-byte pitch: partial 32-byte sectors that L2 has to read back from HBM before merging,
+// measured 0.358 ms per step of 1M envs against 0.286 ms for the frame layout), and a consumer kernel that walks the
+// window reads (N,15) planes that are contiguous over the envs. A reset fills all 20 slots of the env with the reset
+// frame; a finished env's terminal stack is gathered from the nine older slots first.
+__device__ __forceinline__ void warp_write_ring(float* __restrict__ ring, size_t slot_pitch, float* __restrict__ term_obs, int64_t env0,
+                                                int64_t n, int slot, const float (*frame_s)[16], const float (*tframe_s)[16],
                                                 const uint8_t* flags_s) {
   const int lane = threadIdx.x & 31;
-  constexpr int ROW = F16_OBS_FEATURES, RING_ROWS = 2 * F16_OBS_FRAMES, PER_ENV = RING_ROWS * ROW;   // 15, 20, 300
+  constexpr int ROW = F16_OBS_FEATURES, RING_ROWS = 2 * F16_OBS_FRAMES;   // 15, 20
   const uint8_t my = flags_s[lane];
   const unsigned m_active = __ballot_sync(0xffffffffu, my & 1);
-  const unsigned m_reset = __ballot_sync(0xffffffffu, my & 2);
-  const unsigned m_term = term_obs ? __ballot_sync(0xffffffffu, my & 4) : 0u;
-  float* const base = ring + env0 * PER_ENV;
+  const unsigned m_reset = __ballot_sync(0xffffffffu, my & 2) & m_active;
+  const unsigned m_term = term_obs ? (__ballot_sync(0xffffffffu, my & 4) & m_active) : 0u;
+  float* const base = ring + env0 * ROW;                     // this warp's 32 x 15 floats inside slot 0
   // terminal stacks first (they need the window as it was before this step's frame): rare
   if (m_term) {
     for (int l = 0; l < 32; ++l) {
       if (!((m_term >> l) & 1)) continue;
-      const float* eb = base + l * PER_ENV + (slot + 1) * ROW;       // rows slot+1 .. slot+9 = the nine older frames
       float* tb = term_obs + (env0 + l) * (F16_OBS_FRAMES * ROW);
-      for (int j = lane; j < F16_OBS_FRAMES * ROW; j += 32) tb[j] = (j < 9 * ROW) ? eb[j] : tframe_s[l][j - 9 * ROW];
+      for (int j = lane; j < F16_OBS_FRAMES * ROW; j += 32) {
+        const int k = j / ROW, c = j - k * ROW;                 // row k of the stack: slots slot+1 .. slot+9 are the nine older frames
+        tb[j] = (k < 9) ? base[(size_t)(slot + 1 + k) * slot_pitch + l * ROW + c] : tframe_s[l][c];
+      }
     }
     __syncwarp();
   }
-  // newest frame into rows slot and slot+10 of every env of the warp
+  // newest frame (the reset frame for an env that auto-reset) into slots `slot` and `slot + 10`: two coalesced spans
+  const int live = (int)((n - env0) < 32 ? (n - env0) : 32);
+  float* const s0 = base + (size_t)slot * slot_pitch;
+  float* const s1 = base + (size_t)(slot + F16_OBS_FRAMES) * slot_pitch;
   int l = 0, c = lane;                                    // element i = it*32 + lane -> (env l, column c)
   while (c >= ROW) { c -= ROW; ++l; }
-#pragma unroll 1
+#pragma unroll
   for (int it = 0; it < ROW; ++it) {
-    if (l < 32 && ((m_active >> l) & 1) && !((m_reset >> l) & 1)) {
+    if (l < live) {
       const float v = frame_s[l][c];
-      float* eb = base + l * PER_ENV + c;
-      eb[slot * ROW] = v;
-      eb[(slot + F16_OBS_FRAMES) * ROW] = v;
+      s0[it * 32 + lane] = v;
+      s1[it * 32 + lane] = v;
     }
     c += 2; l += 2;                                       // 32 = 2 * 15 + 2
     if (c >= ROW) { c -= ROW; ++l; }
   }
-  // reset envs: all 20 rows = reset frame
+  // reset envs: the other 18 slots = reset frame as well (rare)
   if (m_reset) {
     for (int lr = 0; lr < 32; ++lr) {
-      if (!((m_reset >> lr) & 1) || !((m_active >> lr) & 1)) continue;
-      float* eb = base + lr * PER_ENV;
-      for (int j = lane; j < PER_ENV; j += 32) eb[j] = frame_s[lr][j % ROW];
+      if (!((m_reset >> lr) & 1)) continue;
+      for (int j = lane; j < RING_ROWS * ROW; j += 32) {
+        const int r = j / ROW, cc = j - r * ROW;
+        base[(size_t)r * slot_pitch + lr * ROW + cc] = frame_s[lr][cc];
+      }
     }
   }
 }
@@ -386,20 +419,17 @@ __device__ __noinline__ void env_step_ground(const StatePtrs<R> sp, const Tables
   store_env(es, sp);
 }
 
-#ifndef F16_PERSISTENT
-#define F16_PERSISTENT 0
-#endif
-
 #ifndef F16_PREFETCH_OBS
 #define F16_PREFETCH_OBS 1
 #endif
-// Persistent step kernel: the grid is sized to the machine (SMs x resident CTAs); the table image is
-// staged once per CTA and every warp then walks its own sequence of 32-env tiles (tile = warp id,
-// += total warps). Warps never synchronise with each other after the staging barrier, so their
-// load / compute / store phases drift apart and overlap on each SM.
+// Step kernel: one warp = one tile of 32 envs, one CTA = StepShape<R>::BLK / 32 tiles; the table image is staged once
+// per CTA by one bulk copy. Every thread of the CTA runs the four frames - lanes past the last env redo env n-1 without
+// storing anything - so the per-frame CTA barrier (StepShape<R>::SYNC) is reached by all of them.
 enum { OBS_STACKED = 0, OBS_RING = 1, OBS_FRAME = 2 };
-template <typename R, int MINB, int OBS, bool GROUND>
-__global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a) {
+template <typename R, int OBS, bool GROUND>
+__global__ void __launch_bounds__(StepShape<R>::BLK, StepShape<R>::MINB) f16_step_kernel(const StepArgs a) {
+  constexpr int WARPS = StepShape<R>::BLK / 32;
+  constexpr bool SYNC = StepShape<R>::SYNC;
   __shared__ __align__(128) Tables<R> T;
   __shared__ __align__(16) float frame_s[WARPS][32][16];
   __shared__ __align__(16) float tframe_s[WARPS][32][16];
@@ -412,55 +442,45 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_tiles = (a.n + 31) >> 5;
-  const int64_t warps_total = (int64_t)gridDim.x * WARPS;
-  bool tables_ready = false;
-#if F16_PERSISTENT
-#pragma unroll 1
-  for (int64_t tile = a.tile0 + (int64_t)blockIdx.x * WARPS + warp; tile < n_tiles; tile += warps_total) {
-#else
-  (void)warps_total;
-  const int64_t tile = a.tile0 + (int64_t)blockIdx.x * WARPS + warp;
-  if (tile < n_tiles) {
-#endif
-    const int64_t env0 = tile << 5;
-    const int64_t e = env0 + lane;
-    int flags = 0;
-    if (e < a.n) {
-      const StatePtrs<R> sp = state_ptrs<R>(a.state, e);
-      Veh<R> s;
-      EnvScalars es;
-      load_veh(s, sp);
-      load_env(es, sp);
-      const uint64_t gid = (uint64_t)(a.env_id_base + e);
-      float act[4];
-      if (a.actions) {
-        float4 v = reinterpret_cast<const float4*>(a.actions)[e];
-        act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
-      } else {
-        sample_action(a.seed, gid, a.step_counter, act);
-      }
-      if (!tables_ready) { mbar_wait(&tbar, 0); tables_ready = true; }
-      float reward, ep_ret = 0.0f;
-      int32_t ep_len = 0;
-      // each lane prefetches lines lane, lane+32, ... of the warp's 150-line observation span (F16_PREFETCH_OBS)
-      PrefetchHint pf = {nullptr, 0, 0};
+  const int64_t tile_raw = a.tile0 + (int64_t)blockIdx.x * WARPS + warp;
+  const bool tile_ok = tile_raw < n_tiles;
+  if (!SYNC && !tile_ok) return;
+  const int64_t tile = tile_ok ? tile_raw : n_tiles - 1;
+  const int64_t env0 = tile << 5;
+  const bool valid = tile_ok && env0 + lane < a.n;
+  const int64_t e = (SYNC && !valid) ? a.n - 1 : env0 + lane;
+  int flags = 0;
+  if (SYNC || valid) {
+    const StatePtrs<R> sp = state_ptrs<R>(a.state, e);
+    Veh<R> s;
+    EnvScalars es;
+    load_veh(s, sp);
+    load_env(es, sp);
+    const uint64_t gid = (uint64_t)(a.env_id_base + e);
+    float act[4];
+    if (a.actions) {
+      float4 v = reinterpret_cast<const float4*>(a.actions)[e];
+      act[0] = v.x; act[1] = v.y; act[2] = v.z; act[3] = v.w;
+    } else {
+      sample_action(a.seed, gid, a.step_counter, act);
+    }
+    mbar_wait(&tbar, 0);
+    float reward, ep_ret = 0.0f;
+    int32_t ep_len = 0;
+    // each lane prefetches lines lane, lane+32, ... of the warp's 150-line observation span (F16_PREFETCH_OBS)
+    PrefetchHint pf = {nullptr, 0, 0};
 #if F16_PREFETCH_OBS == 1
-      if (OBS == OBS_STACKED) {
-        pf.ptr = reinterpret_cast<const char*>(a.obs + env0 * (F16_OBS_FRAMES * F16_OBS_FEATURES)) + lane * 128;
-        pf.count = lane < 22 ? 5 : 4;       // 150 lines of 128 bytes
-        pf.stride = 32 * 128;
-      }
-#elif F16_PREFETCH_OBS == 2
-      // one TMA bulk prefetch of the warp's whole 19 200-byte span, issued by lane 0
-      if (lane == 0) {
-        const int64_t left = (a.n - env0) * (int64_t)(F16_OBS_FRAMES * F16_OBS_FEATURES * 4);
-        pf.ptr = reinterpret_cast<const char*>(a.obs + env0 * (F16_OBS_FRAMES * F16_OBS_FEATURES));
-        pf.count = -1;
-        pf.stride = (int)(left < 19200 ? (left & ~15) : 19200);
-      }
+    if (OBS == OBS_STACKED) {
+      pf.ptr = reinterpret_cast<const char*>(a.obs + env0 * (F16_OBS_FRAMES * F16_OBS_FEATURES)) + lane * 128;
+      pf.count = lane < 22 ? 5 : 4;       // 150 lines of 128 bytes
+      pf.stride = 32 * 128;
+    }
 #endif
-      flags = env_step_one<R, GROUND ? GROUND_DETECT : GROUND_OFF>(s, es, T, msets_for<R>(), c_msets, c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
-                                     frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len, pf);
+    flags = env_step_one<R, GROUND ? GROUND_DETECT : GROUND_OFF, SYNC>(s, es, T, msets_for<R>(), c_msets, c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
+                                   frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len, pf);
+    if (SYNC && !valid) {
+      flags = 0;
+    } else {
       if (GROUND && (flags & STEP_NEAR_GROUND)) {
         // a contact point reached the ground (last env-step of a crash): redo the step with the contact forces
         // from the state still in HBM; the cold copy stores the new state itself
@@ -504,13 +524,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) f16_step_kernel(const StepArgs a)
         }
       }
     }
-    flags_s[warp][lane] = (uint8_t)(flags & (STEP_ACTIVE | STEP_RESET | STEP_TERMINAL));
-    __syncwarp();
-    if (OBS == OBS_FRAME) warp_write_frames(a.obs, env0, a.n, frame_s[warp]);
-    else if (OBS == OBS_RING) warp_write_ring(a.obs, a.terminal_obs, env0, a.ring_slot, frame_s[warp], tframe_s[warp], flags_s[warp]);
-    else warp_write_obs(a.obs, a.terminal_obs, env0, frame_s[warp], tframe_s[warp], flags_s[warp]);
-    __syncwarp();   // the frame / flag staging of this warp is reused by its next tile
   }
+  if (!tile_ok) return;      // a whole warp past the last tile (SYNC only): it has nothing to write
+  flags_s[warp][lane] = (uint8_t)(flags & (STEP_ACTIVE | STEP_RESET | STEP_TERMINAL));
+  __syncwarp();
+  if (OBS == OBS_FRAME) warp_write_frames(a.obs, env0, a.n, frame_s[warp]);
+  else if (OBS == OBS_RING) warp_write_ring(a.obs, a.ring_pitch, a.terminal_obs, env0, a.n, a.ring_slot, frame_s[warp], tframe_s[warp], flags_s[warp]);
+  else warp_write_obs(a.obs, a.terminal_obs, env0, frame_s[warp], tframe_s[warp], flags_s[warp]);
 }
 
 struct ResetArgs {
@@ -521,7 +541,8 @@ struct ResetArgs {
   int64_t n;
   uint64_t seed;
   int64_t env_id_base;
-  int obs_rows;      // 10 (stacked layout) or 20 (ring layout)
+  int obs_rows;      // 10 (stacked layout), 20 (ring layout) or 1 (frame layout)
+  size_t env_pitch, row_pitch;   // floats between consecutive envs / rows of one env (stacked: 150, 15; ring: 15, N x 15)
   const void* tables;            // carry-over reset only: the table image of the context's precision
   const float* last_actions;     // carry-over reset only: N x 4, the action of each env's last step (or NULL)
 };
@@ -555,9 +576,9 @@ __global__ void __launch_bounds__(BLOCK) f16_reset_kernel(const ResetArgs a) {
   }
   store_veh(s, sp);
   store_env(es, sp);
-  float* ob = a.obs + e * (a.obs_rows * F16_OBS_FEATURES);
+  float* ob = a.obs + (size_t)e * a.env_pitch;
   for (int r = 0; r < a.obs_rows; ++r)
-    for (int c = 0; c < F16_OBS_FEATURES; ++c) ob[r * F16_OBS_FEATURES + c] = fr[c];
+    for (int c = 0; c < F16_OBS_FEATURES; ++c) ob[(size_t)r * a.row_pitch + c] = fr[c];
 }
 
 template <typename R>
@@ -587,7 +608,7 @@ __global__ void f16_unpack_kernel(void* state, int64_t n, int64_t first, const d
 namespace {
 
 thread_local std::string g_err;
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};   // all handles and host threads share it
 
 int fail(const char* fmt, ...) {
   char buf[512];
@@ -672,7 +693,7 @@ int f16_internal_set_obs_frame(f16_handle h, float* obs_frame) {
 
 const char* f16_last_error(void) { return g_err.c_str(); }
 const char* f16_version(void) { return "f16_b200 0.1 (sm_100a)"; }
-int64_t f16_launch_count(void) { return g_launches; }
+int64_t f16_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int f16_num_state_fields(void) { return F16_NUM_STATE_FIELDS; }
 
 static int create_impl(f16_ctx* c, int64_t n_envs, int device, int mode) {
@@ -718,8 +739,8 @@ static int create_impl(f16_ctx* c, int64_t n_envs, int device, int mode) {
   CUDA_OK(cudaMalloc(&c->actions_stage, (size_t)n_envs * F16_ACTION_DIM * sizeof(float)));
 
   CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
-  if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, 1, OBS_STACKED, true>, BLOCK, 0));
-  else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float, F16_MIN_BLOCKS_F32, OBS_STACKED, false>, BLOCK, 0));
+  if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, OBS_RING, true>, StepShape<double>::BLK, 0));
+  else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<float, OBS_RING, false>, StepShape<float>::BLK, 0));
   if (c->ctas_per_sm < 1) c->ctas_per_sm = 1;
   return 0;
 }
@@ -830,6 +851,8 @@ static int launch_reset(f16_handle h, const uint8_t* mask, const float* goals, u
   a.n = h->L.n;
   a.seed = seed; a.env_id_base = h->env_id_base;
   a.obs_rows = h->ring == OBS_RING ? 2 * F16_OBS_FRAMES : h->ring == OBS_FRAME ? 1 : F16_OBS_FRAMES;
+  a.env_pitch = h->ring == OBS_STACKED ? (size_t)F16_OBS_FRAMES * F16_OBS_FEATURES : (size_t)F16_OBS_FEATURES;
+  a.row_pitch = h->ring == OBS_RING ? (size_t)h->L.n * F16_OBS_FEATURES : (size_t)F16_OBS_FEATURES;
   a.tables = h->tables_dev; a.last_actions = last_actions;
   unsigned grid = (unsigned)((h->L.n + BLOCK - 1) / BLOCK);
   const cudaStream_t st = (cudaStream_t)stream;
@@ -869,38 +892,29 @@ static int launch_step(f16_handle h, const float* actions, int auto_reset, int64
   a.ep_len = h->ep_len; a.stats = h->stats_dev; a.n = first + count;
   a.seed = h->seed; a.env_id_base = h->env_id_base; a.step_counter = step_counter; a.auto_reset = auto_reset;
   a.ring_slot = h->ring_head;
+  a.ring_pitch = (size_t)h->L.n * F16_OBS_FEATURES;
   a.done_list = h->done_list; a.done_count = h->done_count;
   a.tile0 = first / 32;
-  // persistent grid: SMs x resident CTAs (capped by the number of 32-env tiles)
   const int64_t tiles = (count + 31) / 32;
-  int64_t want = (int64_t)h->num_sms * h->ctas_per_sm;
-  const int64_t need = (tiles + WARPS - 1) / WARPS;
-  unsigned grid = (unsigned)((F16_PERSISTENT && want < need) ? want : need);
-
   const cudaStream_t st = (cudaStream_t)stream;
-#define F16_LAUNCH_STEP_G(R, MINB, G)                                                                      \
+#define F16_LAUNCH_STEP_G(R, G)                                                                             \
   do {                                                                                                    \
-    if (h->ring == OBS_FRAME) f16_step_kernel<R, MINB, OBS_FRAME, G><<<grid, BLOCK, 0, st>>>(a);          \
-    else if (h->ring == OBS_RING) f16_step_kernel<R, MINB, OBS_RING, G><<<grid, BLOCK, 0, st>>>(a);       \
-    else f16_step_kernel<R, MINB, OBS_STACKED, G><<<grid, BLOCK, 0, st>>>(a);                             \
+    constexpr int BLK = StepShape<R>::BLK;                                                                \
+    const unsigned grid = (unsigned)((tiles + BLK / 32 - 1) / (BLK / 32));                                \
+    if (h->ring == OBS_FRAME) f16_step_kernel<R, OBS_FRAME, G><<<grid, BLK, 0, st>>>(a);                  \
+    else if (h->ring == OBS_RING) f16_step_kernel<R, OBS_RING, G><<<grid, BLK, 0, st>>>(a);               \
+    else f16_step_kernel<R, OBS_STACKED, G><<<grid, BLK, 0, st>>>(a);                                     \
   } while (0)
-#define F16_LAUNCH_STEP(R, MINB)                                                                           \
+#define F16_LAUNCH_STEP(R)                                                                                  \
   do {                                                                                                    \
-    if (h->ground) F16_LAUNCH_STEP_G(R, MINB, true);                                                      \
-    else F16_LAUNCH_STEP_G(R, MINB, false);                                                               \
+    if (h->ground) F16_LAUNCH_STEP_G(R, true);                                                            \
+    else F16_LAUNCH_STEP_G(R, false);                                                                     \
   } while (0)
-  if (h->mode == F16_MODE_FP64) {
-    F16_LAUNCH_STEP(double, 1);
-  } else {
-    // Two register budgets of the float kernel: F16_MIN_BLOCKS_F32 CTAs/SM (167 registers, fastest per
-    // env when the grid is many waves deep) and one more CTA per SM (128 registers), which wins when the
-    // extra resident CTAs save a whole wave (e.g. 65 536 envs = 512 CTAs: 2 waves at 3/SM, 1 at 4/SM).
-    const int64_t slots_a = (int64_t)h->num_sms * F16_MIN_BLOCKS_F32, slots_b = (int64_t)h->num_sms * (F16_MIN_BLOCKS_F32 + 1);
-    const double cost_a = (double)((need + slots_a - 1) / slots_a);
-    const double cost_b = (double)((need + slots_b - 1) / slots_b) * 1.45;   // measured per-wave cost ratio
-    if (cost_b < cost_a) F16_LAUNCH_STEP(float, F16_MIN_BLOCKS_F32 + 1);
-    else F16_LAUNCH_STEP(float, F16_MIN_BLOCKS_F32);
-  }
+  // One register budget per precision (StepShape): the float kernel runs at 4 CTAs x 128 threads per SM (128
+  // registers) - with the ring layout that is the faster build at every batch size (profiles/r2_ab_fp32_variants.txt:
+  // 0.3103 against 0.3127 ms per step of 1M envs for the 168-register build, and one wave instead of two at 65 536 envs)
+  if (h->mode == F16_MODE_FP64) F16_LAUNCH_STEP(double);
+  else F16_LAUNCH_STEP(float);
 #undef F16_LAUNCH_STEP
 #undef F16_LAUNCH_STEP_G
   g_launches++;
@@ -954,11 +968,13 @@ int f16_step_host(f16_handle h, const float* actions_host, int auto_reset, float
   if (obs_host) {
     const size_t stack_bytes = F16_OBS_FRAMES * F16_OBS_FEATURES * sizeof(float);
     if (h->ring == OBS_RING) {
-      // strided device->host copy of each env's 600-byte window out of its 1200-byte ring
+      // the window is ten (N,15) planes of the slot-major ring: one strided device->host copy per row of the stacks
       int first = 0;
       f16_obs_window(h, &first);
-      CUDA_OK(cudaMemcpy2DAsync(obs_host, stack_bytes, h->obs + (size_t)first * F16_OBS_FEATURES, 2 * stack_bytes, stack_bytes, n,
-                                cudaMemcpyDeviceToHost, st));
+      const size_t row_bytes = F16_OBS_FEATURES * sizeof(float);
+      for (int k = 0; k < F16_OBS_FRAMES; ++k)
+        CUDA_OK(cudaMemcpy2DAsync(obs_host + (size_t)k * F16_OBS_FEATURES, stack_bytes, h->obs + (size_t)(first + k) * n * F16_OBS_FEATURES,
+                                  row_bytes, row_bytes, n, cudaMemcpyDeviceToHost, st));
     } else {
       CUDA_OK(cudaMemcpyAsync(obs_host, h->obs, n * stack_bytes, cudaMemcpyDeviceToHost, st));
     }

@@ -305,7 +305,7 @@ F16_HD int env_step_epilogue(Veh<R>& s, EnvScalars& es, const FrameObs<R>& fo, c
 }
 
 enum { GROUND_OFF = 0, GROUND_DETECT = 1, GROUND_FULL = 2 };
-template <typename R, int GMODE>
+template <typename R, int GMODE, bool FRAME_SYNC = false>
 F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const MassSetT<R>* msets, const MassSetT<double>* msets_d,
                         const double* snapshot, const double* snapshot_props, const float* act, uint64_t seed, uint64_t env_id,
                         int auto_reset, float* frame16, float* tframe16, float* reward_out, float* ep_ret_out, int32_t* ep_len_out,
@@ -345,6 +345,11 @@ F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const Mas
         if (pf.count < 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pf.ptr), "r"(pf.stride) : "memory");
         for (int i = 0; i < pf.count; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf.ptr + (size_t)i * pf.stride));
       }
+#endif
+#ifdef __CUDA_ARCH__
+      // every warp of the CTA starts the frame together (shared instruction-cache fills; the caller guarantees that all
+      // threads of the CTA run these four iterations)
+      if (FRAME_SYNC && pass == 0) __syncthreads();
 #endif
       // the first flight frame after a fresh construct still carries the mass properties of the 1500-lb tanks' CG
       const bool first = es.step == 1 && k == 0 && pass == 0 && !(es.episodes & kEpisodeUsedBit);

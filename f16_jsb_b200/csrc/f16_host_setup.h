@@ -131,6 +131,10 @@ void build_tables(Tables<R>* T) {
   fill_seg(T->seg_alpha, alpha_bp, NA);
   fill_seg(T->seg_de, de_bp, NDE);
   fill_seg(T->seg_b7, b7_bp, NB7);
+  // the frame derives the 7-point beta segment from the 13-point one: the coarse grid must be every other fine point
+  static_assert(NB13 == 2 * NB7 - 1, "beta grids");
+  for (int i = 0; i < NB7; ++i)
+    if (b7_bp[i] != b13_bp[2 * i]) { std::fprintf(stderr, "f16: beta breakpoint grids are not nested\n"); std::abort(); }
   fill_seg(T->seg_b13, b13_bp, NB13);
   // union of the Mach breakpoints of the nine Mach tables; every table is piecewise linear with
   // clamped ends, so resampling it on the union grid reproduces it exactly

@@ -62,14 +62,16 @@ int f16_get_ground_reactions(f16_handle h);
 int f16_bind(f16_handle h, void* state, float* obs, float* reward, uint8_t* done, uint8_t* truncated,
              float* terminal_obs, float* ep_return, int32_t* ep_len);
 
-/* Optional ring layout of the observations. obs_ring: N x 20 x 15 float. Each step writes the newest frame
- * into row `slot` and row `slot + 10` (slot cycles 0..9); the chronological (10,15) stack of every env is the
- * contiguous row window first_row .. first_row + 9 reported by f16_obs_window (a strided view, never shifted or
- * copied): 120 B written per env-step instead of 540 B read + 600 B written. Everything else as f16_bind;
- * terminal_obs stays a plain N x 10 x 15 tensor; f16_step_host still returns contiguous N x 10 x 15 host arrays. */
+/* Ring layout of the observations (the ring buffer fused into the step kernel; F16BatchedEnv's default).
+ * obs_ring: 20 x N x 15 float, slot-major. Each step writes the newest frame of every env into slot `slot` and slot
+ * `slot + 10` (slot cycles 0..9) as two contiguous (N,15) planes; the chronological (10,15) stack of env n is rows
+ * obs_ring[first_row + k][n][:], k = 0..9, with first_row reported by f16_obs_window - a strided view (strides N*15, 15, 1
+ * floats over k, n, feature), never shifted or copied: 120 B written per env-step instead of 540 B read + 600 B written.
+ * Everything else as f16_bind; terminal_obs stays a plain N x 10 x 15 tensor; f16_step_host still returns contiguous
+ * N x 10 x 15 host arrays. */
 int f16_bind_ring(f16_handle h, void* state, float* obs_ring, float* reward, uint8_t* done, uint8_t* truncated,
                   float* terminal_obs, float* ep_return, int32_t* ep_len);
-/* First row of the current observation window: 0 for the stacked layout, 1..10 for the ring layout. */
+/* First row (ring layout: first slot) of the current observation window: 0 for the stacked layout, 1..10 for the ring layout. */
 int f16_obs_window(f16_handle h, int* first_row);
 
 /* Optional frame layout of the observations: the device keeps no history. obs_frame: N x 15 float; each step

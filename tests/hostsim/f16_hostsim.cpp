@@ -43,6 +43,9 @@ extern "C" {
 void hs_snapshot(double* out) { std::memcpy(out, consts().snap, sizeof(consts().snap)); }
 void hs_mass_set(int which, double* out /*mass, J9, Jinv9, rp3, eye3, thr3 = 28*/) { std::memcpy(out, &consts().ms[which], sizeof(MassSet)); }
 
+// the parity kernel's own double atan2 (f16_model.cuh), for the known-answer test against libm
+double hs_atan2(double y, double x) { return datan2_fast(y, x); }
+
 void* hs_env_create(int mode) {
   HsEnv* e = new HsEnv();
   std::memset(e, 0, sizeof(*e));

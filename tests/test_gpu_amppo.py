@@ -135,8 +135,10 @@ def test_time_limit_bootstrap_is_deferred_without_changing_rewards():
         results.append((algo.buffer.rewards.clone(), algo.buffer.returns.clone(), getattr(algo, "_hits", None)))
         env.close()
     assert results[1][2] == 12
-    assert torch.allclose(results[0][0], results[1][0], rtol=0, atol=1e-6), float((results[0][0] - results[1][0]).abs().max())
-    assert float((results[0][0] - results[1][0]).abs().max()) < 1e-6 and float(results[0][0].abs().max()) > 0.5
+    # the value head sees the same terminal observations in batches of different shape (one per step against one per
+    # rollout): float32 GEMM rounding, a few ulp of rewards of magnitude ~10
+    assert torch.allclose(results[0][0], results[1][0], rtol=0, atol=5e-6), float((results[0][0] - results[1][0]).abs().max())
+    assert float((results[0][0] - results[1][0]).abs().max()) < 5e-6 and float(results[0][0].abs().max()) > 0.5
     assert torch.allclose(results[0][1], results[1][1], rtol=0, atol=1e-5)
 
 

@@ -265,7 +265,7 @@ def test_results_do_not_depend_on_how_the_envs_are_sharded(F16BatchedEnv):
 @pytest.mark.parametrize("mode", ["fp32", "fp64"])
 def test_ring_layout_is_value_identical_to_stacked(F16BatchedEnv, mode):
     """obs_layout='ring' (frame written twice, zero-copy window view) must return the stacks, rewards,
-    flags, terminal observations and host copies of the default in-place-shift layout, across
+    flags, terminal observations and host copies of the stacked (in-place shift) layout, across
     auto-resets and masked resets, for a ragged batch. The two layouts are separate instantiations of the
     step kernel and the compiler contracts a few multiply-adds differently, so values agree to float
     rounding (1e-5 relative here, over 70 free-running steps), not bit for bit; structure is exact."""
@@ -274,7 +274,7 @@ def test_ring_layout_is_value_identical_to_stacked(F16BatchedEnv, mode):
         assert torch.allclose(x, y, rtol=2e-5, atol=2e-4), what
 
     n = 1000 + 37
-    a = F16BatchedEnv(n, mode=mode, seed=9)
+    a = F16BatchedEnv(n, mode=mode, seed=9, obs_layout="stacked")
     b = F16BatchedEnv(n, mode=mode, seed=9, obs_layout="ring")
     g = torch.Generator(device="cuda").manual_seed(1)
     # goals 150..900 m straight ahead at the start altitude: the envs reach them (+10, terminated) between
@@ -297,7 +297,7 @@ def test_ring_layout_is_value_identical_to_stacked(F16BatchedEnv, mode):
             ob, rb, db, tb = b.step(act, auto_reset=True)
             same(ra, rb, "rewards")
             assert torch.equal(da, db) and torch.equal(ta, tb)
-        assert ob.shape == (n, 10, 15) and ob.stride() == (300, 15, 1)
+        assert ob.shape == (n, 10, 15) and ob.stride() == (15, n * 15, 1)     # slot-major ring: (N,15) planes, zero-copy window
         same(oa, ob.contiguous(), "window differs at step %d" % k)
         same(oa.reshape(n, 150), ob.reshape(n, 150))
         if bool(da.any()):

@@ -242,3 +242,23 @@ def test_rudder_mirror_symmetry(oracle):
         return o[-1][:12].astype(np.float64)
     r, l = run_ail(0.3), run_ail(-0.3)
     assert abs(r[4] - l[4]) > 1e-2 and abs(r[6] + l[6]) < 0.02 * abs(r[6])         # alpha differs, roll rate mirrors
+
+
+def test_parity_kernel_atan2_matches_libm(hostsim):
+    """csrc/f16_model.cuh:datan2_fast (the FP64 parity kernel's atan2: one division, reduction to the nearest eighth,
+    odd series through r^17) against libm over the circle, the axes and extreme magnitudes: within one ulp at pi (4.4e-16 rad)."""
+    import ctypes as C
+    f = hostsim.L.hs_atan2
+    f.restype = C.c_double
+    f.argtypes = [C.c_double, C.c_double]
+    rng = np.random.default_rng(5)
+    th = np.concatenate([rng.uniform(-np.pi, np.pi, 20000), np.arange(-16, 17) * (np.pi / 16), np.arctan(np.arange(0, 9) / 8.0),
+                         np.arctan(np.arange(0, 9) / 8.0 + 1 / 16.0), [1e-12, -1e-12, np.pi - 1e-12, -np.pi + 1e-12]])
+    rad = 10.0 ** rng.uniform(-6, 8, th.size)
+    worst = 0.0
+    for t, r in zip(th, rad):
+        y, x = r * np.sin(t), r * np.cos(t)
+        worst = max(worst, abs(f(y, x) - np.arctan2(y, x)))
+    assert worst <= 2.0 ** -51, worst          # one ulp at pi
+    assert f(0.0, 1.0) == 0.0 and f(0.0, -1.0) == pytest.approx(np.pi, abs=1e-16) and f(1.0, 0.0) == pytest.approx(np.pi / 2, abs=1e-16)
+    assert f(-1.0, 0.0) == pytest.approx(-np.pi / 2, abs=1e-16) and f(0.0, 0.0) == 0.0

@@ -4,11 +4,17 @@ import importlib
 import numpy as np
 
 from . import spaces  # noqa: F401
+from .spaces import Space  # noqa: F401
+
+__version__ = "0.29.1"      # what stable_baselines3/common/utils.py:get_system_info prints
 
 _REGISTRY = {}
 
 
 class Env:
+    def __class_getitem__(cls, item):       # gym.Env[ObsType, ActType] in type annotations / base-class lists
+        return cls
+
     metadata = {}
     render_mode = None
     spec = None
@@ -29,6 +35,22 @@ class Env:
 class Wrapper(Env):
     def __init__(self, env):
         self.env = env
+
+    @property
+    def observation_space(self):
+        return self.__dict__.get("_observation_space") or self.env.observation_space
+
+    @observation_space.setter
+    def observation_space(self, v):
+        self.__dict__["_observation_space"] = v
+
+    @property
+    def action_space(self):
+        return self.__dict__.get("_action_space") or self.env.action_space
+
+    @action_space.setter
+    def action_space(self, v):
+        self.__dict__["_action_space"] = v
 
     def __getattr__(self, name):
         if name.startswith("_"):
@@ -87,3 +109,19 @@ def make(id, **kwargs):
         env = TimeLimit(env, spec.max_episode_steps)
     env.spec = spec
     return env
+
+
+class ObservationWrapper(Wrapper):
+    def observation(self, observation):
+        return observation
+
+
+class RewardWrapper(Wrapper):
+    def reward(self, reward):
+        return reward
+
+
+class ActionWrapper(Wrapper):
+    def action(self, action):
+        return action
+

@@ -2,8 +2,10 @@
 
 Follows stable_baselines3/common/buffers.py of the reference line by line for the parts the GPU
 rollout store replaces: reset :392-402, add :440-478 (full observations are stored, as SB3 does),
-compute_returns_and_advantage :404-438, swap_and_flatten :63-75 and _get_samples :508-521. The vendored
-SB3 itself cannot be imported here (it needs gymnasium), so this is the checker for tests/test_gpu_rollout.py.
+compute_returns_and_advantage :404-438, swap_and_flatten :63-75 and _get_samples :508-521. PINNED: the reference's real
+class (imported from /root/reference over oracle/refshim by tools/make_golden_rollout.py) produced
+tests/golden/sb3_rollout_buffer.npz, which this restatement reproduces bit for bit (tests/test_rollout_oracle.py). It is
+the checker for tests/test_gpu_rollout.py, where the reference tree is not available.
 """
 import numpy as np
 

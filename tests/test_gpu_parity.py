@@ -351,7 +351,11 @@ def test_ground_contact_step_parity(F16BatchedEnv, oracle, state_fields, mode, t
         got = env.pack_states().cpu().numpy()
         e = rel_err(got, np.stack(s1), floors[None, :])
         if mode == "fp32":
-            e[2 * [c[0] for c in CASES].index("at_rest_static_friction"), state_fields.index("VC_KTS")] = 0.0   # see test_ground_contact
+            # stated tolerance of the float mode for a STANDING aircraft: calibrated airspeed within 0.5 kt absolute
+            # (float32 cannot resolve pow(1 + 1e-7, 1/3.5) - 1; the value only feeds FCS thresholds at 5 kt and above)
+            i_case, i_vc = 2 * [c[0] for c in CASES].index("at_rest_static_friction"), state_fields.index("VC_KTS")
+            assert abs(got[i_case, i_vc] - np.stack(s1)[i_case, i_vc]) <= 0.5
+            e[i_case, i_vc] = min(e[i_case, i_vc], tol / 2)
         worst = np.unravel_index(int(e.argmax()), e.shape)
         assert e.max() < tol, (layout, int(worst[0]), state_fields[int(worst[1])], float(e.max()))
         if mode == "fp64" and layout == "stacked":
@@ -405,8 +409,7 @@ def test_envelope_step_parity(F16BatchedEnv, oracle, state_fields, mode, tol):
     _set_all_steps(env, np.full(n, 7, dtype=np.int32))
     obs, rew, done, trunc = env.step(torch.from_numpy(acts).cuda(), auto_reset=False)
     e = rel_err(env.pack_states().cpu().numpy(), want, floors[None, :])
-    if mode == "fp32":
-        e[want[:, state_fields.index("MACH")] > 0.98, state_fields.index("VC_KTS")] = 0.0   # see test_envelope_parity
+    # (the supersonic calibrated airspeed is inside the common tolerance in both modes: csrc/f16_model.cuh, FGAuxiliary block)
     worst = np.unravel_index(int(e.argmax()), e.shape)
     assert e.max() < tol, (int(worst[0]), state_fields[int(worst[1])], float(e.max()))
     if mode == "fp64":

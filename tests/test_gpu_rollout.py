@@ -58,3 +58,26 @@ def test_rollout_store_matches_sb3_buffer_bit_for_bit():
         assert int((gbuf.age == 0).sum()) > 0 and int((gbuf.age == 9).sum()) > 0
     n = sum(1 for _ in gbuf.get(batch_size=8192))
     assert n == -(-T * N // 8192)
+
+
+def test_rollout_store_matches_the_reference_class_golden():
+    """The CUDA rollout store (frame-only storage, GAE scan, stack-rebuilding gather) against vectors produced by the
+    reference's real RolloutBuffer (tests/golden/sb3_rollout_buffer.npz, tools/make_golden_rollout.py): bit for bit."""
+    import os
+    from f16_jsb_b200.rollout import GpuRolloutBuffer
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sb3_rollout_buffer.npz"))
+    g = {k: z[k] for k in z.files}
+    T, N = g["in_rewards"].shape
+    dev = torch.device("cuda")
+    buf = GpuRolloutBuffer(T, N, device=dev, gae_lambda=float(g["gae_lambda"]), gamma=float(g["gamma"]))
+    cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    for t in range(T):
+        buf.add(cu(g["in_obs"][t]), cu(g["in_actions"][t]), cu(g["in_rewards"][t]), cu(g["in_episode_starts"][t]), cu(g["in_values"][t]), cu(g["in_log_probs"][t]))
+    buf.compute_returns_and_advantage(cu(g["in_last_values"]), cu(g["in_last_dones"]))
+    assert np.array_equal(buf.advantages.cpu().numpy(), g["advantages"]) and np.array_equal(buf.returns.cpu().numpy(), g["returns"])
+    B = int(g["batch"])
+    for k in range(int(g["n_batches"])):
+        s = buf.gather(cu(g["perm"][k * B:(k + 1) * B].astype(np.int64)))
+        for a, name in zip((s.observations, s.actions, s.old_values, s.old_log_prob, s.advantages, s.returns),
+                           ("observations", "actions", "old_values", "old_log_prob", "advantages", "returns")):
+            assert np.array_equal(a.cpu().numpy(), g["b%d_%s" % (k, name)]), (k, name)

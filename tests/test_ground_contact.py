@@ -150,9 +150,12 @@ def test_synthetic_contact_step_parity(oracle, hostsim, state_fields, case, mode
     hs.step(act)
     e = rel_err(hs.get_state(NF), s1, floors)
     if mode == 1 and name == "at_rest_static_friction":
-        # float32 cannot form the calibrated airspeed of a standing aircraft (pow(1 + 1e-7, 1/3.5) - 1); it only
-        # feeds FCS thresholds between 5 and 250 kt, and no state of the reference's flights is slower than 100 kt
-        e[state_fields.index("VC_KTS")] = 0.0
+        # stated tolerance of the float mode for a STANDING aircraft: calibrated airspeed within 0.5 kt absolute. float32
+        # cannot form pow(1 + 1e-7, 1/3.5) - 1; the value only feeds FCS thresholds at 5 kt and above, and no state of the
+        # reference's flights is slower than 100 kt
+        i_vc = state_fields.index("VC_KTS")
+        assert abs(hs.get_state(NF)[i_vc] - s1[i_vc]) <= 0.5
+        e[i_vc] = min(e[i_vc], tol / 2)
     assert e.max() < tol, (name, state_fields[int(e.argmax())], float(e.max()))
     # the contact must have mattered: without it the accelerations are completely different
     assert np.abs(s1[state_fields.index("WDOT_X"):state_fields.index("WDOT_X") + 3]).max() > 1e-3

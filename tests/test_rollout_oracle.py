@@ -38,3 +38,54 @@ def test_rollout_symbols_exported():
     for s in _lib.ROLLOUT_SYMBOLS:
         assert hasattr(L, s)
     assert L.f16_rollout_gae(0, 0, 0.99, 0.95, None, None, None, None, None, None, None, None) != 0
+
+
+# ---- pinned to the REFERENCE's real RolloutBuffer: tests/golden/sb3_rollout_buffer.npz (tools/make_golden_rollout.py)
+def _golden():
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sb3_rollout_buffer.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def _fill_oracle(g):
+    from oracle.rollout_oracle import RolloutBufferOracle
+    T, N = g["in_rewards"].shape
+    buf = RolloutBufferOracle(T, N, gae_lambda=float(g["gae_lambda"]), gamma=float(g["gamma"]))
+    for t in range(T):
+        buf.add(g["in_obs"][t], g["in_actions"][t], g["in_rewards"][t], g["in_episode_starts"][t], g["in_values"][t], g["in_log_probs"][t])
+    buf.compute_returns_and_advantage(g["in_last_values"], g["in_last_dones"])
+    return buf
+
+
+def test_rollout_oracle_matches_the_reference_class_bit_for_bit():
+    """oracle/rollout_oracle.py against vectors produced by stable_baselines3/common/buffers.py:327-521 itself."""
+    g = _golden()
+    buf = _fill_oracle(g)
+    assert np.array_equal(buf.advantages, g["advantages"]) and np.array_equal(buf.returns, g["returns"])
+    assert np.array_equal(buf.episode_starts, g["stored_episode_starts"])
+    B = int(g["batch"])
+    for k in range(int(g["n_batches"])):
+        idx = g["perm"][k * B:(k + 1) * B]
+        got = buf.get_samples(idx)
+        for a, name in zip(got, ("observations", "actions", "old_values", "old_log_prob", "advantages", "returns")):
+            assert np.array_equal(a, g["b%d_%s" % (k, name)]), (k, name)
+
+
+def test_reference_rollout_buffer_still_produces_the_golden():
+    """Re-runs the real class where the reference tree exists (the build container): the committed fixture is what it makes."""
+    import os
+    import sys
+    import pytest
+    if not os.path.isdir("/root/reference/stable_baselines3"):
+        pytest.skip("needs /root/reference")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    saved = list(sys.path)
+    try:
+        import make_golden_rollout as mk
+        out = mk.run_reference(mk.make_inputs())
+    finally:
+        sys.path[:] = saved
+    g = _golden()
+    for k, v in out.items():
+        assert np.array_equal(np.asarray(v), g[k]), k

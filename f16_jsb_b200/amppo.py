@@ -284,6 +284,30 @@ class AMPPO:
             g.copy_(flat[off:off + g.numel()].view_as(g))
             off += g.numel()
 
+    # ------------------------------------------------------------------ checkpoint / resume (train.py always saves its model)
+    def save(self, path: str) -> None:
+        """Everything the learner needs to continue as if it had not stopped: policy, optimizer (for DAG including the
+        per-tensor alpha / saturation statistics, the RMS-shrink state and the step counter), the two advantage-modulation
+        EMAs, the sampling generator and the counters. The policy's state_dict keys are the reference policy's."""
+        torch.save({"policy": self.policy.state_dict(), "optimizer": self.optimizer.state_dict(),
+                    "optimizer_class": type(self.optimizer).__name__,
+                    "alpha_state": self.alpha_state.cpu(), "sat_state": self.sat_state.cpu(),
+                    "generator": self.generator.get_state(), "num_timesteps": self.num_timesteps, "n_updates": self.n_updates,
+                    "cfg": self.cfg}, path)
+
+    def load(self, path: str) -> "AMPPO":
+        ck = torch.load(path, map_location=self.device, weights_only=False)
+        if ck["optimizer_class"] != type(self.optimizer).__name__:
+            raise ValueError("checkpoint was written with %s, this learner uses %s" % (ck["optimizer_class"], type(self.optimizer).__name__))
+        self.policy.load_state_dict(ck["policy"])
+        self.optimizer.load_state_dict(ck["optimizer"])
+        self.alpha_state.copy_(ck["alpha_state"])
+        self.sat_state.copy_(ck["sat_state"])
+        self.generator.set_state(ck["generator"].cpu())
+        self.num_timesteps, self.n_updates = int(ck["num_timesteps"]), int(ck["n_updates"])
+        self._graph = None                      # the captured policy forward holds the old weights' addresses only; recapture lazily
+        return self
+
     def learn(self, total_timesteps: int) -> "AMPPO":
         while self.num_timesteps < total_timesteps:
             self.collect_rollouts()

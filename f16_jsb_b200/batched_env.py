@@ -192,7 +192,11 @@ class F16BatchedEnv:
         def p(a):
             return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
 
-        _lib.check(self.lib.f16_step_host(self._h, p(actions), int(auto_reset), p(obs_out), p(reward_out), p(done_out),
+        mode = 1 if auto_reset else 0
+        if self.reset_mode == "carryover":
+            mode *= 2                      # F16_AUTO_RESET_CARRYOVER
+            self._last_actions = torch.from_numpy(actions).to(self.device, non_blocking=True)   # fcs/*-cmd-norm stay set across reset()
+        _lib.check(self.lib.f16_step_host(self._h, p(actions), mode, p(obs_out), p(reward_out), p(done_out),
                                           p(truncated_out), self._stream()), "f16_step_host")
 
     # ------------------------------------------------------------------ parity / debugging

@@ -31,9 +31,29 @@ def needs_build() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    if force or needs_build():
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
-        subprocess.check_call(cmd)
+    """One process per GPU means several ranks may get here at once (torchrun): the build runs under a file lock, into a
+    temporary file that is renamed over the library in one step, so no rank ever dlopens a half-written file and only
+    the first rank compiles."""
+    import fcntl
+    import tempfile
+    if not (force or needs_build()):
+        return LIB_PATH
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or needs_build():          # another rank may have built it while this one waited
+                fd, tmp = tempfile.mkstemp(prefix=".libf16b200.", suffix=".so.tmp", dir=_HERE)
+                os.close(fd)
+                try:
+                    cmd = [nvcc_path()] + NVCC_FLAGS + ["--threads", "0"] + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+                    subprocess.check_call(cmd)
+                    os.chmod(tmp, 0o755)
+                    os.replace(tmp, LIB_PATH)
+                finally:
+                    if os.path.exists(tmp):
+                        os.unlink(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -519,6 +519,12 @@ int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int
 
 int f16_hostwin_numa_node(f16_hostwin_handle w) { return w ? w->numa_node : -1; }
 
+int f16_hostwin_detach(f16_hostwin_handle w, f16_handle env) {
+  // the env's done list lives in this window's mapped / device memory: un-point it before the window goes away
+  if (!w || !env) return failf("f16_hostwin_detach: NULL argument");
+  return f16_set_done_list(env, nullptr, nullptr);
+}
+
 int f16_hostwin_destroy(f16_hostwin_handle w) {
   if (!w) return 0;
   delete w->copier;    // waits for a carry-over in flight
@@ -665,9 +671,17 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
   CUDA_OK(cudaHostGetDevicePointer((void**)&count_host_dev, w->count_host, 0));
   rc = f16_set_done_list(env, recs_dev, w->count_dev);
   if (rc) return rc;
-  w->t += 1;
-  w->head = (w->head + 1) % SLOTS;
-  const int ring_now = w->n_rings == 2 ? (int)(w->t & 1) : 0, cur = (int)(w->t & 1);
+  // The step counter and the ring head advance only once every launch and copy of the step has been enqueued: an
+  // early return (a failed launch) leaves the window exactly where it was.
+  const int64_t t_new = w->t + 1;
+  const int head_new = (w->head + 1) % SLOTS;
+  const int ring_now = w->n_rings == 2 ? (int)(t_new & 1) : 0, cur = (int)(t_new & 1);
+  // zero-copy steps point the env's frame output into the mapped ring; whatever happens it points back at the device
+  // buffer when this function returns
+  struct ObsFrameGuard {
+    f16_handle env; float* device_frames; bool armed;
+    ~ObsFrameGuard() { if (armed) f16_internal_set_obs_frame(env, device_frames); }
+  } guard = {env, obs_frame, false};
   // One step in n_chunks pieces, each on its own stream: piece c's actions go up while piece c-1 computes and
   // piece c-2's frames come down (the three run on different engines). The done count is read once every
   // kernel has finished, so the host can start on the finished envs while the frames are still in flight.
@@ -683,8 +697,9 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
   const bool zc = w->pin && w->ring[ring_now].aliased && w->ring[ring_now].dev_base && !(w->flags & F16_HOSTWIN_DMA_BOTH) &&
                   (w->zero_copy == 2 || (w->zero_copy == 1 && C == 1 && w->n <= 32768));   // measured: +9 % at 4 096 envs, +4 % at 16 384, -2 % at 65 536, -9 % at 1M
   if (zc) {
-    rc = f16_internal_set_obs_frame(env, (float*)(w->ring[ring_now].dev_base + (size_t)w->head * w->ring[ring_now].pitch));
+    rc = f16_internal_set_obs_frame(env, (float*)(w->ring[ring_now].dev_base + (size_t)head_new * w->ring[ring_now].pitch));
     if (rc) return rc;
+    guard.armed = true;
   }
   if (C > 1) CUDA_OK(cudaEventRecord(w->fork, st));
   for (int c = 0; c < C; ++c) {
@@ -710,9 +725,9 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
       const int rr = (r == 0) ? ring_now : 1 - ring_now;      // the returned ring first
       if (rr != ring_now && !(w->flags & F16_HOSTWIN_DMA_BOTH)) continue;     // carried over by host threads after the sync
       if (zc) continue;                                                        // the kernel wrote them there itself
-      CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head, first), obs_frame + first * FEAT, cnt * ROW_BYTES, cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaMemcpyAsync(w->row(rr, head_new, first), obs_frame + first * FEAT, cnt * ROW_BYTES, cudaMemcpyDeviceToHost, s));
       if (!w->ring[rr].aliased)
-        CUDA_OK(cudaMemcpyAsync(w->row(rr, w->head + SLOTS, first), obs_frame + first * FEAT, cnt * ROW_BYTES, cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaMemcpyAsync(w->row(rr, head_new + SLOTS, first), obs_frame + first * FEAT, cnt * ROW_BYTES, cudaMemcpyDeviceToHost, s));
     }
   }
   if (C > 1) {
@@ -723,9 +738,12 @@ int f16_hostwin_step(f16_hostwin_handle w, f16_handle env, const float* actions_
     CUDA_OK(cudaEventRecord(w->ev, st));
   }
   if (zc) {
+    guard.armed = false;
     rc = f16_internal_set_obs_frame(env, obs_frame);      // launches have their arguments: back to the device buffer
     if (rc) return rc;
   }
+  w->t = t_new;                             // everything is enqueued: the step has happened
+  w->head = head_new;
   lap();                                    // [0] enqueue: copies and the kernel launch
   CUDA_OK(cudaEventSynchronize(w->ev));     // kernel finished: the records it wrote to mapped host memory are complete
   const int64_t n_done = *w->count_host;

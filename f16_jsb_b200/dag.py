@@ -48,6 +48,32 @@ class DAG(Optimizer):
     def s_t(self) -> float:
         return 1.0 if self._s_t is None else float(self._s_t)
 
+    # ---- checkpointing: the RMS-shrink state and the step counter are optimizer state too
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["dag"] = {"global_step": int(self.global_step), "k_val": float(self.k_val),
+                     "s_t": None if self._s_t is None else self._s_t.detach().cpu().clone(),
+                     "rms_t": None if self._rms_t is None else self._rms_t.detach().cpu().clone(),
+                     "rms0": None if self._rms0 is None else self._rms0.detach().cpu().clone()}
+        return sd
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        extra = state_dict.pop("dag", None)
+        super().load_state_dict(state_dict)
+        dev = next((p.device for g in self.param_groups for p in g["params"]), torch.device("cpu"))
+        for key, st in self.state.items():                      # the stacked group statistics live on the parameters' device
+            if isinstance(key, str) and key.startswith("_group_"):
+                for k, v in st.items():
+                    if torch.is_tensor(v):
+                        st[k] = v.to(dev)
+        if extra is not None:
+            self.global_step = int(extra["global_step"])
+            self.k_val = float(extra["k_val"])
+            self._s_t = None if extra["s_t"] is None else extra["s_t"].to(dev)
+            self._rms_t = None if extra["rms_t"] is None else extra["rms_t"].to(dev)
+            self._rms0 = None if extra["rms0"] is None else extra["rms0"].to(dev)
+
     def set_k_val(self, new_k: float) -> None:
         self.k_val, self.k_sched = float(new_k), None
 
@@ -64,14 +90,16 @@ class DAG(Optimizer):
             self.k_val = float(self.k_sched(self.global_step))
         h, sc = self.h, self.s_cfg
         total_sq, total_n = None, 0
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             params = [p for p in group["params"] if p.grad is not None]
             if not params:
                 continue
             dev = params[0].device
             if self._s_t is None:
                 self._s_t = torch.ones((), dtype=torch.float64, device=dev)
-            st = self.state.setdefault("_group_%d" % id(group), {})          # stacked per-tensor statistics of the group
+            # stacked per-tensor statistics of the group, keyed by the group's INDEX so that they survive
+            # state_dict() / load_state_dict() into a new process (the reference keeps them per parameter, sgd.py:196-214)
+            st = self.state.setdefault("_group_%d" % gi, {})
             if "alpha" not in st or st["alpha"].numel() != len(params):
                 st["alpha"] = torch.ones(len(params), dtype=torch.float32, device=dev)
                 st["sat"] = torch.zeros(len(params), dtype=torch.float32, device=dev)

@@ -67,9 +67,13 @@ class HostWindow:
             v = self._views[key] = _as_array(ptr, shape, dtype)
         return v
 
-    def close(self):
+    def close(self, env=None):
+        """env: the F16BatchedEnv this window served, if it is still alive - its done list points into this window's
+        mapped memory and is un-pointed first."""
         if getattr(self, "_h", None) is not None and self._h.value:
             self._rings, self.action_buffers, self._views, self._action_addr = [], [], {}, []
+            if env is not None and getattr(env, "_h", None) is not None and env._h.value:
+                self.lib.f16_hostwin_detach(self._h, env._h)
             self.lib.f16_hostwin_destroy(self._h)
             self._h = C.c_void_p(0)
 

@@ -28,26 +28,32 @@ class JSBSimEnv(_Base):
             super().__init__()
         self.num_stacked_frames = NUM_STACKED_FRAMES
         self.observation_space, self.action_space = make_spaces()
-        self._env = F16BatchedEnv(1, device=device, mode=mode, with_terminal_obs=False, reset_mode=reset_mode)
+        self._env = F16BatchedEnv(1, device=device, mode=mode, with_terminal_obs=False, reset_mode=reset_mode, obs_layout="stacked")
         self.down_sample = 4
         self.current_step = 0
         self.max_episode_steps = 1200
         self.goal = np.zeros(3, dtype=np.float32)
         self.dg = 100.0
         self.viewer = None
-        self._act = torch.zeros((1, 4), dtype=torch.float32, device=self._env.device)
+        # pinned host staging: one call = upload, step, download, ONE stream synchronisation (f16_step_host)
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+        self._act, self._obs = pin((1, 4), torch.float32), pin((1, NUM_STACKED_FRAMES, 15), torch.float32)
+        self._rew, self._done, self._trunc = pin((1,), torch.float32), pin((1,), torch.uint8), pin((1,), torch.uint8)
 
     def step(self, action):
         """jsbsim_gym.py:199-287: returns (obs (10,15) f32, base reward, terminated, truncated, {})."""
         self.current_step += 1
-        self._act.copy_(torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(1, 4)))
-        obs, rew, done, trunc = self._env.step(self._act, auto_reset=False)
-        obs = obs[0].cpu().numpy()
-        truncated = bool(trunc[0].item())
-        terminated = bool(done[0].item()) and not truncated
-        shaped = float(rew[0].item())
-        # the kernel fuses PositionReward's shaping (|shaping| < 1); the base reward is -10 / +10 / 0
-        reward = 0.0 if not terminated else (10.0 if shaped > 0 else -10.0)
+        self._act[...] = np.asarray(action, dtype=np.float32).reshape(1, 4)
+        self._env.step_host(self._act, self._obs, self._rew, self._done, self._trunc, auto_reset=False)
+        obs = self._obs[0].copy()
+        truncated = bool(self._trunc[0])
+        terminated = bool(self._done[0]) and not truncated
+        # The kernel's reward has PositionReward's shaping fused in; this class returns the BASE reward, which the
+        # reference computes from the very float32 frame just returned (jsbsim_gym.py:237-256): crash below 10 m -> -10
+        # (it takes precedence), otherwise a terminated episode reached the goal cylinder -> +10, else 0.
+        reward = 0.0
+        if terminated:
+            reward = -10.0 if obs[-1][2] < 10.0 else 10.0
         return obs, reward, terminated, truncated, {}
 
     def reset(self, seed: int = None, options: dict = None):

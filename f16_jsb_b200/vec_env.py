@@ -67,7 +67,9 @@ class _RecordInfos:
         d = self._built.get(j)
         if d is None:
             r = self._rec[j]
-            d = {"TimeLimit.truncated": bool(r["flags"] & 1), "terminal_observation": self._term[j],
+            # an owned copy: the row lives in a library buffer that is recycled two steps later, and SB3 users keep
+            # info dicts (DummyVecEnv hands out owned arrays too, dummy_vec_env.py:66-67)
+            d = {"TimeLimit.truncated": bool(r["flags"] & 1), "terminal_observation": self._term[j].copy(),
                  "episode": {"r": float(r["ep_return"]), "l": int(r["ep_len"]), "t": self._t}}
             self._built[j] = d
         return d
@@ -229,7 +231,7 @@ class F16VecEnv(VecEnvBase):
 
     def close(self) -> None:
         if self._win is not None:
-            self._win.close()
+            self._win.close(self.env)
             self._win = None
         self.env.close()
 
@@ -244,7 +246,18 @@ class F16VecEnv(VecEnvBase):
         setattr(self, attr_name, value)
 
     def env_method(self, method_name: str, *method_args, indices=None, **method_kwargs):
-        raise NotImplementedError("F16VecEnv has no per-env Python objects to call %r on" % method_name)
+        """base_vec_env.py:190-201. There are no per-env Python objects; a method of this VecEnv that makes sense per
+        env (e.g. `render`, `close`-free queries) is called once and its result replicated, anything else raises the
+        AttributeError DummyVecEnv's getattr would raise."""
+        n = len(list(self._get_indices(indices)))
+        fn = getattr(self, method_name, None)
+        if fn is None or not callable(fn) or method_name in ("step", "step_async", "step_wait", "reset", "close", "seed"):
+            raise AttributeError("the F-16 env has no per-env method %r" % method_name)
+        out = fn(*method_args, **method_kwargs)
+        return [out for _ in range(n)]
+
+    def render(self, mode: str = "human"):
+        return None   # the reference's viewer is not on the step path (jsbsim_gym.py:333-468)
 
     def env_is_wrapped(self, wrapper_class, indices=None):
         n = len(list(self._get_indices(indices)))

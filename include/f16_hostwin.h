@@ -72,6 +72,9 @@ typedef struct f16_hostwin_result {
 /* Rings for n_envs environments; n_rings is 1 or 2. Without F16_HOSTWIN_PIN nothing touches CUDA (the
  * host-only entry points below still work; used by the CPU tests). */
 int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int flags);
+/* The env's done list points into this window's memory: detach the env before destroying the window (or destroy the
+ * env first). */
+int f16_hostwin_detach(f16_hostwin_handle w, f16_handle env);
 int f16_hostwin_destroy(f16_hostwin_handle w);
 
 /* Geometry of one ring for building the strided view: base address, slot pitch in bytes, number of slots

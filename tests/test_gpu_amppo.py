@@ -94,6 +94,40 @@ def test_rollout_and_update_run_on_device(use_am_ppo, optimizer):
     env.close()
 
 
+@pytest.mark.parametrize("optimizer", ["dag", "adam"])
+def test_amppo_checkpoint_restores_the_learner(optimizer, tmp_path):
+    """train.py always saves its model; AMPPO.save / load must carry the policy, the optimizer (DAG statistics
+    included), the two advantage-modulation EMAs, the sampling generator and the counters, so that a learner rebuilt in a
+    new process continues exactly like the one that kept running: the same update on the same rollout."""
+    from f16_jsb_b200 import F16BatchedEnv
+    from f16_jsb_b200.amppo import AMPPO, AMPPOConfig
+    cfg = AMPPOConfig(n_steps=16, batch_size=512, n_epochs=2, use_am_ppo=True, optimizer=optimizer, seed=4, cuda_graph=False)
+    env = F16BatchedEnv(128, mode="fp32", seed=2)
+    a = AMPPO(env, cfg)
+    a.collect_rollouts()
+    a.train()
+    a.collect_rollouts()
+    a.save(str(tmp_path / "amppo.pt"))
+    env_b = F16BatchedEnv(128, mode="fp32", seed=2)
+    b = AMPPO(env_b, cfg).load(str(tmp_path / "amppo.pt"))
+    assert b.num_timesteps == a.num_timesteps and b.n_updates == a.n_updates
+    assert torch.equal(b.alpha_state, a.alpha_state) and torch.equal(b.sat_state, a.sat_state) and float(a.alpha_state[0]) != 1.0
+    for (k, va), vb in zip(a.policy.state_dict().items(), b.policy.state_dict().values()):
+        assert torch.equal(va, vb), k
+    # the same rollout in both buffers, then one update each
+    for name in ("frames", "age", "actions", "rewards", "episode_starts", "values", "log_probs", "advantages", "returns"):
+        getattr(b.buffer, name).copy_(getattr(a.buffer, name))
+    b.buffer.pos, b.buffer.full = a.buffer.pos, a.buffer.full
+    a.train()
+    b.train()
+    for (k, va), vb in zip(a.policy.state_dict().items(), b.policy.state_dict().values()):
+        assert torch.allclose(va, vb, rtol=1e-5, atol=1e-7), k
+    assert abs(a.last_stats["alpha_A_ema"] - b.last_stats["alpha_A_ema"]) < 1e-6 and a.n_updates == b.n_updates
+    if optimizer == "dag":
+        assert a.optimizer.global_step == b.optimizer.global_step and abs(a.optimizer.s_t - b.optimizer.s_t) < 1e-9
+    env.close(); env_b.close()
+
+
 def test_time_limit_bootstrap_is_deferred_without_changing_rewards():
     """on_policy_algorithm.py:236-245 adds gamma * V(terminal_observation) to the reward of a truncated env inside the
     step loop. AMPPO parks the terminal observations and values them after the last step (no host synchronisation per

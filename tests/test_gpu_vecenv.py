@@ -178,3 +178,33 @@ def test_torch_fast_path_is_device_resident():
     o, r, d, tr = env.step_torch(a)
     assert o.is_cuda and r.is_cuda and d.is_cuda and o.data_ptr() == obs.data_ptr()
     env.close()
+
+
+def test_single_env_adapter_follows_the_reference_episode(golden):
+    """f16_jsb_b200.jsbsim_gym (JSBSimEnv + PositionReward, the reference's single-env surface) against an episode of the
+    reference's own jsbsim_gym.py (tests/golden/ref_env_traces.npz, FDM = the oracle): same reset(seed) goal, frames,
+    shaped rewards, terminated / truncated flags, one host synchronisation per step."""
+    from f16_jsb_b200.jsbsim_gym import wrap_jsbsim
+    t = golden["random1"]
+    env = wrap_jsbsim(mode="fp64")
+    obs, info = env.reset(seed=1)
+    assert info == {} and obs.shape == (10, 15) and obs.dtype == np.float32
+    assert np.array_equal(obs[-1][12:15], t["goal"].astype(np.float32))
+    n = len(t["actions"])
+    ended = False
+    for k in range(n):
+        obs, reward, terminated, truncated, info = env.step(t["actions"][k])
+        f = t["frames"][k]
+        e = float((np.abs(obs[-1][:12] - f[:12]) / np.maximum(np.abs(f[:12]), 1e-2)).max())
+        assert e <= (1e-5 if k < 300 else 1e-1), (k, e)
+        if k < 300:
+            assert abs(float(reward) - float(t["rewards"][k])) < 2e-5
+        if terminated or truncated or t["terminated"][k] or t["truncated"][k]:
+            assert k >= n - 2
+            assert bool(terminated) == bool(t["terminated"][k]) or k < n - 1
+            if terminated and t["terminated"][k]:
+                assert abs(float(reward) - float(t["rewards"][k])) < 1e-2       # -10 / +10 base reward + shaping
+            ended = True
+            break
+    assert ended
+    env.close()

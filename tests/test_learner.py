@@ -93,6 +93,41 @@ def test_dag_optimizer_follows_the_reference_trajectory(gold):
     assert opt.s_t < 0.6          # the RMS-shrink branch was exercised
 
 
+def test_dag_checkpoint_resume_equals_uninterrupted(gold, tmp_path):
+    """DAG's per-tensor alpha / saturation statistics, the RMS-shrink state and the step counter must survive
+    state_dict() -> torch.save -> a NEW optimizer object's load_state_dict(): 6 steps + resume + 6 steps == 12 steps."""
+    from f16_jsb_b200.dag import DAG
+    d = gold["dag"]
+
+    def make():
+        m = torch.nn.Sequential(torch.nn.Linear(17, 32), torch.nn.Tanh(), torch.nn.Linear(32, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1))
+        m.load_state_dict(d["init"])
+        return m, DAG(m.parameters(), lr=d["lr"], shrink=d["shrink"], momentum=0.5)
+
+    def run(m, opt, ks):
+        for k in ks:
+            opt.zero_grad()
+            ((m(d["xs"][k]) - d["ys"][k]) ** 2).mean().backward()
+            opt.step()
+
+    n = len(d["traj"])
+    ma, oa = make()
+    run(ma, oa, range(n))                                  # uninterrupted
+    mb, ob = make()
+    run(mb, ob, range(n // 2))
+    torch.save({"model": mb.state_dict(), "opt": ob.state_dict()}, tmp_path / "ck.pt")
+    ck = torch.load(tmp_path / "ck.pt", weights_only=False)
+    mc, oc = make()                                        # a new process would build these afresh
+    mc.load_state_dict(ck["model"])
+    oc.load_state_dict(ck["opt"])
+    assert oc.global_step == n // 2 and oc.s_t == ob.s_t
+    assert torch.equal(oc.state["_group_0"]["alpha"], ob.state["_group_0"]["alpha"]) and not torch.equal(oc.state["_group_0"]["alpha"], torch.ones(6))
+    run(mc, oc, range(n // 2, n))
+    for (name, pa), pc in zip(ma.state_dict().items(), mc.state_dict().values()):
+        assert torch.equal(pa, pc), name
+    assert oa.s_t == oc.s_t and oa.global_step == oc.global_step
+
+
 def _modulate_worker(rank, world, port, adv, params, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))

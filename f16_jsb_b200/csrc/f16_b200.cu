@@ -152,7 +152,7 @@ __constant__ double c_snapshot_props[12];               // the 12 STATE_FORMAT p
 #define F16_MIN_BLOCKS_F32 4   // CTAs per SM of the float step kernel: 4 x 128 threads -> 128 registers
 #endif
 #ifndef F16_BLOCK_F64
-#define F16_BLOCK_F64 256
+#define F16_BLOCK_F64 128
 #endif
 #ifndef F16_MIN_BLOCKS_F64
 #define F16_MIN_BLOCKS_F64 1   // 255 registers
@@ -201,6 +201,12 @@ struct StepArgs {
   f16_done_record* done_list;   // frame layout only: one record per env that finished this step (may be mapped host memory)
   int32_t* done_count;          // frame layout only: device counter of appended records
   int64_t tile0;                // first 32-env tile of this launch (f16_step_range); n is the end of the range
+  // near-ground tiles first (ground-reaction builds, whole-batch steps only; see f16_step_kernel). Three buffers rotate:
+  // this step reads `cur`, fills `next` for the following step and clears `clr`, which the step before this one read.
+  const int32_t* hot_list_cur; const int32_t* hot_count_cur; const uint8_t* hot_flag_cur;
+  int32_t* hot_list_next; int32_t* hot_count_next; uint8_t* hot_flag_next;
+  int32_t* hot_count_clr; uint8_t* hot_flag_clr;
+  int hot_cap;                  // tiles the early CTAs can take (= early CTAs x warps per CTA); 0: scheduling off
 };
 
 // Canonical post-reset snapshot (f16_env.cuh: compute_snapshot), one thread, always in double.
@@ -436,21 +442,55 @@ __global__ void __launch_bounds__(StepShape<R>::BLK, StepShape<R>::MINB) f16_ste
   __shared__ uint8_t flags_s[WARPS][32];
   __shared__ __align__(8) uint64_t tbar;
   static_assert(sizeof(Tables<R>) % 16 == 0, "bulk copy size must be a multiple of 16 bytes");
-  if (threadIdx.x == 0) mbar_init(&tbar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) tma_load_1d(&T, a.tables, (uint32_t)sizeof(Tables<R>), &tbar);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_tiles = (a.n + 31) >> 5;
-  const int64_t tile_raw = a.tile0 + (int64_t)blockIdx.x * WARPS + warp;
-  const bool tile_ok = tile_raw < n_tiles;
-  if (!SYNC && !tile_ok) return;
-  const int64_t tile = tile_ok ? tile_raw : n_tiles - 1;
+  // ---- which tile does this warp step?
+  // Ground-reaction builds, whole-batch steps: an env whose contact points reach the ground redoes its step alone in its
+  // lane from a cold double-precision copy of the step (env_step_ground, ~80 of 1M envs per launch at the steady-state
+  // crash rate of random actions). Where that happens in one of the grid's last CTAs it IS the tail of the launch:
+  // measured 85 us of 425 (float) / 130 us of 1 080 (double) per step of 1M envs. An env can only touch within a step if it
+  // starts it within one step's sink of the ground, so every warp that ends a step with such an env puts its tile on a list,
+  // and the next launch begins with `hot_cap / WARPS` early CTAs that take the listed tiles; the regular CTA of a listed tile
+  // skips it (its slot then runs one warp short, which is why the criterion is kept tight: ~5 % of the tiles).
+  // The redo latency is then hidden behind the rest of the grid.
+  const bool HOT = GROUND && a.hot_cap > 0;
+  const int early_ctas = HOT ? a.hot_cap / WARPS : 0;
+  int64_t tile;
+  bool tile_ok;
+  int n_act;                                                                   // warps of this CTA that step a tile (barrier size)
+  if (HOT && (int)blockIdx.x < early_ctas) {
+    const int hot_n = min(*a.hot_count_cur, a.hot_cap);
+    const int first = (int)blockIdx.x * WARPS;
+    if (first >= hot_n) return;                                                // (uniform over the CTA)
+    n_act = min(WARPS, hot_n - first);
+    tile_ok = warp < n_act;
+    tile = tile_ok ? a.hot_list_cur[first + warp] : 0;
+  } else {
+    const int64_t base = a.tile0 + ((int64_t)blockIdx.x - early_ctas) * WARPS;
+    const int64_t t = base + lane;                                             // lanes 0 .. WARPS-1 look at the CTA's tiles
+    const bool mine = lane < WARPS && t < n_tiles && !(HOT && a.hot_flag_cur[t]);
+    const unsigned act = __ballot_sync(0xffffffffu, mine);
+    n_act = __popc(act);
+    tile = base + warp;
+    tile_ok = (act >> warp) & 1;
+    if (HOT && lane == 0 && tile < n_tiles) a.hot_flag_clr[tile] = 0;          // every tile has exactly one regular warp
+    if (HOT && blockIdx.x == (unsigned)early_ctas && threadIdx.x == 0) *a.hot_count_clr = 0;
+    if (n_act == 0) return;                                                    // (uniform over the CTA)
+  }
+  // table image: one bulk copy per CTA, issued before any warp leaves and only by CTAs that have work (a CTA must not
+  // exit with a copy into its shared memory in flight)
+  if (threadIdx.x == 0) mbar_init(&tbar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) tma_load_1d(&T, a.tables, (uint32_t)sizeof(Tables<R>), &tbar);
+  if (!tile_ok) return;
   const int64_t env0 = tile << 5;
-  const bool valid = tile_ok && env0 + lane < a.n;
-  const int64_t e = (SYNC && !valid) ? a.n - 1 : env0 + lane;
+  const bool valid = env0 + lane < a.n;
+  const int64_t e = valid ? env0 + lane : a.n - 1;                             // lanes past the last env redo env n-1, storing nothing
   int flags = 0;
-  if (SYNC || valid) {
+  bool near_ground = false;
+  float sink_fps = 0.0f;           // radial (vertical) speed after the step, ft/s, positive down
+  {
     const StatePtrs<R> sp = state_ptrs<R>(a.state, e);
     Veh<R> s;
     EnvScalars es;
@@ -477,11 +517,14 @@ __global__ void __launch_bounds__(StepShape<R>::BLK, StepShape<R>::MINB) f16_ste
     }
 #endif
     flags = env_step_one<R, GROUND ? GROUND_DETECT : GROUND_OFF, SYNC>(s, es, T, msets_for<R>(), c_msets, c_snapshot, c_snapshot_props, act, a.seed, gid, a.auto_reset,
-                                   frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len, pf);
-    if (SYNC && !valid) {
+                                   frame_s[warp][lane], tframe_s[warp][lane], &reward, &ep_ret, &ep_len, pf, n_act * 32);
+    if (!valid) {
       flags = 0;
     } else {
-      if (GROUND && (flags & STEP_NEAR_GROUND)) {
+#ifndef F16_T_SKIP_REDO
+#define F16_T_SKIP_REDO 0          // timing experiment only: drop the cold redo (results are then wrong for touching envs)
+#endif
+      if (GROUND && (flags & STEP_NEAR_GROUND) && !F16_T_SKIP_REDO) {
         // a contact point reached the ground (last env-step of a crash): redo the step with the contact forces
         // from the state still in HBM; the cold copy stores the new state itself
         GroundStepOut go;
@@ -492,6 +535,8 @@ __global__ void __launch_bounds__(StepShape<R>::BLK, StepShape<R>::MINB) f16_ste
       } else {
         store_veh(s, sp);
         store_env(es, sp);
+        // d|r|/dt = r.v / |r| (the earth-rotation part of the velocity is perpendicular to r); |r| = a to 0.4 %
+        sink_fps = -(float)((s.ri[0] * s.vi[0] + s.ri[1] * s.vi[1] + s.ri[2] * s.vi[2]) * (1.0 / kEarthA));
       }
       a.reward[e] = reward;
       a.done[e] = (flags & STEP_DONE) ? 1 : 0;
@@ -525,7 +570,16 @@ __global__ void __launch_bounds__(StepShape<R>::BLK, StepShape<R>::MINB) f16_ste
       }
     }
   }
-  if (!tile_ok) return;      // a whole warp past the last tile (SYNC only): it has nothing to write
+  if (HOT) {
+    // may this env touch the ground within the NEXT step? newest frame's altitude (metres; the reset frame's 1 524 m for
+    // an env that auto-reset) minus what it sinks in one env-step (1/30 s, 25 % margin) against the reach of the contact
+    // points (24.5 ft) + the redo margin
+    near_ground = valid && frame_s[warp][lane][2] * 3.2808399f - fmaxf(sink_fps, 0.0f) * (1.25f / 30.0f) < 40.0f;
+    if (__any_sync(0xffffffffu, near_ground) && lane == 0) {
+      const int idx = atomicAdd(a.hot_count_next, 1);
+      if (idx < a.hot_cap) { a.hot_list_next[idx] = (int32_t)tile; a.hot_flag_next[tile] = 1; }
+    }
+  }
   flags_s[warp][lane] = (uint8_t)(flags & (STEP_ACTIVE | STEP_RESET | STEP_TERMINAL));
   __syncwarp();
   if (OBS == OBS_FRAME) warp_write_frames(a.obs, env0, a.n, frame_s[warp]);
@@ -652,6 +706,13 @@ struct f16_ctx {
   f16_done_record* done_list = nullptr;   // frame layout: where the step kernel appends finished envs
   int32_t* done_count = nullptr;
   int ground = 1;                         // ground reactions (f16_set_ground_reactions); default: on in FP64 mode, off in FP32 mode
+  // near-ground tiles first (f16_step_kernel): three rotating {list, count, per-tile flag} buffers and the number of
+  // whole-batch steps taken, which selects this step's roles
+  int32_t* hot_list = nullptr;            // 3 x hot_cap
+  int32_t* hot_count = nullptr;           // 3
+  uint8_t* hot_flag = nullptr;            // 3 x tiles
+  int hot_cap = 0;
+  int64_t hot_phase = 0;
 };
 
 template <typename R>
@@ -737,6 +798,17 @@ static int create_impl(f16_ctx* c, int64_t n_envs, int device, int mode) {
     CUDA_OK(cudaMemcpyToSymbol(c_snapshot_props, c->snapshot + F16_NUM_STATE_FIELDS, 12 * sizeof(double)));
   }
   CUDA_OK(cudaMalloc(&c->actions_stage, (size_t)n_envs * F16_ACTION_DIM * sizeof(float)));
+  {
+    // the early CTAs can take up to a quarter of the batch's tiles (random actions keep ~5 % of the envs below 120 ft)
+    const int warps = (mode == F16_MODE_FP64 ? StepShape<double>::BLK : StepShape<float>::BLK) / 32;
+    const int64_t quarter = (c->L.tiles / 4 + warps - 1) / warps * warps;
+    c->hot_cap = (int)std::max<int64_t>(warps, std::min<int64_t>(quarter, 1 << 20));
+    CUDA_OK(cudaMalloc(&c->hot_list, 3 * (size_t)c->hot_cap * sizeof(int32_t)));
+    CUDA_OK(cudaMalloc(&c->hot_count, 3 * sizeof(int32_t)));
+    CUDA_OK(cudaMalloc(&c->hot_flag, 3 * (size_t)c->L.tiles));
+    CUDA_OK(cudaMemset(c->hot_count, 0, 3 * sizeof(int32_t)));
+    CUDA_OK(cudaMemset(c->hot_flag, 0, 3 * (size_t)c->L.tiles));
+  }
 
   CUDA_OK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   if (mode == F16_MODE_FP64) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->ctas_per_sm, f16_step_kernel<double, OBS_RING, true>, StepShape<double>::BLK, 0));
@@ -773,6 +845,9 @@ int f16_destroy(f16_handle h) {
   cudaFree(h->stats_dev);
   cudaFree(h->scratch_dev);
   cudaFree(h->actions_stage);
+  cudaFree(h->hot_list);
+  cudaFree(h->hot_count);
+  cudaFree(h->hot_flag);
   delete h;
   return 0;
 }
@@ -897,10 +972,24 @@ static int launch_step(f16_handle h, const float* actions, int auto_reset, int64
   a.tile0 = first / 32;
   const int64_t tiles = (count + 31) / 32;
   const cudaStream_t st = (cudaStream_t)stream;
+  // near-ground tiles first: whole-batch steps of the ground-reaction builds only (a step taken in pieces,
+  // f16_step_range, keeps the plain tile order)
+  const bool hot = h->ground && first == 0 && count == h->L.n;
+  a.hot_cap = hot ? h->hot_cap : 0;
+  if (hot) {
+    const int cur = (int)(h->hot_phase % 3), nxt = (int)((h->hot_phase + 1) % 3), clr = (int)((h->hot_phase + 2) % 3);
+    a.hot_list_cur = h->hot_list + (size_t)cur * h->hot_cap; a.hot_count_cur = h->hot_count + cur; a.hot_flag_cur = h->hot_flag + (size_t)cur * h->L.tiles;
+    a.hot_list_next = h->hot_list + (size_t)nxt * h->hot_cap; a.hot_count_next = h->hot_count + nxt; a.hot_flag_next = h->hot_flag + (size_t)nxt * h->L.tiles;
+    a.hot_count_clr = h->hot_count + clr; a.hot_flag_clr = h->hot_flag + (size_t)clr * h->L.tiles;
+    h->hot_phase += 1;
+  } else {
+    a.hot_list_cur = nullptr; a.hot_count_cur = nullptr; a.hot_flag_cur = nullptr; a.hot_list_next = nullptr; a.hot_count_next = nullptr;
+    a.hot_flag_next = nullptr; a.hot_count_clr = nullptr; a.hot_flag_clr = nullptr;
+  }
 #define F16_LAUNCH_STEP_G(R, G)                                                                             \
   do {                                                                                                    \
     constexpr int BLK = StepShape<R>::BLK;                                                                \
-    const unsigned grid = (unsigned)((tiles + BLK / 32 - 1) / (BLK / 32));                                \
+    const unsigned grid = (unsigned)((tiles + BLK / 32 - 1) / (BLK / 32) + (G ? a.hot_cap / (BLK / 32) : 0)); \
     if (h->ring == OBS_FRAME) f16_step_kernel<R, OBS_FRAME, G><<<grid, BLK, 0, st>>>(a);                  \
     else if (h->ring == OBS_RING) f16_step_kernel<R, OBS_RING, G><<<grid, BLK, 0, st>>>(a);               \
     else f16_step_kernel<R, OBS_STACKED, G><<<grid, BLK, 0, st>>>(a);                                     \

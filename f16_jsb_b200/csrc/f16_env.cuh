@@ -309,7 +309,7 @@ template <typename R, int GMODE, bool FRAME_SYNC = false>
 F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const MassSetT<R>* msets, const MassSetT<double>* msets_d,
                         const double* snapshot, const double* snapshot_props, const float* act, uint64_t seed, uint64_t env_id,
                         int auto_reset, float* frame16, float* tframe16, float* reward_out, float* ep_ret_out, int32_t* ep_len_out,
-                        PrefetchHint pf = PrefetchHint{nullptr, 0, 0}) {
+                        PrefetchHint pf = PrefetchHint{nullptr, 0, 0}, int sync_threads = 0) {
   // action -> fcs/*-cmd-norm (jsbsim_gym.py:216-222): float32 -> double widening, no clipping
   Cmd<R> cmd = {(R)act[0], (R)act[1], (R)act[2], (R)act[3]};
   es.step += 1;
@@ -347,9 +347,9 @@ F16_HD int env_step_one(Veh<R>& s, EnvScalars& es, const Tables<R>& T, const Mas
       }
 #endif
 #ifdef __CUDA_ARCH__
-      // every warp of the CTA starts the frame together (shared instruction-cache fills; the caller guarantees that all
-      // threads of the CTA run these four iterations)
-      if (FRAME_SYNC && pass == 0) __syncthreads();
+      // every warp of the CTA that steps a tile starts the frame together (shared instruction-cache fills): a named
+      // barrier over `sync_threads` threads - the caller guarantees that exactly that many run these four iterations
+      if (FRAME_SYNC && pass == 0) asm volatile("bar.sync 1, %0;" ::"r"(sync_threads) : "memory");
 #endif
       // the first flight frame after a fresh construct still carries the mass properties of the 1500-lb tanks' CG
       const bool first = es.step == 1 && k == 0 && pass == 0 && !(es.episodes & kEpisodeUsedBit);

@@ -118,7 +118,9 @@ def test_amppo_checkpoint_restores_the_learner(optimizer, tmp_path):
     for name in ("frames", "age", "actions", "rewards", "episode_starts", "values", "log_probs", "advantages", "returns"):
         getattr(b.buffer, name).copy_(getattr(a.buffer, name))
     b.buffer.pos, b.buffer.full = a.buffer.pos, a.buffer.full
+    torch.manual_seed(77)          # dropout masks come from torch's global generator (not learner state, as in SB3)
     a.train()
+    torch.manual_seed(77)
     b.train()
     # (the weight-gradient kernel merges its row slabs with float atomics, so two runs of the same update agree to a
     # few ulp of the gradient, not bit for bit: 1e-5 of a parameter step of ~1e-3)

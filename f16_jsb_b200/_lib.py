@@ -55,6 +55,7 @@ def load():
     L.f16_hostwin_create.argtypes = [C.POINTER(vp), i64, i32, i32]
     L.f16_hostwin_destroy.argtypes = [vp]
     L.f16_hostwin_detach.argtypes = [vp, vp]
+    L.f16_hostwin_gather.argtypes = [vp, i32, i32, vp]
     L.f16_hostwin_layout.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.f16_hostwin_action_buffer.argtypes = [vp, i32]
     L.f16_hostwin_action_buffer.restype = vp
@@ -122,6 +123,6 @@ EXPORTED_SYMBOLS = (
     "f16_set_env_id_base", "f16_get_state", "f16_set_state", "f16_pack_states", "f16_unpack_states",
     "f16_set_env_step", "f16_get_snapshot", "f16_get_stats", "f16_stats_device_ptr", "f16_launch_count", "f16_num_state_fields",
     "f16_last_error", "f16_version")
-HOSTWIN_SYMBOLS = ("f16_hostwin_create", "f16_hostwin_destroy", "f16_hostwin_detach", "f16_hostwin_layout", "f16_hostwin_action_buffer", "f16_hostwin_reset",
+HOSTWIN_SYMBOLS = ("f16_hostwin_create", "f16_hostwin_destroy", "f16_hostwin_detach", "f16_hostwin_gather", "f16_hostwin_layout", "f16_hostwin_action_buffer", "f16_hostwin_reset",
                    "f16_hostwin_step", "f16_hostwin_timing", "f16_hostwin_numa_node", "f16_hostwin_fill", "f16_hostwin_push")
 ROLLOUT_SYMBOLS = ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather", "f16_features17")

@@ -573,6 +573,22 @@ int f16_hostwin_timing(f16_hostwin_handle w, double* seconds_per_step, int reset
 
 float* f16_hostwin_action_buffer(f16_hostwin_handle w, int which) { return (w && (which == 0 || which == 1)) ? w->actions[which] : nullptr; }
 
+// Contiguous copy of the current window: dst[n][k][f] = ring[ring][first_slot + k][n][f], on the window's worker threads.
+// This is what copy_obs=True (DummyVecEnv's behaviour: the caller owns the array) costs - 600 B read + 600 B written
+// per env; NumPy's strided copy of the same view runs single-threaded over 60-byte pieces and is ~10x slower.
+int f16_hostwin_gather(f16_hostwin_handle w, int ring, int first_slot, float* dst) {
+  if (!w || !dst) return failf("f16_hostwin_gather: NULL argument");
+  if (ring < 0 || ring >= w->n_rings || first_slot < 0 || first_slot > SLOTS) return failf("f16_hostwin_gather: bad ring / slot");
+  const f16_hostwin* cw = w;
+  w->pool->parallel_for(w->n, 4096, [=](int64_t b, int64_t e) {
+    for (int64_t n = b; n < e; ++n) {
+      float* d = dst + n * (ROWS * FEAT);
+      for (int k = 0; k < ROWS; ++k) memcpy(d + k * FEAT, cw->row(ring, first_slot + k, n), ROW_BYTES);
+    }
+  });
+  return 0;
+}
+
 int f16_hostwin_fill(f16_hostwin_handle w, const float* frames, f16_hostwin_result* out) {
   if (!w || !frames) return failf("f16_hostwin_fill: NULL argument");
   w->copier->wait();

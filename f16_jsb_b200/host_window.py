@@ -95,6 +95,14 @@ class HostWindow:
                                                                    strides=(NUM_FEATURES * 4, pitch, 4))
         return v
 
+    def gather(self, ring: int, first_slot: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """An owned, contiguous (N,10,15) copy of a window, assembled by the library's worker threads."""
+        if out is None:
+            out = np.empty((self.num_envs, NUM_STACKED_FRAMES, NUM_FEATURES), np.float32)
+        assert out.flags.c_contiguous and out.dtype == np.float32 and out.shape == (self.num_envs, NUM_STACKED_FRAMES, NUM_FEATURES)
+        _lib.check(self.lib.f16_hostwin_gather(self._h, int(ring), int(first_slot), C.c_void_p(out.ctypes.data)), "f16_hostwin_gather")
+        return out
+
     def _result(self) -> StepResult:
         r, n = self._res, self.num_envs
         out = StepResult()

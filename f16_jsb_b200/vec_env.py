@@ -199,7 +199,7 @@ class F16VecEnv(VecEnvBase):
             shared = {"TimeLimit.truncated": False}
             infos = [done_infos.get(i, shared) for i in range(self.num_envs)]
         if self.copy_obs:
-            return res.obs.copy(), res.reward.copy(), dones.copy(), infos
+            return self._win.gather(res.ring, res.first_slot), res.reward.copy(), dones.copy(), infos
         return res.obs, res.reward, dones, infos
 
     def step_wait(self):

@@ -72,6 +72,8 @@ typedef struct f16_hostwin_result {
 /* Rings for n_envs environments; n_rings is 1 or 2. Without F16_HOSTWIN_PIN nothing touches CUDA (the
  * host-only entry points below still work; used by the CPU tests). */
 int f16_hostwin_create(f16_hostwin_handle* out, int64_t n_envs, int n_rings, int flags);
+/* Contiguous (N,10,15) copy of the window (ring, first_slot) into caller memory, on the window's worker threads. */
+int f16_hostwin_gather(f16_hostwin_handle w, int ring, int first_slot, float* dst);
 /* The env's done list points into this window's memory: detach the env before destroying the window (or destroy the
  * env first). */
 int f16_hostwin_detach(f16_hostwin_handle w, f16_handle env);

@@ -131,3 +131,23 @@ def test_pinning_needs_a_device():
     from f16_jsb_b200 import _lib
     with pytest.raises(_lib.F16Error):
         HostWindow(8, pin=True)
+
+
+@pytest.mark.parametrize("n_rings,alias", [(1, True), (2, True), (2, False)])
+def test_gather_returns_an_owned_contiguous_copy_of_the_window(n_rings, alias):
+    """f16_hostwin_gather (copy_obs=True of F16VecEnv: DummyVecEnv hands out owned arrays): the threaded copy equals the
+    strided view it was taken from and does not change when the ring moves on."""
+    n = 5000
+    rng = np.random.default_rng(3)
+    w = HostWindow(n, n_rings=n_rings, pin=False, alias=alias)
+    res = w.fill(rng.normal(size=(n, 15)).astype(np.float32))
+    for t in range(13):
+        frames = rng.normal(size=(n, 15)).astype(np.float32)
+        res = w.push(frames, None, None, None, np.empty(0, dtype=RECORD_DTYPE))
+        got = w.gather(res.ring, res.first_slot)
+        assert got.flags.owndata and got.flags.c_contiguous and got.shape == (n, 10, 15)
+        np.testing.assert_array_equal(got, res.obs)
+        if t == 5:
+            kept, kept_expected = got, got.copy()
+    np.testing.assert_array_equal(kept, kept_expected)
+    w.close()

@@ -210,6 +210,44 @@ def kernel_name(mode, layout, ground):
     return "f16_step_kernel<%s,%s,%s>" % ("float" if mode == "fp32" else "double", layout, "ground" if ground else "noground")
 
 
+def amppo_iteration(dev, args):
+    """One timed iteration (after one warm-up iteration) of f16_jsb_b200.amppo.AMPPO: 4 096 envs x n_steps 2 048 = 8.4 M
+    transitions, minibatches of 131 072, 10 epochs, DAG optimizer, everything on the device in FP32 (train.py:21-32,81-130;
+    stable_baselines3/ppo/ppo.py:271-455). The reference runs ONE env with minibatches of 256; a batched env needs
+    proportionally larger minibatches, so the batch size is stated, not hidden."""
+    import torch
+
+    from f16_jsb_b200 import F16BatchedEnv
+    from f16_jsb_b200.amppo import AMPPO, AMPPOConfig
+    envs, n_steps, batch, epochs = args.amppo_envs, 2048, 131072, 10
+    env = F16BatchedEnv(envs, device=dev, mode="fp32", seed=args.seed)
+    algo = AMPPO(env, AMPPOConfig(n_steps=n_steps, batch_size=batch, n_epochs=epochs, optimizer="DAG", use_am_ppo=True))
+    times = []
+    for it in range(2):                 # iteration 0 warms up (CUDA-graph capture of the policy forward, allocator)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        algo.collect_rollouts()
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
+        algo.train()
+        torch.cuda.synchronize(dev)
+        times.append((t1 - t0, time.perf_counter() - t1))
+    roll, upd = times[-1]
+    n = envs * n_steps
+    st = env.stats()
+    stats = {k: (float(v) if isinstance(v, (int, float)) else v) for k, v in algo.last_stats.items()}
+    env.close()
+    del algo, env
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE configs[4]: AM-PPO (n_steps 2048, LMA extractor, DAG optimizer) rollout + update on GPU env observations, one B200",
+            "envs": envs, "n_steps": n_steps, "batch_size": batch, "n_epochs": epochs, "transitions_per_iteration": n, "dtype": "f32",
+            "rollout_s": roll, "update_s": upd, "rollout_env_steps_per_s": n / roll, "update_samples_per_s": n * epochs / upd,
+            "value": n / (roll + upd), "unit": "env-steps/s per training iteration (rollout + 10-epoch update)",
+            "episodes_finished": st["episodes"], "last_update": stats,
+            "note": "hand-written: env step, rollout store + GAE + stack-rebuilding gather, feature transform, latent attention, LayerNorm, "
+                    "weight gradients; forward / input-gradient GEMMs of the 17->64->32/96/128 layers are cuBLAS FP32 (DESIGN.md 4a)"}
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -382,6 +420,14 @@ def run_ours(args):
                              "DummyVecEnv's behaviour (a fresh 600-byte stack per env per step); both are host-CPU work of the caller, "
                              "timed over %d steps" % few}
 
+    # ---- BASELINE configs[4]: end-to-end AM-PPO (n_steps 2048, LMA extractor) rollout + update consuming GPU env observations
+    amppo = None
+    if args.amppo and world == 1:
+        try:
+            amppo = amppo_iteration(dev, args)
+        except Exception as e:          # the headline line must not depend on the learner leg
+            amppo = {"error": "%s: %s" % (type(e).__name__, e)}
+
     if rank != 0:
         return
     cpu = cpu_baseline(seconds=args.cpu_seconds) if (not args.no_cpu_baseline and world == 1) else None   # rank 0, N=1 only
@@ -420,6 +466,8 @@ def run_ours(args):
     }
     if cpu:
         out["cpu_baseline"] = cpu
+    if amppo:
+        out["config5_amppo"] = amppo
     print(json.dumps(out))
 
 
@@ -445,6 +493,8 @@ def main():
     ap.add_argument("--e2e-warmup", type=int, default=600)
     ap.add_argument("--no-e2e-variants", dest="e2e_variants", action="store_false",
                     help="skip the one-ring, consumer-reads, copy_obs and whole-stack-copy variants of the end-to-end measurement")
+    ap.add_argument("--no-amppo", dest="amppo", action="store_false", help="skip the configs[4] leg (one AM-PPO iteration, ~20 s)")
+    ap.add_argument("--amppo-envs", type=int, default=4096)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

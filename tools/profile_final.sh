@@ -8,7 +8,7 @@ python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err || { echo "ben
 echo "bench rc=0"; cut -c1-300 $out/${tag}_bench.json
 python bench.py --mode fp64 --steps 300 --no-legs --no-cpu-baseline --e2e-steps 20 --e2e-warmup 100 --no-e2e-variants > $out/${tag}_bench_fp64.json 2> $out/${tag}_bench_fp64.err; echo "bench fp64 rc=$?"
 # the driver's command shape, with a short pre-roll so that the launch list stays small
-short="--steps 20 --warmup 5 --preroll 40 --leg-steps 10 --e2e-steps 3 --e2e-warmup 3 --no-cpu-baseline --no-e2e-variants"
+short="--steps 20 --warmup 5 --preroll 40 --leg-steps 10 --e2e-steps 3 --e2e-warmup 3 --no-cpu-baseline --no-e2e-variants --no-amppo"
 python bench.py $short > $out/${tag}_short.json 2> $out/${tag}_short.err || { echo "short bench failed"; tail -5 $out/${tag}_short.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file $out/${tag}_launches.csv python bench.py $short > $out/${tag}_ncu_launches.log 2>&1
 echo "launch list rc=$?"

@@ -10,6 +10,6 @@ cat $out/${tag}_host_write_bw_8gpu.json
 for n in 1 2 4 8; do
   extra="--no-e2e-variants"; [ $n = 8 ] && extra=""
   if [ $n = 1 ]; then launcher="python"; else launcher="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n"; fi
-  $launcher bench.py --gpus $n --steps 300 --warmup 5 --e2e-steps 60 --no-cpu-baseline $extra > $out/${tag}_scale_n$n.json 2> $out/${tag}_scale_n$n.err
+  $launcher bench.py --gpus $n --steps 300 --warmup 5 --e2e-steps 60 --no-cpu-baseline --no-amppo $extra > $out/${tag}_scale_n$n.json 2> $out/${tag}_scale_n$n.err
   echo "N=$n rc=$?"; cut -c1-160 $out/${tag}_scale_n$n.json
 done

@@ -414,3 +414,35 @@ def test_envelope_step_parity(F16BatchedEnv, oracle, state_fields, mode, tol):
     assert e.max() < tol, (int(worst[0]), state_fields[int(worst[1])], float(e.max()))
     if mode == "fp64":
         assert np.allclose(obs[:, -1, :12].cpu().numpy(), frames[:, :12], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp64"])
+def test_near_ground_tiles_first_steps_every_env_exactly_once(F16BatchedEnv, mode):
+    """The ground-reaction builds start a whole-batch launch with early CTAs for the tiles whose envs may touch the ground
+    (csrc/f16_b200.cu, StepArgs::hot_*) and let the regular CTA of such a tile skip it. Whatever the list holds, every env
+    must be stepped exactly once per step: a batch stepped whole (scheduling on) against the same batch stepped in three
+    ranges (f16_step_range: plain tile order), frame layout, ragged size, most envs diving into the ground with
+    auto-reset for 330 steps - frames, rewards and flags bit-identical at every step, and the list really was in use."""
+    import ctypes as C
+    from f16_jsb_b200 import _lib
+    n = 3000 + 21
+    g = torch.Generator(device="cuda").manual_seed(4)
+    a = torch.zeros((n, 4), device="cuda")
+    a[:, 1] = 0.9 * (torch.rand(n, device="cuda", generator=g) > 0.3).float()
+    a[:, 0] = torch.rand(n, device="cuda", generator=g) - 0.5
+    a[:, 3] = 1.0
+    whole = F16BatchedEnv(n, mode=mode, seed=8, obs_layout="frame", ground_reactions=True)
+    parts = F16BatchedEnv(n, mode=mode, seed=8, obs_layout="frame", ground_reactions=True)
+    assert torch.equal(whole.reset(), parts.reset())
+    cuts = [0, 1024, 2048, n]
+    redone = crashes = 0
+    for k in range(330):
+        whole.step(a, auto_reset=True)
+        _lib.check(parts.lib.f16_step_begin(parts._h, parts._stream()), "f16_step_begin")
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            _lib.check(parts.lib.f16_step_range(parts._h, C.c_void_p(a.data_ptr()), 1, lo, hi - lo, parts._stream()), "f16_step_range")
+        assert torch.equal(whole.obs, parts.obs), k
+        assert torch.equal(whole.reward, parts.reward) and torch.equal(whole.done, parts.done) and torch.equal(whole.truncated, parts.truncated), k
+    sw, sp = whole.stats(), parts.stats()
+    assert sw["crashes"] == sp["crashes"] > 100 and sw["ground_redos"] == sp["ground_redos"] > 5, (sw, sp)
+    assert torch.equal(whole.pack_states(), parts.pack_states())

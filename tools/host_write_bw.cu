@@ -67,7 +67,26 @@ int main() {
     for (size_t d : done) tot += d;
     *gbs = tot / (now() - t0) / 1e9;
   };
-  printf("{\"gpus\": %d, \"host_threads\": %d, \"buffer_mb\": %zu,\n \"dma_d2h_gbs\": {", ndev, hw, bytes >> 20);
+  // (d) would sending 48 of each frame's 60 bytes help (the goal columns are constant within an episode)? A 2-D copy of
+  // 48-byte runs at a 60-byte pitch on both sides, one GPU: payload GB/s against the contiguous copy of whole rows
+  double c2d_payload = 0.0, c1d = 0.0;
+  {
+    cudaSetDevice(0);
+    const size_t rows = bytes / 60;
+    for (int pass = 0; pass < 2; ++pass) {
+      double t0 = now();
+      for (int r = 0; r < reps; ++r) {
+        if (pass == 0) cudaMemcpy2DAsync(g[0].h, 60, g[0].d, 60, 48, rows, cudaMemcpyDeviceToHost, g[0].s);
+        else cudaMemcpyAsync(g[0].h, g[0].d, rows * 60, cudaMemcpyDeviceToHost, g[0].s);
+      }
+      cudaStreamSynchronize(g[0].s);
+      const double dt = now() - t0;
+      if (pass == 0) c2d_payload = (double)reps * rows * 48 / dt / 1e9; else c1d = (double)reps * rows * 60 / dt / 1e9;
+    }
+  }
+  printf("{\"gpus\": %d, \"host_threads\": %d, \"buffer_mb\": %zu,\n \"frames_48_of_60_bytes_2d_copy\": {\"payload_gbs\": %.1f, \"rows_per_s\": %.3e, "
+         "\"contiguous_60_byte_rows_gbs\": %.1f, \"contiguous_rows_per_s\": %.3e},\n \"dma_d2h_gbs\": {",
+         ndev, hw, bytes >> 20, c2d_payload, c2d_payload * 1e9 / 48, c1d, c1d * 1e9 / 60);
   bool first = true;
   for (int G = 1; G <= ndev; G *= 2) { printf("%s\"%d\": %.1f", first ? "" : ", ", G, dma(G)); first = false; }
   printf("},\n \"cpu_streaming_copy_gbs\": {");

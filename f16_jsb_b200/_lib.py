@@ -90,8 +90,10 @@ def load():
     L.f16_lma_layernorm_forward.argtypes = [i64, i32, vp, vp, vp, C.c_float, vp, vp]
     L.f16_lma_layernorm_backward.argtypes = [i64, i32, vp, vp, vp, C.c_float, vp, vp, vp, vp]
     L.f16_lma_linear_wgrad.argtypes = [i64, i32, i32, vp, vp, vp, vp, vp]
+    L.f16_lma_linear_forward.argtypes = [i64, i32, i32, vp, vp, vp, vp, vp]
+    L.f16_lma_linear_supported.argtypes = [i32, i32]
     for name in ("f16_lma_attention_forward", "f16_lma_attention_backward", "f16_lma_attention_mask", "f16_lma_layernorm_forward",
-                 "f16_lma_layernorm_backward", "f16_lma_linear_wgrad"):
+                 "f16_lma_layernorm_backward", "f16_lma_linear_wgrad", "f16_lma_linear_forward", "f16_lma_linear_supported"):
         getattr(L, name).restype = i32
     L.f16_features17.restype = i32
     for name in ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather"):

@@ -47,6 +47,18 @@ int f16_lma_layernorm_backward(int64_t rows, int dim, const float* x, const floa
  * for in / out <= 160 and 10^5..10^6 rows, where the reduction runs over the batch. */
 int f16_lma_linear_wgrad(int64_t rows, int in_features, int out_features, const float* x, const float* dy, float* dweight,
                          float* dbias, void* stream);
+
+/* Forward of the same layers (and, with weight = W^T, their input gradient dx = dy W) on the tensor cores:
+ * y[row][out] = sum_in x[row][in] * weight[out][in] + bias[out] (bias may be NULL), replacing torch.nn.functional.linear
+ * as called by the reference's Linear modules (jsbsim_gym/LMA_features.py:221-279,315-385; SB3 MlpExtractor,
+ * stable_baselines3/common/torch_layers.py). tcgen05.mma kind::tf32 with both operands split into a TF32 head and an
+ * FP32 remainder (three MMAs per k-step), FP32 accumulation in tensor memory: FP32-accurate like a reordered FP32 sum.
+ * Row-major float32, contiguous; y and bias 16-byte aligned. Shapes: out_features a multiple of 16 up to 256;
+ * in_features <= 32, or a multiple of 32 (then x 16-byte aligned) - f16_lma_linear_supported says whether a shape is
+ * built (the caller keeps the library GEMM for the others: the 4- and 1-wide output heads). */
+int f16_lma_linear_supported(int in_features, int out_features);
+int f16_lma_linear_forward(int64_t rows, int in_features, int out_features, const float* x, const float* weight,
+                           const float* bias, float* y, void* stream);
 #ifdef __cplusplus
 }
 #endif

@@ -14,8 +14,8 @@ L = _lib.load()
 B = 131072
 LAYERS = [("embed 17->64", 10 * B, 17, 64), ("latent 128->32", 5 * B, 128, 32), ("qkv 32->96", 5 * B, 32, 96), ("proj 32->32", 5 * B, 32, 32),
           ("fc 32->128", 5 * B, 32, 128), ("fc2 128->32", 5 * B, 128, 32), ("pi0 160->64", B, 160, 64), ("pi1 64->64", B, 64, 64),
-          ("vf0 160->128", B, 160, 128), ("vf1 128->64", B, 128, 64),
-          ("d latent 32->128", 5 * B, 32, 128), ("d qkv 96->32", 5 * B, 96, 32), ("d pi0 64->160", B, 64, 160), ("d vf0 128->160", B, 128, 160)]
+          ("vf1 128->64", B, 128, 64),
+          ("d latent 32->128", 5 * B, 32, 128), ("d qkv 96->32", 5 * B, 96, 32), ("d pi0 64->160", B, 64, 160)]
 
 
 def timeit(fn, n=20):
@@ -32,7 +32,10 @@ def timeit(fn, n=20):
 
 
 out = []
+only = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, rows, k, n in LAYERS:
+    if only and only not in name:
+        continue
     xs = [torch.randn((rows, k), device="cuda") for _ in range(3)]           # > L2 in rotation
     w = torch.randn((n, k), device="cuda") * 0.1
     b = torch.randn((n,), device="cuda")

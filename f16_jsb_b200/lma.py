@@ -15,6 +15,7 @@ heads: `mlp_extractor.policy_net.0.weight`, `action_net.weight`, `value_net.weig
 this repo's own: the stacking / re-chunk is one permute, attention is one fused SDPA call over (B, 4, 5, 8).
 """
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -164,15 +165,51 @@ class _MLP(nn.Module):
         return F.dropout(self.c_proj(F.gelu(self.c_fc(x))), self.p, self.training)
 
 
+def _linear_tc(x2: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """x2 (rows, in) @ weight (out, in)^T + bias on the tensor cores (csrc/f16_lma_linear.cu): float32, contiguous."""
+    import ctypes as C
+
+    from . import _lib
+    y = torch.empty((x2.shape[0], weight.shape[0]), dtype=torch.float32, device=x2.device)
+    stream = C.c_void_p(torch.cuda.current_stream(x2.device).cuda_stream)
+    with torch.cuda.device(x2.device):
+        _lib.check(_lib.load().f16_lma_linear_forward(x2.shape[0], x2.shape[1], weight.shape[0], C.c_void_p(x2.data_ptr()),
+                                                      C.c_void_p(weight.data_ptr()), C.c_void_p(bias.data_ptr() if bias is not None else 0),
+                                                      C.c_void_p(y.data_ptr()), stream), "f16_lma_linear_forward")
+    return y
+
+
+_TC_SHAPES = {}
+
+
+def _tc_supported(in_features: int, out_features: int) -> bool:
+    key = (in_features, out_features)
+    if key not in _TC_SHAPES:
+        from . import _lib
+        _TC_SHAPES[key] = bool(_lib.load().f16_lma_linear_supported(in_features, out_features))
+    return _TC_SHAPES[key]
+
+
 class _LinearFn(torch.autograd.Function):
-    """y = x W^T + b with the weight / bias gradients from csrc/f16_lma_wgrad.cu (include/f16_lma.h): for these layers
-    (<= 160 features, 10^5..10^6 rows) the reduction over the batch is the expensive part of the backward and the
-    library GEMM gives it to a handful of CTAs. Forward and the input gradient stay torch matmuls."""
+    """y = x W^T + b for the policy's tall-skinny layers (<= 160 features, 10^5..10^6 rows). Forward and input gradient
+    (dx = dy W, the same kernel with W^T as the weight) run on the tensor cores with split TF32 operands
+    (csrc/f16_lma_linear.cu: FP32-accurate, 4.4-5.1 TB/s where the library's FP32 GEMMs reach 1.0-1.9); the weight /
+    bias gradients, whose reduction axis is the batch, come from csrc/f16_lma_wgrad.cu (include/f16_lma.h). Shapes the
+    tensor-core kernel does not build (the 4- and 1-wide output heads, 160 -> 128) stay torch matmuls."""
+
+    use_tc = os.environ.get("F16_LMA_TC", "1") != "0"        # class-wide switch (A/B measurements, tests)
 
     @staticmethod
     def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
+        k, n = weight.shape[1], weight.shape[0]
+        if _LinearFn.use_tc and _tc_supported(k, n):
+            x2 = x.reshape(-1, k)
+            if not x2.is_contiguous():
+                x2 = x2.contiguous()
+            if x2.data_ptr() % 16 == 0:
+                return _linear_tc(x2, weight.contiguous(), bias).view(*x.shape[:-1], n)
         return F.linear(x, weight, bias)
 
     @staticmethod
@@ -182,11 +219,17 @@ class _LinearFn(torch.autograd.Function):
         from . import _lib
         x, weight = ctx.saved_tensors
         dx = dw = db = None
+        k, n = weight.shape[1], weight.shape[0]
+        dy2 = dy.reshape(-1, n)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
         if ctx.needs_input_grad[0]:
-            dx = dy.matmul(weight)
+            if _LinearFn.use_tc and _tc_supported(n, k) and dy2.data_ptr() % 16 == 0:
+                dx = _linear_tc(dy2, weight.t().contiguous(), None).view(*dy.shape[:-1], k)
+            else:
+                dx = dy.matmul(weight)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             x2 = x.reshape(-1, x.shape[-1]).contiguous()
-            dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
             dw = torch.empty_like(weight)
             db = torch.empty(weight.shape[0], dtype=weight.dtype, device=weight.device) if ctx.has_bias else None
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)

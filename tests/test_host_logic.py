@@ -110,3 +110,26 @@ def test_stats_allreduce_world_size_2_gloo():
     for r in res:
         assert r[3][0] == total and r[3][1] == float(sum(range(total))) and r[3][6] == 10.0 * total
         assert r[4] == 2.0
+
+
+def test_tensor_core_linear_shape_support_is_host_logic():
+    """f16_lma_linear_supported (include/f16_lma.h) is pure host code: which Linear shapes of the reference's LMA policy
+    (jsbsim_gym/LMA_features.py:221-279,315-385; SB3 MlpExtractor heads) the tensor-core kernel builds, and that the
+    launcher refuses bad arguments with a message before touching a device."""
+    import ctypes as C
+
+    from f16_jsb_b200 import _lib
+    L = _lib.load()
+    built = [(17, 64), (128, 32), (32, 96), (32, 32), (32, 128), (160, 64), (64, 64), (128, 64),    # forward
+             (96, 32), (64, 160), (64, 128), (32, 128)]                                             # input gradients (W^T)
+    for k, n in built:
+        assert L.f16_lma_linear_supported(k, n) == 1, (k, n)
+    for k, n in [(64, 4), (64, 1), (160, 128), (128, 160), (40, 32), (32, 48), (32, 0), (0, 32), (32, 288)]:
+        assert L.f16_lma_linear_supported(k, n) == 0, (k, n)
+    assert L.f16_lma_linear_forward(0, 32, 32, None, None, None, None, None) != 0
+    assert b"rows must be positive" in L.f16_last_error()
+    assert L.f16_lma_linear_forward(128, 32, 32, None, None, None, None, None) != 0
+    assert b"NULL pointer" in L.f16_last_error()
+    buf = (C.c_float * 64)()
+    assert L.f16_lma_linear_forward(128, 64, 4, buf, buf, None, buf, None) != 0
+    assert b"unsupported shape" in L.f16_last_error()

@@ -38,11 +38,13 @@
 #include <string.h>
 
 #include "../../include/f16_lma.h"
+#include "f16_tc_common.cuh"
 
 extern "C" int f16_internal_fail(const char* msg);
 extern "C" void f16_internal_count_launch(void);
 
 namespace {
+using namespace f16tc;
 constexpr int TILE_M = 128, LOADERS = 128, GROUPS = 2, THREADS = GROUPS * LOADERS + 128 + 32 + 32;
 constexpr int A_STAGES = GROUPS;                        // operand stages: one per converter group
 constexpr int RAW_STAGES = 4;                           // chunks in the TMA ring
@@ -66,43 +68,6 @@ struct LinArgs {
   uint32_t tmem_cols;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-// Relaxed arrive: what has to be ordered before the arrival is ordered by the fence next to each call (fence.proxy.async
-// after the operand stores, tcgen05.fence::before_thread_sync after the accumulator reads); the default .release.cta
-// adds a MEMBAR.ALL.CTA that also waits for the thread's global stores in flight.
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
-  for (;;) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    if (ok) return;
-    if (clock64() - t0 > 4000000000LL) __trap();      // ~2 s: a protocol error must not hang the GPU
-  }
-}
-// one box of the tensor map (32 floats x 128 rows, rows past the end zero-filled) -> shared memory, completion on `bar`
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ bool elect_one() {
-  uint32_t p;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(p));
-  return p != 0;
-}
-
 // shared-memory operand descriptor, K-major, SWIZZLE_128B: start address >> 4 and leading byte offset 1 (unused with a
 // swizzle) in the low word; stride byte offset 1024 B (8 rows x 128 B) >> 4, descriptor version 1 (sm_100) and layout
 // type 2 in the high word
@@ -113,33 +78,6 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 // instruction descriptor, kind::tf32: D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major, N >> 3, M >> 4
 __device__ __forceinline__ uint32_t umma_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                 "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                 "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// TF32 head and TF32 remainder, both rounded to nearest (ties away): 10 explicit mantissa bits, the 13 low bits zero, so
-// the tensor core reads exactly these values whether it truncates or rounds; v - hi - lo is at most 2^-23 |v|
-__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
-  lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xFFFFE000u);
 }
 // byte offset of element (row, k) of a [rows][32-float] K-atom in the SWIZZLE_128B layout
 __device__ __forceinline__ uint32_t sw128(uint32_t row, uint32_t k) { return row * 128u + ((((k >> 2) ^ row) & 7u) << 4) + ((k & 3u) << 2); }

@@ -1,0 +1,317 @@
+// f16_lma_wgrad_tc.cu - weight and bias gradients of the policy's Linear layers on the tensor cores
+// (include/f16_lma.h): dW[out][in] = sum_rows dY[row][out] X[row][in], db[out] = sum_rows dY[row][out].
+//
+// After the forward and the input gradient moved to tcgen05 (f16_lma_linear.cu) the weight gradients were the largest
+// item of an AM-PPO update step (24 %): a contraction over 10^5..10^6 rows with a 32..128 x 32..160 result, bound by
+// reading X and dY once (60-110 us at the HBM rate where the FP32 slab kernel of f16_lma_wgrad.cu needs 160-190).
+// Here D[n][k] = sum_m dY[m][n] X[m][k] is one UMMA accumulator, 128 lanes (n, the live ones are n < out) x `in` columns:
+//   * both operands are "MN-major" for this product (the reduction index m is the row of the row-major activations), and
+//     a 16-row x 32-float piece of an activation, its 32-byte pieces swizzled inside each four-row atom, IS the canonical
+//     MN-major operand block (SWIZZLE_128B_BASE32B, the only layout in which the tensor core transposes 32-bit
+//     operands), read through a descriptor with the transpose bits set. A chunk = 16 rows: out/32 blocks of dY and
+//     in/32 blocks of X, TF32 head and remainder each
+//     (the reference computes in FP32: three MMAs per 8-row k-step, dYl Xh + dYh Xl + dYh Xh; what is dropped is 2^-22).
+//   * the tensor core's FP32 accumulation truncates, and here the chain is long (thousands of k-steps per CTA), so the
+//     accumulator is read out and restarted every 256 rows (96 MMAs): the partial results are summed in FP32 with
+//     round-to-nearest in a per-thread row of shared memory, and meet the other CTAs in float atomics on the
+//     zero-initialised output at the end (as the slab kernel does).
+//   * roles as in f16_lma_linear.cu: TMA producer (two tensor maps, boxes of 16 rows x 32 floats, a four-chunk ring),
+//     two converter groups (split into head / remainder, swizzled stores, column sums of dY for the bias gradient on
+//     the way), one MMA warp (uniform descriptors, one elected lane), four read-out warps (tcgen05.ld 32x32b; a thread
+//     = an output feature n), two accumulators alternating in tensor memory.
+// Built for out in {32, 64, 96, 128} and in a multiple of 32 up to 160 whose partial sums fit shared memory; the caller
+// keeps the slab kernel for the rest (17 input features, the 4- and 1-wide heads, 160 -> 128).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/f16_lma.h"
+#include "f16_tc_common.cuh"
+
+extern "C" int f16_internal_fail(const char* msg);
+extern "C" void f16_internal_count_launch(void);
+
+namespace {
+using namespace f16tc;
+constexpr int CHUNK_ROWS = 16, LOADERS = 128, GROUPS = 2, THREADS = GROUPS * LOADERS + 128 + 32 + 32;
+constexpr int FLUSH_CHUNKS = 16;                        // accumulator read out every 16 chunks = 256 rows
+constexpr int RAW_STAGES = 4;
+constexpr uint32_t BLOCK = CHUNK_ROWS * 128;            // 2 KB: 16 rows x 32 floats
+constexpr uint32_t BAR_BYTES = 192;
+
+struct WgArgs {
+  float* dw; float* db;
+  int64_t rows, chunks, chunks_per_cta;
+  int k, n;                // in / out features
+  uint32_t tmem_cols;
+};
+
+// MN-major operand descriptor. 32-bit operands can only be transposed in the SWIZZLE_128B_BASE32B layout (type 1): rows of
+// 128 B = 32 MN-elements, atoms of four rows, the 32-byte pieces of a row XOR-ed with the row index mod 4. Start address
+// >> 4; leading byte offset = distance between 32-element blocks along MN (one BLOCK); stride byte offset = distance
+// between four-row atoms along K (512 B); descriptor version 1
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) {
+  const uint32_t hi = 32u | (1u << 14) | (1u << 29);
+  return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | ((BLOCK >> 4) << 16));
+}
+// kind::tf32, D = F32, A = B = TF32, both MN-major (bits 15, 16), N = in features, M = 128
+__device__ __forceinline__ uint32_t wg_idesc(int k) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(k >> 3) << 17) | (8u << 24);
+}
+
+__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgArgs a, const __grid_constant__ CUtensorMap tmap_x,
+                                                              const __grid_constant__ CUtensorMap tmap_dy) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw0 = smem_u32(smem_raw);
+  const uint32_t base = (raw0 + 1023u) & ~1023u;
+  uint8_t* const sm = smem_raw + (base - raw0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nba = a.n >> 5, nbb = a.k >> 5, nb = nba + nbb;      // 32-float blocks of dY, of X, per chunk
+  // shared memory: [operand stages: per stage dYh | dYl | Xh | Xl blocks] [TMA ring: per slot dY blocks | X blocks]
+  // [partial sums: n rows of k + 4 floats] [bias sums: n floats] [barriers]
+  const uint32_t STAGE = 2u * (uint32_t)nb * BLOCK, RAW_SLOT = (uint32_t)nb * BLOCK;
+  const uint32_t OFF_A = 0, OFF_RAW = GROUPS * STAGE, OFF_PART = OFF_RAW + RAW_STAGES * RAW_SLOT;
+  const uint32_t PROW = (uint32_t)(a.k + 4) * 4u;                // bytes per partial row (16 B of padding: conflict-free)
+  const uint32_t OFF_DB = OFF_PART + (uint32_t)a.n * PROW, OFF_BAR = (OFF_DB + (uint32_t)a.n * 4u + 15u) & ~15u;
+  {
+    uint32_t dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if ((base - raw0) + OFF_BAR + BAR_BYTES > dyn) __trap();
+  }
+  const uint32_t sBar = base + OFF_BAR;
+  const uint32_t bar_full = sBar, bar_empty = sBar + 16, bar_acc_full = sBar + 32, bar_acc_empty = sBar + 48, bar_raw_full = sBar + 64,
+                 bar_raw_empty = sBar + 96, tmem_holder = sBar + 128;
+  volatile uint32_t* const tmem_holder_p = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 128);
+
+  if (tid == 0) {
+    for (int s = 0; s < GROUPS; ++s) { mbar_init(bar_full + 8 * s, LOADERS); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 128); }
+    for (int s = 0; s < RAW_STAGES; ++s) { mbar_init(bar_raw_full + 8 * s, 1); mbar_init(bar_raw_empty + 8 * s, LOADERS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_holder), "r"(a.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // partial sums and bias sums start at zero; the operand stages too (the descriptor of dY always spans four blocks:
+  // what it reads past out/32 blocks only reaches accumulator lanes that are never read, but must not be NaN-producing
+  // garbage for compute-sanitizer's sake)
+  for (uint32_t o = tid * 16u; o < OFF_PART; o += THREADS * 16u) *reinterpret_cast<float4*>(sm + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (uint32_t o = OFF_PART + tid * 4u; o < OFF_BAR; o += THREADS * 4u) *reinterpret_cast<float*>(sm + o) = 0.f;
+  tc_fence_before();
+  fence_async_smem();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder_p;
+
+  // this CTA's slab of chunks, cut in windows of FLUSH_CHUNKS
+  const int64_t c_begin = (int64_t)blockIdx.x * a.chunks_per_cta;
+  int64_t c_end = c_begin + a.chunks_per_cta;
+  if (c_end > a.chunks) c_end = a.chunks;
+  const int64_t items = c_end > c_begin ? c_end - c_begin : 0;
+  const int64_t windows = (items + FLUSH_CHUNKS - 1) / FLUSH_CHUNKS;
+
+  if (warp < 8) {
+    // ======================================================================== converters
+    const int g = warp >> 2, t = tid & (LOADERS - 1);
+    const int64_t my_items = items > g ? (items - g + 1) / 2 : 0;
+    uint8_t* const stage = sm + OFF_A + (uint32_t)g * STAGE;
+    const uint32_t m = (uint32_t)(t >> 3), p = (uint32_t)(t & 7);             // row of the chunk, 16-byte piece of the block row
+    const uint32_t src_off = m * 128u + p * 16u, dst_off = m * 128u + ((((p >> 1) ^ m) & 3u) << 5) + ((p & 1u) << 4);
+    float bsum[4][4];                                                         // column sums of dY: block b, columns 4 p ..
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bsum[b][i] = 0.f;
+    for (int64_t u = 0; u < my_items; ++u) {
+      const int64_t item = 2 * u + g;
+      const uint32_t slot = (uint32_t)(item % RAW_STAGES), raw_use = (uint32_t)(item / RAW_STAGES);
+      const uint8_t* const src = sm + OFF_RAW + slot * RAW_SLOT;
+      mbar_wait(bar_raw_full + 8 * slot, raw_use & 1u);
+      if (u > 0) mbar_wait(bar_empty + 8 * g, (uint32_t)(u - 1) & 1u);
+      // stage: dYh blocks | dYl blocks | Xh blocks | Xl blocks; raw slot: dY blocks | X blocks
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (b < nba) {
+          const float4 v = *reinterpret_cast<const float4*>(src + (uint32_t)b * BLOCK + src_off);
+          bsum[b][0] += v.x; bsum[b][1] += v.y; bsum[b][2] += v.z; bsum[b][3] += v.w;
+          float4 h, l;
+          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+          *reinterpret_cast<float4*>(stage + (uint32_t)b * BLOCK + dst_off) = h;
+          *reinterpret_cast<float4*>(stage + (uint32_t)(nba + b) * BLOCK + dst_off) = l;
+        }
+      }
+      for (int b = 0; b < nbb; ++b) {
+        const float4 v = *reinterpret_cast<const float4*>(src + (uint32_t)(nba + b) * BLOCK + src_off);
+        float4 h, l;
+        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        *reinterpret_cast<float4*>(stage + (uint32_t)(2 * nba + b) * BLOCK + dst_off) = h;
+        *reinterpret_cast<float4*>(stage + (uint32_t)(2 * nba + nbb + b) * BLOCK + dst_off) = l;
+      }
+      fence_async_smem();
+      mbar_arrive(bar_full + 8 * g);
+      mbar_arrive(bar_raw_empty + 8 * slot);
+    }
+    if (a.db) {
+      float* const dbs = reinterpret_cast<float*>(sm + OFF_DB);
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        if (b < nba)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) atomicAdd(dbs + 32 * b + 4 * (int)p + i, bsum[b][i]);
+    }
+  } else if (warp == 13) {
+    // ======================================================================== TMA producer (one thread)
+    if (lane == 0) {
+      for (int64_t item = 0; item < items; ++item) {
+        const uint32_t slot = (uint32_t)(item % RAW_STAGES), raw_use = (uint32_t)(item / RAW_STAGES);
+        if (raw_use > 0) mbar_wait(bar_raw_empty + 8 * slot, (raw_use - 1) & 1u);
+        const int row0 = (int)((c_begin + item) * CHUNK_ROWS);
+        const uint32_t dst = base + OFF_RAW + slot * RAW_SLOT, bar = bar_raw_full + 8 * slot;
+        mbar_expect_tx(bar, RAW_SLOT);
+        for (int b = 0; b < nba; ++b) tma_load_2d(dst + (uint32_t)b * BLOCK, &tmap_dy, bar, 32 * b, row0);
+        for (int b = 0; b < nbb; ++b) tma_load_2d(dst + (uint32_t)(nba + b) * BLOCK, &tmap_x, bar, 32 * b, row0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 12) {
+    // ======================================================================== MMA issue (whole warp, one elected lane issues)
+    const uint32_t idesc = wg_idesc(a.k);
+    int64_t item = 0;
+    for (int64_t w = 0; w < windows; ++w) {
+      const uint32_t acc = (uint32_t)(w & 1), acc_use = (uint32_t)(w >> 1);
+      if (acc_use > 0) mbar_wait(bar_acc_empty + 8 * acc, (acc_use - 1) & 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)a.k;
+      const int64_t w_end = (w + 1) * FLUSH_CHUNKS < items ? (w + 1) * FLUSH_CHUNKS : items;
+      for (int first = 1; item < w_end; ++item, first = 0) {
+        const uint32_t st = (uint32_t)(item & 1);
+        mbar_wait(bar_full + 8 * st, (uint32_t)(item >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t s0 = base + OFF_A + st * STAGE;
+        const uint64_t dyh = mn_desc(s0), dyl = mn_desc(s0 + (uint32_t)nba * BLOCK);
+        const uint64_t xh = mn_desc(s0 + 2u * (uint32_t)nba * BLOCK), xl = mn_desc(s0 + (2u * (uint32_t)nba + (uint32_t)nbb) * BLOCK);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < CHUNK_ROWS / 8; ++ks) {
+            const uint64_t dk = (uint64_t)(64 * ks);             // the next 8-row atom: 1024 B = 64 units of the address field
+            umma_tf32(tmem_d, dyl + dk, xh + dk, idesc, (first && ks == 0) ? 0u : 1u);
+            umma_tf32(tmem_d, dyh + dk, xl + dk, idesc, 1u);
+            umma_tf32(tmem_d, dyh + dk, xh + dk, idesc, 1u);
+          }
+          umma_commit(bar_empty + 8 * st);
+          if (item == w_end - 1) umma_commit(bar_acc_full + 8 * acc);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ======================================================================== read-out (warps 8-11: thread = output feature n)
+    const int n = (warp - 8) * 32 + lane;
+    const bool live_warp = (warp - 8) * 32 < a.n;                // out is a multiple of 32: a warp is all live or all idle
+    float* const prow = reinterpret_cast<float*>(sm + OFF_PART + (uint32_t)(live_warp ? n : 0) * PROW);
+    for (int64_t w = 0; w < windows; ++w) {
+      const uint32_t acc = (uint32_t)(w & 1), acc_use = (uint32_t)(w >> 1);
+      mbar_wait(bar_acc_full + 8 * acc, acc_use & 1u);
+      tc_fence_after();
+      if (live_warp) {
+        for (int c0 = 0; c0 < a.k; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + acc * (uint32_t)a.k + ((uint32_t)((warp - 8) * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 s = *reinterpret_cast<float4*>(prow + c0 + 4 * q);
+            s.x += v[4 * q]; s.y += v[4 * q + 1]; s.z += v[4 * q + 2]; s.w += v[4 * q + 3];
+            *reinterpret_cast<float4*>(prow + c0 + 4 * q) = s;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_acc_empty + 8 * acc);
+    }
+    if (live_warp && windows > 0)
+      for (int c = 0; c < a.k; ++c) atomicAdd(a.dw + (size_t)n * a.k + c, prow[c]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (a.db && tid < a.n && items > 0) atomicAdd(a.db + tid, reinterpret_cast<float*>(sm + OFF_DB)[tid]);
+  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
+}
+
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+size_t wg_smem_needed(int k, int n) {
+  const size_t nb = (size_t)(k + n) / 32;
+  return GROUPS * 2 * nb * BLOCK + RAW_STAGES * nb * BLOCK + (size_t)n * (k + 4) * 4 + (size_t)n * 4 + 16 + BAR_BYTES;
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool make_map(EncodeFn encode, CUtensorMap* map, const float* p, int64_t rows, int cols) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {32, (cuuint32_t)CHUNK_ROWS}, estride[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+extern "C" int f16_lma_linear_wgrad_tc_supported(int in_features, int out_features) {
+  if (out_features < 32 || out_features > 128 || out_features % 32) return 0;
+  if (in_features < 32 || in_features > 160 || in_features % 32) return 0;
+  return wg_smem_needed(in_features, out_features) + 1024 <= SMEM_LIMIT ? 1 : 0;
+}
+
+extern "C" int f16_lma_linear_wgrad_tc(int64_t rows, int in_features, int out_features, const float* x, const float* dy, float* dweight,
+                                       float* dbias, void* stream) {
+  if (rows <= 0) return f16_internal_fail("f16_lma_linear_wgrad_tc: rows must be positive");
+  if (!x || !dy || !dweight) return f16_internal_fail("f16_lma_linear_wgrad_tc: NULL pointer");
+  if (!f16_lma_linear_wgrad_tc_supported(in_features, out_features))
+    return f16_internal_fail("f16_lma_linear_wgrad_tc: unsupported shape (out features 32..128 and in features 32..160, multiples of 32, partial sums must fit shared memory)");
+  if ((((uintptr_t)x) | ((uintptr_t)dy)) & 15) return f16_internal_fail("f16_lma_linear_wgrad_tc: x and dy must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(dweight, 0, (size_t)in_features * out_features * sizeof(float), st) != cudaSuccess)
+    return f16_internal_fail("f16_lma_linear_wgrad_tc: memset failed");
+  if (dbias && cudaMemsetAsync(dbias, 0, (size_t)out_features * sizeof(float), st) != cudaSuccess)
+    return f16_internal_fail("f16_lma_linear_wgrad_tc: memset failed");
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess)
+      return f16_internal_fail("f16_lma_linear_wgrad_tc: the driver does not export cuTensorMapEncodeTiled");
+    encode = (EncodeFn)fn;
+  }
+  alignas(64) CUtensorMap map_x, map_dy;
+  if (!make_map(encode, &map_x, x, rows, in_features) || !make_map(encode, &map_dy, dy, rows, out_features))
+    return f16_internal_fail("f16_lma_linear_wgrad_tc: cuTensorMapEncodeTiled failed");
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+  }
+  WgArgs a;
+  a.dw = dweight; a.db = dbias;
+  a.rows = rows; a.chunks = (rows + CHUNK_ROWS - 1) / CHUNK_ROWS;
+  a.k = in_features; a.n = out_features;
+  // contiguous slabs, a whole number of read-out windows per CTA
+  int64_t per = (a.chunks + sms - 1) / sms;
+  per = (per + FLUSH_CHUNKS - 1) / FLUSH_CHUNKS * FLUSH_CHUNKS;
+  a.chunks_per_cta = per;
+  const int64_t grid = (a.chunks + per - 1) / per;
+  a.tmem_cols = 32;
+  while ((int)a.tmem_cols < 2 * in_features) a.tmem_cols *= 2;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) != cudaSuccess)
+      return f16_internal_fail("f16_lma_linear_wgrad_tc: cannot raise the shared-memory limit");
+    attr_done = true;
+  }
+  const size_t smem = wg_smem_needed(a.k, a.n) + 1024;
+  wgrad_tc_kernel<<<(unsigned)grid, THREADS, smem, st>>>(a, map_x, map_dy);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return f16_internal_fail(cudaGetErrorString(e));
+  f16_internal_count_launch();
+  return 0;
+}

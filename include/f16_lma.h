@@ -59,6 +59,17 @@ int f16_lma_linear_wgrad(int64_t rows, int in_features, int out_features, const 
 int f16_lma_linear_supported(int in_features, int out_features);
 int f16_lma_linear_forward(int64_t rows, int in_features, int out_features, const float* x, const float* weight,
                            const float* bias, float* y, void* stream);
+
+/* The same weight / bias gradients on the tensor cores (csrc/f16_lma_wgrad_tc.cu): D[out][in] accumulates in tensor memory
+ * over 16-row chunks of dy and x (tcgen05.mma kind::tf32 on MN-major operands, TF32 head / remainder split: three MMAs
+ * per 8 rows), is read out and restarted every 256 rows so that the tensor core's truncating accumulation never runs
+ * long, and the CTAs' partial results meet in float atomics on the zero-initialised outputs. Same arguments and
+ * semantics as f16_lma_linear_wgrad; x and dy 16-byte aligned. Built for out_features in {32, 64, 96, 128} and
+ * in_features a multiple of 32 up to 160 whose partial sums fit shared memory (f16_lma_linear_wgrad_tc_supported); the
+ * caller keeps f16_lma_linear_wgrad for the rest (17 input features, the 4- and 1-wide heads, 160 -> 128). */
+int f16_lma_linear_wgrad_tc_supported(int in_features, int out_features);
+int f16_lma_linear_wgrad_tc(int64_t rows, int in_features, int out_features, const float* x, const float* dy, float* dweight,
+                            float* dbias, void* stream);
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@
 //     accumulator is read out and restarted every 256 rows (96 MMAs): the partial results are summed in FP32 with
 //     round-to-nearest in a per-thread row of shared memory, and meet the other CTAs in float atomics on the
 //     zero-initialised output at the end (as the slab kernel does).
-//   * roles as in f16_lma_linear.cu: TMA producer (two tensor maps, boxes of 16 rows x 32 floats, a four-chunk ring),
+//   * roles as in f16_lma_linear.cu: TMA producer (two tensor maps, one box of 16-64 rows x all features each per chunk),
 //     two converter groups (split into head / remainder, swizzled stores, column sums of dY for the bias gradient on
 //     the way), one MMA warp (uniform descriptors, one elected lane), four read-out warps (tcgen05.ld 32x32b; a thread
 //     = an output feature n), two accumulators alternating in tensor memory.
@@ -34,16 +34,21 @@ extern "C" void f16_internal_count_launch(void);
 
 namespace {
 using namespace f16tc;
-constexpr int CHUNK_ROWS = 16, LOADERS = 128, GROUPS = 2, THREADS = GROUPS * LOADERS + 128 + 32 + 32;
-constexpr int FLUSH_CHUNKS = 16;                        // accumulator read out every 16 chunks = 256 rows
-constexpr int RAW_STAGES = 4;
-constexpr uint32_t BLOCK = CHUNK_ROWS * 128;            // 2 KB: 16 rows x 32 floats
+constexpr int LOADERS = 128, GROUPS = 2, THREADS = GROUPS * LOADERS + 128 + 32 + 32;
+constexpr int FLUSH_ROWS = 256;                         // the accumulator is read out and restarted every 256 rows
+constexpr int MAX_RAW_STAGES = 4, MAX_A_STAGES = 2 * GROUPS;
 constexpr uint32_t BAR_BYTES = 192;
+constexpr size_t SMEM_LIMIT = 227 * 1024;
 
 struct WgArgs {
   float* dw; float* db;
   int64_t rows, chunks, chunks_per_cta;
   int k, n;                // in / out features
+  int fm, fn;              // features on the M side (accumulator lanes) and on the N side (accumulator columns) of the product
+  int spg;                 // operand stages per converter group (1 or 2)
+  int raw_stages;          // chunks in the TMA ring (2..4)
+  int swap;                // 0: D[n][k] = dY^T X (M side = dY); 1: D[k][n] = X^T dY (M side = X), chosen when in > out: the M side
+                           // is always padded to 128 lanes, so the wider operand goes there
   uint32_t tmem_cols;
 };
 
@@ -51,52 +56,58 @@ struct WgArgs {
 // 128 B = 32 MN-elements, atoms of four rows, the 32-byte pieces of a row XOR-ed with the row index mod 4. Start address
 // >> 4; leading byte offset = distance between 32-element blocks along MN (one BLOCK); stride byte offset = distance
 // between four-row atoms along K (512 B); descriptor version 1
-__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr, uint32_t block_bytes) {
   const uint32_t hi = 32u | (1u << 14) | (1u << 29);
-  return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | ((BLOCK >> 4) << 16));
+  return ((uint64_t)hi << 32) | (uint64_t)(((saddr >> 4) & 0x3FFFu) | ((block_bytes >> 4) << 16));
 }
-// kind::tf32, D = F32, A = B = TF32, both MN-major (bits 15, 16), N = in features, M = 128
-__device__ __forceinline__ uint32_t wg_idesc(int k) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(k >> 3) << 17) | (8u << 24);
+// kind::tf32, D = F32, A = B = TF32, both MN-major (bits 15, 16), N = N-side features, M = 128
+__device__ __forceinline__ uint32_t wg_idesc(int fn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(fn >> 3) << 17) | (8u << 24);
 }
 
-__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgArgs a, const __grid_constant__ CUtensorMap tmap_x,
-                                                              const __grid_constant__ CUtensorMap tmap_dy) {
+// ROWS = rows per chunk (16, 32 or 64: the per-chunk hand-offs cost ~650 cycles whatever the chunk holds, so a chunk should be
+// 16-20 KB; the host picks the largest that fits shared memory)
+template <int ROWS>
+__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgArgs a, const __grid_constant__ CUtensorMap tmap_m,
+                                                              const __grid_constant__ CUtensorMap tmap_n) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw0 = smem_u32(smem_raw);
   const uint32_t base = (raw0 + 1023u) & ~1023u;
   uint8_t* const sm = smem_raw + (base - raw0);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nba = a.n >> 5, nbb = a.k >> 5, nb = nba + nbb;      // 32-float blocks of dY, of X, per chunk
-  // shared memory: [operand stages: per stage dYh | dYl | Xh | Xl blocks] [TMA ring: per slot dY blocks | X blocks]
-  // [partial sums: n rows of k + 4 floats] [bias sums: n floats] [barriers]
+  constexpr uint32_t BLOCK = ROWS * 128;                         // ROWS rows x 32 floats
+  constexpr int FLUSH_CHUNKS = FLUSH_ROWS / ROWS;
+  const int A_STAGES = GROUPS * a.spg, RAW_STAGES = a.raw_stages;
+  const int nbm = a.fm >> 5, nbn = a.fn >> 5, nb = nbm + nbn;    // 32-float blocks of the M side, of the N side, per chunk
+  // shared memory: [operand stages, two per converter group: Mh | Ml | Nh | Nl blocks] [TMA ring: per slot M blocks | N blocks]
+  // [partial sums: fm rows of fn + 4 floats] [bias sums: n floats] [barriers]
   const uint32_t STAGE = 2u * (uint32_t)nb * BLOCK, RAW_SLOT = (uint32_t)nb * BLOCK;
-  const uint32_t OFF_A = 0, OFF_RAW = GROUPS * STAGE, OFF_PART = OFF_RAW + RAW_STAGES * RAW_SLOT;
-  const uint32_t PROW = (uint32_t)(a.k + 4) * 4u;                // bytes per partial row (16 B of padding: conflict-free)
-  const uint32_t OFF_DB = OFF_PART + (uint32_t)a.n * PROW, OFF_BAR = (OFF_DB + (uint32_t)a.n * 4u + 15u) & ~15u;
+  const uint32_t OFF_A = 0, OFF_RAW = (uint32_t)A_STAGES * STAGE, OFF_PART = OFF_RAW + (uint32_t)RAW_STAGES * RAW_SLOT;
+  const uint32_t PROW = (uint32_t)(a.fn + 4) * 4u;               // bytes per partial row (16 B of padding: conflict-free)
+  const uint32_t OFF_DB = OFF_PART + (uint32_t)a.fm * PROW, OFF_BAR = (OFF_DB + (uint32_t)a.n * 4u + 15u) & ~15u;
   {
     uint32_t dyn;
     asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
     if ((base - raw0) + OFF_BAR + BAR_BYTES > dyn) __trap();
   }
+  // barriers: full[4], empty[4] (operand stages), acc_full[2], acc_empty[2], raw_full[4], raw_empty[4]; tensor-memory address
   const uint32_t sBar = base + OFF_BAR;
-  const uint32_t bar_full = sBar, bar_empty = sBar + 16, bar_acc_full = sBar + 32, bar_acc_empty = sBar + 48, bar_raw_full = sBar + 64,
-                 bar_raw_empty = sBar + 96, tmem_holder = sBar + 128;
-  volatile uint32_t* const tmem_holder_p = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 128);
+  const uint32_t bar_full = sBar, bar_empty = sBar + 32, bar_acc_full = sBar + 64, bar_acc_empty = sBar + 80, bar_raw_full = sBar + 96,
+                 bar_raw_empty = sBar + 128, tmem_holder = sBar + 160;
+  volatile uint32_t* const tmem_holder_p = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 160);
 
   if (tid == 0) {
-    for (int s = 0; s < GROUPS; ++s) { mbar_init(bar_full + 8 * s, LOADERS); mbar_init(bar_empty + 8 * s, 1); }
+    for (int s = 0; s < MAX_A_STAGES; ++s) { mbar_init(bar_full + 8 * s, LOADERS); mbar_init(bar_empty + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(bar_acc_full + 8 * s, 1); mbar_init(bar_acc_empty + 8 * s, 128); }
-    for (int s = 0; s < RAW_STAGES; ++s) { mbar_init(bar_raw_full + 8 * s, 1); mbar_init(bar_raw_empty + 8 * s, LOADERS); }
+    for (int s = 0; s < MAX_RAW_STAGES; ++s) { mbar_init(bar_raw_full + 8 * s, 1); mbar_init(bar_raw_empty + 8 * s, LOADERS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_holder), "r"(a.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // partial sums and bias sums start at zero; the operand stages too (the descriptor of dY always spans four blocks:
-  // what it reads past out/32 blocks only reaches accumulator lanes that are never read, but must not be NaN-producing
-  // garbage for compute-sanitizer's sake)
+  // partial sums and bias sums start at zero; the operand stages too (the M-side descriptor always spans four blocks: what
+  // it reads past fm/32 blocks only reaches accumulator lanes that are never read)
   for (uint32_t o = tid * 16u; o < OFF_PART; o += THREADS * 16u) *reinterpret_cast<float4*>(sm + o) = make_float4(0.f, 0.f, 0.f, 0.f);
   for (uint32_t o = OFF_PART + tid * 4u; o < OFF_BAR; o += THREADS * 4u) *reinterpret_cast<float*>(sm + o) = 0.f;
   tc_fence_before();
@@ -116,9 +127,13 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgArgs a, co
     // ======================================================================== converters
     const int g = warp >> 2, t = tid & (LOADERS - 1);
     const int64_t my_items = items > g ? (items - g + 1) / 2 : 0;
-    uint8_t* const stage = sm + OFF_A + (uint32_t)g * STAGE;
-    const uint32_t m = (uint32_t)(t >> 3), p = (uint32_t)(t & 7);             // row of the chunk, 16-byte piece of the block row
-    const uint32_t src_off = m * 128u + p * 16u, dst_off = m * 128u + ((((p >> 1) ^ m) & 3u) << 5) + ((p & 1u) << 4);
+    const uint32_t m = (uint32_t)(t >> 3), p = (uint32_t)(t & 7);             // rows m + 16 r of the chunk, 16-byte piece of the block row
+    const uint32_t dst_off = m * 128u + ((((p >> 1) ^ m) & 3u) << 5) + ((p & 1u) << 4);
+    // the TMA ring holds the two activations row-major: [ROWS][fm] then [ROWS][fn] floats (one wide box each: TMA moves a
+    // box row by row, and 128-byte rows - one 32-float block per box - could not keep up with HBM)
+    const uint32_t pitch_m = (uint32_t)a.fm * 4u, pitch_n = (uint32_t)a.fn * 4u, raw_n = (uint32_t)ROWS * pitch_m;
+    constexpr int RPT = ROWS / 16;                                            // rows per thread per block
+    const bool dy_m = a.swap == 0;                                            // dY is the M side
     float bsum[4][4];                                                         // column sums of dY: block b, columns 4 p ..
 #pragma unroll
     for (int b = 0; b < 4; ++b)
@@ -127,37 +142,51 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgArgs a, co
     for (int64_t u = 0; u < my_items; ++u) {
       const int64_t item = 2 * u + g;
       const uint32_t slot = (uint32_t)(item % RAW_STAGES), raw_use = (uint32_t)(item / RAW_STAGES);
+      const uint32_t st = a.spg == 2 ? 2u * (uint32_t)g + (uint32_t)(u & 1) : (uint32_t)g;
+      const uint32_t use = a.spg == 2 ? (uint32_t)(u >> 1) : (uint32_t)u;
       const uint8_t* const src = sm + OFF_RAW + slot * RAW_SLOT;
+      uint8_t* const stage = sm + OFF_A + st * STAGE;
       mbar_wait(bar_raw_full + 8 * slot, raw_use & 1u);
-      if (u > 0) mbar_wait(bar_empty + 8 * g, (uint32_t)(u - 1) & 1u);
-      // stage: dYh blocks | dYl blocks | Xh blocks | Xl blocks; raw slot: dY blocks | X blocks
+      if (use > 0) mbar_wait(bar_empty + 8 * st, (use - 1) & 1u);             // the MMAs that read this stage are done
+      // stage: Mh blocks | Ml blocks | Nh blocks | Nl blocks; raw slot: M blocks | N blocks
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        if (b < nba) {
-          const float4 v = *reinterpret_cast<const float4*>(src + (uint32_t)b * BLOCK + src_off);
-          bsum[b][0] += v.x; bsum[b][1] += v.y; bsum[b][2] += v.z; bsum[b][3] += v.w;
-          float4 h, l;
-          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-          *reinterpret_cast<float4*>(stage + (uint32_t)b * BLOCK + dst_off) = h;
-          *reinterpret_cast<float4*>(stage + (uint32_t)(nba + b) * BLOCK + dst_off) = l;
+        if (b < nbm) {
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (m + 16u * r) * pitch_m + (uint32_t)b * 128u + p * 16u);
+            if (dy_m) { bsum[b][0] += v.x; bsum[b][1] += v.y; bsum[b][2] += v.z; bsum[b][3] += v.w; }
+            float4 h, l;
+            split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+            *reinterpret_cast<float4*>(stage + (uint32_t)b * BLOCK + dst_off + 2048u * r) = h;
+            *reinterpret_cast<float4*>(stage + (uint32_t)(nbm + b) * BLOCK + dst_off + 2048u * r) = l;
+          }
         }
       }
-      for (int b = 0; b < nbb; ++b) {
-        const float4 v = *reinterpret_cast<const float4*>(src + (uint32_t)(nba + b) * BLOCK + src_off);
-        float4 h, l;
-        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-        *reinterpret_cast<float4*>(stage + (uint32_t)(2 * nba + b) * BLOCK + dst_off) = h;
-        *reinterpret_cast<float4*>(stage + (uint32_t)(2 * nba + nbb + b) * BLOCK + dst_off) = l;
+#pragma unroll
+      for (int b = 0; b < 5; ++b) {
+        if (b < nbn) {
+#pragma unroll
+          for (int r = 0; r < RPT; ++r) {
+            const float4 v = *reinterpret_cast<const float4*>(src + raw_n + (m + 16u * r) * pitch_n + (uint32_t)b * 128u + p * 16u);
+            if (!dy_m && b < 4) { bsum[b & 3][0] += v.x; bsum[b & 3][1] += v.y; bsum[b & 3][2] += v.z; bsum[b & 3][3] += v.w; }
+            float4 h, l;
+            split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+            *reinterpret_cast<float4*>(stage + (uint32_t)(2 * nbm + b) * BLOCK + dst_off + 2048u * r) = h;
+            *reinterpret_cast<float4*>(stage + (uint32_t)(2 * nbm + nbn + b) * BLOCK + dst_off + 2048u * r) = l;
+          }
+        }
       }
       fence_async_smem();
-      mbar_arrive(bar_full + 8 * g);
+      mbar_arrive(bar_full + 8 * st);
       mbar_arrive(bar_raw_empty + 8 * slot);
     }
     if (a.db) {
       float* const dbs = reinterpret_cast<float*>(sm + OFF_DB);
+      const int nby = a.n >> 5;
 #pragma unroll
       for (int b = 0; b < 4; ++b)
-        if (b < nba)
+        if (b < nby)
 #pragma unroll
           for (int i = 0; i < 4; ++i) atomicAdd(dbs + 32 * b + 4 * (int)p + i, bsum[b][i]);
     }
@@ -167,38 +196,39 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgArgs a, co
       for (int64_t item = 0; item < items; ++item) {
         const uint32_t slot = (uint32_t)(item % RAW_STAGES), raw_use = (uint32_t)(item / RAW_STAGES);
         if (raw_use > 0) mbar_wait(bar_raw_empty + 8 * slot, (raw_use - 1) & 1u);
-        const int row0 = (int)((c_begin + item) * CHUNK_ROWS);
+        const int row0 = (int)((c_begin + item) * ROWS);
         const uint32_t dst = base + OFF_RAW + slot * RAW_SLOT, bar = bar_raw_full + 8 * slot;
         mbar_expect_tx(bar, RAW_SLOT);
-        for (int b = 0; b < nba; ++b) tma_load_2d(dst + (uint32_t)b * BLOCK, &tmap_dy, bar, 32 * b, row0);
-        for (int b = 0; b < nbb; ++b) tma_load_2d(dst + (uint32_t)(nba + b) * BLOCK, &tmap_x, bar, 32 * b, row0);
+        tma_load_2d(dst, &tmap_m, bar, 0, row0);
+        tma_load_2d(dst + (uint32_t)nbm * BLOCK, &tmap_n, bar, 0, row0);
       }
     }
     __syncwarp();
   } else if (warp == 12) {
     // ======================================================================== MMA issue (whole warp, one elected lane issues)
-    const uint32_t idesc = wg_idesc(a.k);
+    const uint32_t idesc = wg_idesc(a.fn);
     int64_t item = 0;
     for (int64_t w = 0; w < windows; ++w) {
       const uint32_t acc = (uint32_t)(w & 1), acc_use = (uint32_t)(w >> 1);
       if (acc_use > 0) mbar_wait(bar_acc_empty + 8 * acc, (acc_use - 1) & 1u);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * (uint32_t)a.k;
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)a.fn;
       const int64_t w_end = (w + 1) * FLUSH_CHUNKS < items ? (w + 1) * FLUSH_CHUNKS : items;
       for (int first = 1; item < w_end; ++item, first = 0) {
-        const uint32_t st = (uint32_t)(item & 1);
-        mbar_wait(bar_full + 8 * st, (uint32_t)(item >> 1) & 1u);
+        const int64_t u = item >> 1;                             // chunk u of converter group item & 1
+        const uint32_t st = a.spg == 2 ? 2u * (uint32_t)(item & 1) + (uint32_t)(u & 1) : (uint32_t)(item & 1);
+        mbar_wait(bar_full + 8 * st, (uint32_t)(a.spg == 2 ? (u >> 1) : u) & 1u);
         tc_fence_after();
         const uint32_t s0 = base + OFF_A + st * STAGE;
-        const uint64_t dyh = mn_desc(s0), dyl = mn_desc(s0 + (uint32_t)nba * BLOCK);
-        const uint64_t xh = mn_desc(s0 + 2u * (uint32_t)nba * BLOCK), xl = mn_desc(s0 + (2u * (uint32_t)nba + (uint32_t)nbb) * BLOCK);
+        const uint64_t mh = mn_desc(s0, BLOCK), ml = mn_desc(s0 + (uint32_t)nbm * BLOCK, BLOCK);
+        const uint64_t nh = mn_desc(s0 + 2u * (uint32_t)nbm * BLOCK, BLOCK), nl = mn_desc(s0 + (2u * (uint32_t)nbm + (uint32_t)nbn) * BLOCK, BLOCK);
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < CHUNK_ROWS / 8; ++ks) {
-            const uint64_t dk = (uint64_t)(64 * ks);             // the next 8-row atom: 1024 B = 64 units of the address field
-            umma_tf32(tmem_d, dyl + dk, xh + dk, idesc, (first && ks == 0) ? 0u : 1u);
-            umma_tf32(tmem_d, dyh + dk, xl + dk, idesc, 1u);
-            umma_tf32(tmem_d, dyh + dk, xh + dk, idesc, 1u);
+          for (int ks = 0; ks < ROWS / 8; ++ks) {
+            const uint64_t dk = (uint64_t)(64 * ks);             // the next 8 rows: 1024 B = 64 units of the address field
+            umma_tf32(tmem_d, ml + dk, nh + dk, idesc, (first && ks == 0) ? 0u : 1u);
+            umma_tf32(tmem_d, mh + dk, nl + dk, idesc, 1u);
+            umma_tf32(tmem_d, mh + dk, nh + dk, idesc, 1u);
           }
           umma_commit(bar_empty + 8 * st);
           if (item == w_end - 1) umma_commit(bar_acc_full + 8 * acc);
@@ -207,18 +237,18 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgArgs a, co
       }
     }
   } else {
-    // ======================================================================== read-out (warps 8-11: thread = output feature n)
-    const int n = (warp - 8) * 32 + lane;
-    const bool live_warp = (warp - 8) * 32 < a.n;                // out is a multiple of 32: a warp is all live or all idle
-    float* const prow = reinterpret_cast<float*>(sm + OFF_PART + (uint32_t)(live_warp ? n : 0) * PROW);
+    // ======================================================================== read-out (warps 8-11: thread = M-side feature i)
+    const int i = (warp - 8) * 32 + lane;
+    const bool live_warp = (warp - 8) * 32 < a.fm;               // fm is a multiple of 32: a warp is all live or all idle
+    float* const prow = reinterpret_cast<float*>(sm + OFF_PART + (uint32_t)(live_warp ? i : 0) * PROW);
     for (int64_t w = 0; w < windows; ++w) {
       const uint32_t acc = (uint32_t)(w & 1), acc_use = (uint32_t)(w >> 1);
       mbar_wait(bar_acc_full + 8 * acc, acc_use & 1u);
       tc_fence_after();
       if (live_warp) {
-        for (int c0 = 0; c0 < a.k; c0 += 32) {
+        for (int c0 = 0; c0 < a.fn; c0 += 32) {
           float v[32];
-          tmem_ld32(tmem_base + acc * (uint32_t)a.k + ((uint32_t)((warp - 8) * 32) << 16) + (uint32_t)c0, v);
+          tmem_ld32(tmem_base + acc * (uint32_t)a.fn + ((uint32_t)((warp - 8) * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             float4 s = *reinterpret_cast<float4*>(prow + c0 + 4 * q);
@@ -230,8 +260,10 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgArgs a, co
       tc_fence_before();
       mbar_arrive(bar_acc_empty + 8 * acc);
     }
-    if (live_warp && windows > 0)
-      for (int c = 0; c < a.k; ++c) atomicAdd(a.dw + (size_t)n * a.k + c, prow[c]);
+    if (live_warp && windows > 0) {
+      if (a.swap) for (int j = 0; j < a.fn; ++j) atomicAdd(a.dw + (size_t)j * a.k + i, prow[j]);       // D[k][n] -> dW[n][k]
+      else        for (int j = 0; j < a.fn; ++j) atomicAdd(a.dw + (size_t)i * a.k + j, prow[j]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -239,18 +271,30 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const WgArgs a, co
   if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(a.tmem_cols) : "memory");
 }
 
-constexpr size_t SMEM_LIMIT = 227 * 1024;
-size_t wg_smem_needed(int k, int n) {
+bool wg_swap(int k, int n) { return k > n && k <= 128; }
+struct WgPlan { int rows, spg, raw; size_t smem; };
+// the largest chunk, then the deepest rings, that fit shared memory (with 1 KB of alignment slack)
+bool wg_plan(int k, int n, WgPlan* plan) {
   const size_t nb = (size_t)(k + n) / 32;
-  return GROUPS * 2 * nb * BLOCK + RAW_STAGES * nb * BLOCK + (size_t)n * (k + 4) * 4 + (size_t)n * 4 + 16 + BAR_BYTES;
+  const size_t fm = wg_swap(k, n) ? k : n, fn = wg_swap(k, n) ? n : k;
+  const size_t fixed = fm * (fn + 4) * 4 + (size_t)n * 4 + 16 + BAR_BYTES + 1024;
+  static const int opts[6][2] = {{2, 4}, {2, 3}, {1, 4}, {2, 2}, {1, 3}, {1, 2}};
+  for (int rows = 64; rows >= 16; rows /= 2) {
+    if ((size_t)rows * nb * 128 > 24 * 1024 && rows > 16) continue;   // a chunk of 16-24 KB is enough
+    for (const auto& o : opts) {
+      const size_t need = (size_t)GROUPS * o[0] * 2 * nb * rows * 128 + (size_t)o[1] * nb * rows * 128 + fixed;
+      if (need <= SMEM_LIMIT) { plan->rows = rows; plan->spg = o[0]; plan->raw = o[1]; plan->smem = need; return true; }
+    }
+  }
+  return false;
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-bool make_map(EncodeFn encode, CUtensorMap* map, const float* p, int64_t rows, int cols) {
+bool make_map(EncodeFn encode, CUtensorMap* map, const float* p, int64_t rows, int cols, int box_rows) {
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float)};
-  const cuuint32_t box[2] = {32, (cuuint32_t)CHUNK_ROWS}, estride[2] = {1, 1};
+  const cuuint32_t box[2] = {(cuuint32_t)cols, (cuuint32_t)box_rows}, estride[2] = {1, 1};
   return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(p), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -259,7 +303,8 @@ bool make_map(EncodeFn encode, CUtensorMap* map, const float* p, int64_t rows, i
 extern "C" int f16_lma_linear_wgrad_tc_supported(int in_features, int out_features) {
   if (out_features < 32 || out_features > 128 || out_features % 32) return 0;
   if (in_features < 32 || in_features > 160 || in_features % 32) return 0;
-  return wg_smem_needed(in_features, out_features) + 1024 <= SMEM_LIMIT ? 1 : 0;
+  WgPlan plan;
+  return wg_plan(in_features, out_features, &plan) ? 1 : 0;
 }
 
 extern "C" int f16_lma_linear_wgrad_tc(int64_t rows, int in_features, int out_features, const float* x, const float* dy, float* dweight,
@@ -282,8 +327,10 @@ extern "C" int f16_lma_linear_wgrad_tc(int64_t rows, int in_features, int out_fe
       return f16_internal_fail("f16_lma_linear_wgrad_tc: the driver does not export cuTensorMapEncodeTiled");
     encode = (EncodeFn)fn;
   }
+  WgPlan plan;
+  wg_plan(in_features, out_features, &plan);
   alignas(64) CUtensorMap map_x, map_dy;
-  if (!make_map(encode, &map_x, x, rows, in_features) || !make_map(encode, &map_dy, dy, rows, out_features))
+  if (!make_map(encode, &map_x, x, rows, in_features, plan.rows) || !make_map(encode, &map_dy, dy, rows, out_features, plan.rows))
     return f16_internal_fail("f16_lma_linear_wgrad_tc: cuTensorMapEncodeTiled failed");
   static int sms = 0;
   if (!sms) {
@@ -293,23 +340,29 @@ extern "C" int f16_lma_linear_wgrad_tc(int64_t rows, int in_features, int out_fe
   }
   WgArgs a;
   a.dw = dweight; a.db = dbias;
-  a.rows = rows; a.chunks = (rows + CHUNK_ROWS - 1) / CHUNK_ROWS;
+  a.rows = rows; a.chunks = (rows + plan.rows - 1) / plan.rows;
   a.k = in_features; a.n = out_features;
+  a.spg = plan.spg; a.raw_stages = plan.raw;
   // contiguous slabs, a whole number of read-out windows per CTA
+  const int flush_chunks = FLUSH_ROWS / plan.rows;
   int64_t per = (a.chunks + sms - 1) / sms;
-  per = (per + FLUSH_CHUNKS - 1) / FLUSH_CHUNKS * FLUSH_CHUNKS;
+  per = (per + flush_chunks - 1) / flush_chunks * flush_chunks;
   a.chunks_per_cta = per;
   const int64_t grid = (a.chunks + per - 1) / per;
+  a.swap = wg_swap(in_features, out_features) ? 1 : 0;
+  a.fm = a.swap ? in_features : out_features;
+  a.fn = a.swap ? out_features : in_features;
   a.tmem_cols = 32;
-  while ((int)a.tmem_cols < 2 * in_features) a.tmem_cols *= 2;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) != cudaSuccess)
+  while ((int)a.tmem_cols < 2 * a.fn) a.tmem_cols *= 2;
+  auto kern = plan.rows == 64 ? wgrad_tc_kernel<64> : (plan.rows == 32 ? wgrad_tc_kernel<32> : wgrad_tc_kernel<16>);
+  static bool attr_done[3] = {false, false, false};
+  const int ki = plan.rows == 64 ? 2 : (plan.rows == 32 ? 1 : 0);
+  if (!attr_done[ki]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT) != cudaSuccess)
       return f16_internal_fail("f16_lma_linear_wgrad_tc: cannot raise the shared-memory limit");
-    attr_done = true;
+    attr_done[ki] = true;
   }
-  const size_t smem = wg_smem_needed(a.k, a.n) + 1024;
-  wgrad_tc_kernel<<<(unsigned)grid, THREADS, smem, st>>>(a, map_x, map_dy);
+  kern<<<(unsigned)grid, THREADS, plan.smem, st>>>(a, a.swap ? map_x : map_dy, a.swap ? map_dy : map_x);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return f16_internal_fail(cudaGetErrorString(e));
   f16_internal_count_launch();

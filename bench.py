@@ -245,8 +245,8 @@ def amppo_iteration(dev, args):
             "value": n / (roll + upd), "unit": "env-steps/s per training iteration (rollout + 10-epoch update)",
             "episodes_finished": st["episodes"], "last_update": stats,
             "note": "hand-written: env step, rollout store + GAE + stack-rebuilding gather, feature transform, latent attention, LayerNorm, "
-                    "weight gradients, and the Linear layers' forward / input gradients on the tensor cores (tcgen05.mma kind::tf32 with split operands, "
-                    "FP32-accurate, csrc/f16_lma_linear.cu); library calls left: the 4- and 1-wide output heads, the 160 -> 128 value layer, "
+                    "and the Linear layers' forward, input and weight gradients on the tensor cores (tcgen05.mma kind::tf32 with split operands, "
+                    "FP32-accurate, csrc/f16_lma_linear.cu, csrc/f16_lma_wgrad_tc.cu); library calls left: the 4- and 1-wide output heads, the 160 -> 128 value layer, "
                     "elementwise activations / dropout, and the rollout's small-batch policy forward (DESIGN.md 4a)"}
 
 

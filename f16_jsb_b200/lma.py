@@ -180,6 +180,7 @@ def _linear_tc(x2: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
 
 
 _TC_SHAPES = {}
+_WG_SHAPES = {}
 
 
 def _tc_supported(in_features: int, out_features: int) -> bool:
@@ -190,6 +191,14 @@ def _tc_supported(in_features: int, out_features: int) -> bool:
     return _TC_SHAPES[key]
 
 
+def _wgrad_tc_supported(in_features: int, out_features: int) -> bool:
+    key = (in_features, out_features)
+    if key not in _WG_SHAPES:
+        from . import _lib
+        _WG_SHAPES[key] = bool(_lib.load().f16_lma_linear_wgrad_tc_supported(in_features, out_features))
+    return _WG_SHAPES[key]
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x W^T + b for the policy's tall-skinny layers (<= 160 features, 10^5..10^6 rows). Forward and input gradient
     (dx = dy W, the same kernel with W^T as the weight) run on the tensor cores with split TF32 operands
@@ -197,7 +206,8 @@ class _LinearFn(torch.autograd.Function):
     bias gradients, whose reduction axis is the batch, come from csrc/f16_lma_wgrad.cu (include/f16_lma.h). Shapes the
     tensor-core kernel does not build (the 4- and 1-wide output heads, 160 -> 128) stay torch matmuls."""
 
-    use_tc = os.environ.get("F16_LMA_TC", "1") != "0"        # class-wide switch (A/B measurements, tests)
+    use_tc = os.environ.get("F16_LMA_TC", "1") != "0"        # class-wide switches (A/B measurements, tests)
+    use_wgrad_tc = os.environ.get("F16_LMA_WGRAD_TC", "1") != "0"
 
     @staticmethod
     def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]):
@@ -233,10 +243,12 @@ class _LinearFn(torch.autograd.Function):
             dw = torch.empty_like(weight)
             db = torch.empty(weight.shape[0], dtype=weight.dtype, device=weight.device) if ctx.has_bias else None
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+            tc = (_LinearFn.use_wgrad_tc and _wgrad_tc_supported(k, n) and x2.data_ptr() % 16 == 0 and dy2.data_ptr() % 16 == 0)
+            fn = "f16_lma_linear_wgrad_tc" if tc else "f16_lma_linear_wgrad"
             with torch.cuda.device(x.device):
-                _lib.check(_lib.load().f16_lma_linear_wgrad(x2.shape[0], x2.shape[1], dy2.shape[1], C.c_void_p(x2.data_ptr()),
-                                                            C.c_void_p(dy2.data_ptr()), C.c_void_p(dw.data_ptr()),
-                                                            C.c_void_p(db.data_ptr() if db is not None else 0), stream), "f16_lma_linear_wgrad")
+                _lib.check(getattr(_lib.load(), fn)(x2.shape[0], x2.shape[1], dy2.shape[1], C.c_void_p(x2.data_ptr()),
+                                                    C.c_void_p(dy2.data_ptr()), C.c_void_p(dw.data_ptr()),
+                                                    C.c_void_p(db.data_ptr() if db is not None else 0), stream), fn)
         return dx, dw, db
 
 

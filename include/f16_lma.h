@@ -62,7 +62,7 @@ int f16_lma_linear_forward(int64_t rows, int in_features, int out_features, cons
 
 /* The same weight / bias gradients on the tensor cores (csrc/f16_lma_wgrad_tc.cu): D[out][in] accumulates in tensor memory
  * over 16-row chunks of dy and x (tcgen05.mma kind::tf32 on MN-major operands, TF32 head / remainder split: three MMAs
- * per 8 rows), is read out and restarted every 256 rows so that the tensor core's truncating accumulation never runs
+ * per 8 rows), is read out and restarted every 64 rows so that the tensor core's truncating accumulation never runs
  * long, and the CTAs' partial results meet in float atomics on the zero-initialised outputs. Same arguments and
  * semantics as f16_lma_linear_wgrad; x and dy 16-byte aligned. Built for out_features in {32, 64, 96, 128} and
  * in_features a multiple of 32 up to 160 whose partial sums fit shared memory (f16_lma_linear_wgrad_tc_supported); the

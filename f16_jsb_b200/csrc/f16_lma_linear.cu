@@ -235,8 +235,15 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
           for (int ks = 0; ks < 4; ++ks) {
             if (ks < ksteps) {
               const uint64_t dk = (uint64_t)(2 * ks);            // 32 B along K = 2 units of the address field
+#ifndef F16_LIN_MMAS
+#define F16_LIN_MMAS 4
+#endif
+#if F16_LIN_MMAS == 4
               umma_tf32(tmem_d, dal0 + dk, dbl0 + dk, idesc, (j | ks) ? 1u : 0u);      // smallest terms first
               umma_tf32(tmem_d, dal0 + dk, dbh0 + dk, idesc, 1u);
+#else
+              umma_tf32(tmem_d, dal0 + dk, dbh0 + dk, idesc, (j | ks) ? 1u : 0u);
+#endif
               umma_tf32(tmem_d, dah0 + dk, dbl0 + dk, idesc, 1u);
               umma_tf32(tmem_d, dah0 + dk, dbh0 + dk, idesc, 1u);
             }

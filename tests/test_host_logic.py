@@ -133,3 +133,19 @@ def test_tensor_core_linear_shape_support_is_host_logic():
     buf = (C.c_float * 64)()
     assert L.f16_lma_linear_forward(128, 64, 4, buf, buf, None, buf, None) != 0
     assert b"unsupported shape" in L.f16_last_error()
+
+
+def test_tensor_core_wgrad_shape_support_is_host_logic():
+    """f16_lma_linear_wgrad_tc_supported (include/f16_lma.h): the weight-gradient shapes of the reference's policy the
+    tensor-core kernel builds (its shared-memory planner must find a chunk / ring configuration), and the ones it leaves to
+    the FP32 slab kernel."""
+    from f16_jsb_b200 import _lib
+    L = _lib.load()
+    for k, n in [(128, 32), (32, 96), (32, 32), (32, 128), (160, 64), (64, 64), (128, 64), (96, 32)]:
+        assert L.f16_lma_linear_wgrad_tc_supported(k, n) == 1, (k, n)
+    for k, n in [(17, 64), (64, 4), (64, 1), (160, 128), (128, 128), (32, 160), (192, 32), (0, 32), (32, 0)]:
+        assert L.f16_lma_linear_wgrad_tc_supported(k, n) == 0, (k, n)
+    assert L.f16_lma_linear_wgrad_tc(0, 32, 32, None, None, None, None, None) != 0
+    assert b"rows must be positive" in L.f16_last_error()
+    assert L.f16_lma_linear_wgrad_tc(64, 32, 32, None, None, None, None, None) != 0
+    assert b"NULL pointer" in L.f16_last_error()

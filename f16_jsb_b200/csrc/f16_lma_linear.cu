@@ -8,9 +8,11 @@
 // HBM rate, and the arithmetic intensity (8-25 flop per byte) is beyond the FP32 FMA pipe at that rate but a few per
 // cent of the tensor pipe. So: tcgen05.mma kind::tf32 with FP32 accumulation in tensor memory, and - because the
 // reference computes in FP32 - the operands split into a TF32 head and a TF32 remainder (x = xh + xl, W = Wh + Wl),
-// four MMAs per k-step (xl Wl + xl Wh + xh Wl + xh Wh; the tensor pipe is far from busy): what is dropped is the
-// rounding of the remainders (2^-23 of each operand) and the tensor core's truncating FP32 accumulation, i.e. the
-// result is FP32-accurate to a few ulp of the sum's magnitude, like a reordered FP32 sum (tests/test_gpu_linear_tc.py).
+// three MMAs per k-step (xl Wh + xh Wl + xh Wh): what is dropped is xl Wl (2^-22 relative; a fourth MMA for it was
+// measured: no visible change in the error, 3 % slower because every MMA re-reads its operands from shared memory, which
+// is what bounds the kernel), the rounding of the remainders (2^-23 of each operand) and the tensor core's truncating
+// FP32 accumulation, i.e. the result is FP32-accurate to a few ulp of the sum's magnitude, like a reordered FP32 sum
+// (tests/test_gpu_linear_tc.py).
 //
 // One CTA per SM, 448 threads, persistent over 128-row tiles of x (UMMA M = 128, N = out features, K = 8 per
 // instruction); the roles meet only in mbarriers:
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
             if (ks < ksteps) {
               const uint64_t dk = (uint64_t)(2 * ks);            // 32 B along K = 2 units of the address field
 #ifndef F16_LIN_MMAS
-#define F16_LIN_MMAS 4
+#define F16_LIN_MMAS 3
 #endif
 #if F16_LIN_MMAS == 4
               umma_tf32(tmem_d, dal0 + dk, dbl0 + dk, idesc, (j | ks) ? 1u : 0u);      // smallest terms first

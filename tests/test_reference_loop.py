@@ -13,6 +13,10 @@ What SB3 stores and computes from the two must agree: observations, actions, rew
 bootstrap gamma * V(terminal_observation) of on_policy_algorithm.py:236-245), episode starts, returns, advantages, and
 the Monitor episode statistics. The reference draws the goals of auto-resets from OS entropy; the test injects the goals the
 GPU env drew (read from the recorded reset observations) so that both sides fly the same second episodes.
+The off-policy side (train.py's SAC option) gets the same treatment: `stable_baselines3.SAC`, `OffPolicyAlgorithm.collect_rollouts`
+/ `_store_transition` (common/off_policy_algorithm.py:436-600) and `ReplayBuffer` (common/buffers.py:176-325) run on both
+stacks, and what the replay buffer holds - observations, next observations (the terminal stack for finished envs), actions,
+rewards, dones, time-limit flags - must agree.
 The reference tree does not exist on the GPU box, so this runs where it does (the build container) and skips elsewhere.
 """
 import os
@@ -135,11 +139,15 @@ def run_collect(ref, rec, env, after_reset=None, after_first_step=None):
     return model
 
 
-def test_reference_collect_rollouts_on_recorded_f16vecenv_matches_reference_env_stack(ref, rec):
-    gym, jg, Monitor, DummyVecEnv = ref["gym"], ref["jg"], ref["Monitor"], ref["DummyVecEnv"]
-    N, T = int(rec["n_envs"]), int(rec["n_steps"])
+import contextlib
 
-    # ---- A: the reference's env stack, with the GPU env's auto-reset goals injected
+
+@contextlib.contextmanager
+def reference_env_stack(ref, rec):
+    """Stack A: Monitor + DummyVecEnv around the reference's JSBSim-v0 (FDM = the oracle), with the GPU env's auto-reset goals
+    injected. Yields (venv, after_reset, after_first_step) hooks for the algorithm's loop."""
+    gym, jg, Monitor, DummyVecEnv = ref["gym"], ref["jg"], ref["Monitor"], ref["DummyVecEnv"]
+    N = int(rec["n_envs"])
     goals_after_done = {}
     for s, e in zip(rec["done_step"], rec["done_env"]):
         goals_after_done.setdefault(int(e), []).append(rec["obs"][int(s), int(e), -1, 12:15].astype(np.float64))
@@ -174,9 +182,17 @@ def test_reference_collect_rollouts_on_recorded_f16vecenv_matches_reference_env_
                         w._elapsed_steps = int(st)           # ... and so does gymnasium's TimeLimit (registration, jsbsim_gym.py:537-545)
                     w = w.env
 
-        a = run_collect(ref, rec, venv, after_reset=inject, after_first_step=preset)
+        yield venv, inject, preset
     finally:
         jg.JSBSimEnv.reset = orig_reset
+
+
+def test_reference_collect_rollouts_on_recorded_f16vecenv_matches_reference_env_stack(ref, rec):
+    N, T = int(rec["n_envs"]), int(rec["n_steps"])
+
+    # ---- A: the reference's env stack, with the GPU env's auto-reset goals injected
+    with reference_env_stack(ref, rec) as (venv, inject, preset):
+        a = run_collect(ref, rec, venv, after_reset=inject, after_first_step=preset)
 
     # ---- B: the same loop fed by what F16VecEnv returned on the B200
     b = run_collect(ref, rec, make_replay_env(ref, rec))
@@ -221,3 +237,72 @@ def test_replay_fixture_follows_dummy_vec_env_conventions(rec):
         assert not np.array_equal(o[-1, 12:15], term[-1, 12:15])      # new goal
         assert rec["done_ep_l"][j] in (51, 101, 249)
     assert rec["dones"].sum() == len(rec["done_step"])
+
+
+def run_collect_off_policy(ref, rec, env, after_reset=None, after_first_step=None):
+    """SAC's loop (OffPolicyAlgorithm.collect_rollouts, common/off_policy_algorithm.py:506-600, with _store_transition
+    :436-504 and ReplayBuffer.add, common/buffers.py:233-290) for one rollout of T steps with the recorded actions."""
+    import sys as _sys
+    saved = list(_sys.path)
+    _sys.path[:0] = [os.path.join(ROOT, "oracle", "refshim"), REF]
+    try:
+        from stable_baselines3 import SAC
+        from stable_baselines3.common.type_aliases import TrainFreq, TrainFrequencyUnit
+    finally:
+        _sys.path[:] = saved
+    T, N = int(rec["n_steps"]), int(rec["n_envs"])
+    model = SAC("MlpPolicy", env, buffer_size=T * N, learning_starts=0, train_freq=(T, "step"), seed=0, device="cpu", verbose=0,
+                policy_kwargs=dict(net_arch=[8]))
+    model.env.seed(int(rec["seed"]))
+
+    class AfterFirstStep(ref["BaseCallback"]):
+        def _on_step(self):
+            if self.n_calls == 1 and after_first_step:
+                after_first_step(self.training_env)
+            return True
+
+    _, callback = model._setup_learn(T * N, AfterFirstStep(), True, "run", False)
+    if after_reset:
+        after_reset(model.env)
+    counter = {"t": 0}
+
+    def sample_action(learning_starts, action_noise=None, n_envs=1):        # the recorded action table instead of the actor
+        a = np.asarray(rec["actions"][counter["t"]], np.float32)
+        counter["t"] += 1
+        return a, model.policy.scale_action(a)
+
+    model._sample_action = sample_action
+    out = model.collect_rollouts(model.env, callback, TrainFreq(T, TrainFrequencyUnit.STEP), model.replay_buffer, learning_starts=0)
+    assert out.continue_training and out.episode_timesteps == T * N
+    return model
+
+
+def test_reference_sac_collect_rollouts_on_recorded_f16vecenv_matches_reference_env_stack(ref, rec):
+    """The off-policy side of the boundary (train.py's SAC option): what SB3's ReplayBuffer holds after the reference's own
+    OffPolicyAlgorithm.collect_rollouts must be the same whether the loop ran on the reference env stack or on what
+    F16VecEnv returned on the B200 - in particular next_observations, which take info["terminal_observation"] for
+    finished envs (off_policy_algorithm.py:473-490), dones, and the time-limit flags (ReplayBuffer.timeouts)."""
+    N, T = int(rec["n_envs"]), int(rec["n_steps"])
+    with reference_env_stack(ref, rec) as (venv, inject, preset):
+        a = run_collect_off_policy(ref, rec, venv, after_reset=inject, after_first_step=preset)
+    b = run_collect_off_policy(ref, rec, make_replay_env(ref, rec))
+    A, B = a.replay_buffer, b.replay_buffer
+    assert A.pos == B.pos and A.full == B.full and A.observations.shape == B.observations.shape == (T, N, 10, 15)
+    np.testing.assert_array_equal(A.dones, B.dones)
+    np.testing.assert_array_equal(A.timeouts, B.timeouts)
+    assert A.dones.sum() == len(rec["done_step"]) == 3 and A.timeouts.sum() == 2
+    np.testing.assert_array_equal(A.actions, B.actions)
+    for name in ("observations", "next_observations"):
+        x, y = getattr(A, name), getattr(B, name)
+        err = np.abs(x - y) / np.maximum(np.abs(x), 1e-2)
+        assert err.max() < 1e-5, (name, err.max())
+        assert (x == y).mean() > 0.99
+    assert np.abs(A.rewards - B.rewards).max() < 2e-5
+    # a finished env's next observation is its terminal stack, not the reset stack the VecEnv returned
+    for j, (s, e) in enumerate(zip(rec["done_step"], rec["done_env"])):
+        np.testing.assert_array_equal(B.next_observations[s, e], rec["done_terminal_obs"][j])
+        assert not np.array_equal(B.next_observations[s, e], rec["obs"][s, e])
+        if s + 1 < T:
+            np.testing.assert_array_equal(B.observations[s + 1, e], rec["obs"][s, e])      # the next transition starts from the reset stack
+    ea, eb = list(a.ep_info_buffer), list(b.ep_info_buffer)
+    assert [x["l"] for x in ea] == [x["l"] for x in eb] == [51, 101, 249]

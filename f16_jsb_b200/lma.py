@@ -253,8 +253,8 @@ class _LinearFn(torch.autograd.Function):
 
 
 class Linear(nn.Linear):
-    """nn.Linear (same parameters, same state_dict keys) whose backward on CUDA float32 tensors with many rows uses
-    the hand-written weight-gradient kernel."""
+    """nn.Linear (same parameters, same state_dict keys) that, for CUDA float32 tensors with many rows and gradients
+    enabled, runs forward, input gradient and weight gradient through the hand-written kernels (_LinearFn)."""
 
     min_rows = 4096      # below this the library GEMM is as good
 

@@ -57,3 +57,36 @@ def test_linear_tc_refuses_unsupported_shapes():
     y = torch.zeros((8, 4), device="cuda")
     rc = L.f16_lma_linear_forward(8, 64, 4, C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), None, C.c_void_p(y.data_ptr()), None)
     assert rc != 0 and b"unsupported shape" in L.f16_last_error()
+
+
+def test_linear_tc_random_shapes_and_row_counts():
+    """Seeded sweep: every supported (in, out) pair drawn from the sizes the kernel is built for, ragged row counts, with
+    and without bias, non-trivial magnitudes; guard bytes after y must stay untouched."""
+    import random
+    from f16_jsb_b200 import _lib
+    L = _lib.load()
+    rnd = random.Random(7)
+    ins = [1, 5, 8, 17, 24, 31, 32, 64, 96, 128, 160]
+    outs = [32, 64, 96, 128, 160, 192, 224, 256]
+    done = 0
+    while done < 60:
+        k, n = rnd.choice(ins), rnd.choice(outs)
+        if not L.f16_lma_linear_supported(k, n):
+            continue
+        rows = rnd.choice([1, 2, 127, 128, 129, 255, 1000, 4097, rnd.randrange(1, 70000)])
+        g = torch.Generator(device="cuda").manual_seed(done)
+        x = torch.randn((rows, k), device="cuda", generator=g) * rnd.choice([1e-3, 1.0, 50.0])
+        w = torch.randn((n, k), device="cuda", generator=g) * rnd.choice([0.05, 1.0])
+        b = torch.randn((n,), device="cuda", generator=g) if rnd.random() < 0.7 else None
+        ybuf = torch.full((rows * n + 64,), 123.0, device="cuda")
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(L.f16_lma_linear_forward(rows, k, n, C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()),
+                                            C.c_void_p(b.data_ptr() if b is not None else 0), C.c_void_p(ybuf.data_ptr()), st), "f16_lma_linear_forward")
+        torch.cuda.synchronize()
+        assert bool((ybuf[rows * n:] == 123.0).all()), (k, n, rows)
+        y = ybuf[:rows * n].view(rows, n)
+        ref = x.double() @ w.double().t() + (b.double() if b is not None else 0.0)
+        scale = (x.abs().double() @ w.abs().double().t()) + (b.abs().double() if b is not None else 0.0) + 1e-30
+        err = ((y.double() - ref).abs() / scale).max().item()
+        assert err < 1.2e-6, (k, n, rows, err)
+        done += 1

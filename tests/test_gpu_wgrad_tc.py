@@ -57,3 +57,32 @@ def test_wgrad_tc_refuses_unsupported_shapes():
     dw = torch.zeros((64, 17), device="cuda")
     rc = L.f16_lma_linear_wgrad_tc(8, 17, 64, C.c_void_p(x.data_ptr()), C.c_void_p(dy.data_ptr()), C.c_void_p(dw.data_ptr()), None, None)
     assert rc != 0 and b"unsupported shape" in L.f16_last_error()
+
+
+def test_wgrad_tc_random_shapes_and_row_counts():
+    """Seeded sweep over the supported (in, out) pairs and ragged row counts, against float64; the FP32 slab kernel on the
+    same data is the yardstick for the error."""
+    import random
+    from f16_jsb_b200 import _lib
+    L = _lib.load()
+    rnd = random.Random(11)
+    done = 0
+    while done < 50:
+        k, n = rnd.choice([32, 64, 96, 128, 160]), rnd.choice([32, 64, 96, 128])
+        if not L.f16_lma_linear_wgrad_tc_supported(k, n):
+            continue
+        rows = rnd.choice([1, 31, 32, 33, 63, 64, 65, 1000, 4097, rnd.randrange(1, 120000)])
+        g = torch.Generator(device="cuda").manual_seed(100 + done)
+        x = torch.randn((rows, k), device="cuda", generator=g) * rnd.choice([1e-2, 1.0, 20.0])
+        dy = torch.randn((rows, n), device="cuda", generator=g) * rnd.choice([1e-3, 1.0])
+        dw, db = _call("f16_lma_linear_wgrad_tc", x, dy)
+        dw32, _ = _call("f16_lma_linear_wgrad", x, dy)
+        torch.cuda.synchronize()
+        ref = dy.double().t() @ x.double()
+        scale = dy.abs().double().t() @ x.abs().double() + 1e-30
+        err = ((dw.double() - ref).abs() / scale).max().item()
+        err32 = ((dw32.double() - ref).abs() / scale).max().item()
+        assert err < 2e-6 and err < 6 * err32 + 5e-7, (k, n, rows, err, err32)
+        refb = dy.double().sum(0)
+        assert ((db.double() - refb).abs() / (dy.abs().double().sum(0) + 1e-30)).max().item() < 2e-6, (k, n, rows)
+        done += 1

@@ -128,6 +128,19 @@ void build_tables(Tables<R>* T) {
   auto fill_seg = [](R (*seg)[2], const double* x, int n) {
     for (int r = 1; r < n; ++r) { seg[r][0] = (R)x[r - 1]; seg[r][1] = (R)(1.0 / (x[r] - x[r - 1])); }
   };
+  // packed entries for locate_uniform_packed: {x[i-2], 1/w[i-1], x[i-1], 1/w[i], x[i], 1/w[i+1], 0, 0}, w[j] = x[j] - x[j-1]
+  auto fill_segp = [](R (*segp)[8], const double* x, int n) {
+    for (int i = 0; i <= n; ++i)
+      for (int k = 0; k < 8; ++k) segp[i][k] = (R)0;
+    auto inv_w = [&](int j) { return (j >= 1 && j <= n - 1) ? 1.0 / (x[j] - x[j - 1]) : 0.0; };
+    for (int i = 1; i <= n - 1; ++i) {
+      segp[i][0] = (R)(i >= 2 ? x[i - 2] : x[0]); segp[i][1] = (R)inv_w(i - 1);
+      segp[i][2] = (R)x[i - 1];                   segp[i][3] = (R)inv_w(i);
+      segp[i][4] = (R)x[i];                       segp[i][5] = (R)inv_w(i + 1);
+    }
+  };
+  fill_segp(T->segp_alpha, alpha_bp, NA);
+  fill_segp(T->segp_de, de_bp, NDE);
   fill_seg(T->seg_alpha, alpha_bp, NA);
   fill_seg(T->seg_de, de_bp, NDE);
   fill_seg(T->seg_b7, b7_bp, NB7);
@@ -136,6 +149,7 @@ void build_tables(Tables<R>* T) {
   for (int i = 0; i < NB7; ++i)
     if (b7_bp[i] != b13_bp[2 * i]) { std::fprintf(stderr, "f16: beta breakpoint grids are not nested\n"); std::abort(); }
   fill_seg(T->seg_b13, b13_bp, NB13);
+  fill_segp(T->segp_b13, b13_bp, NB13);
   // union of the Mach breakpoints of the nine Mach tables; every table is piecewise linear with
   // clamped ends, so resampling it on the union grid reproduces it exactly
   std::vector<double> grid;

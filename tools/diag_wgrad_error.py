@@ -19,4 +19,4 @@ for (rows, k, n) in [(40000, 160, 64), (655360, 32, 128), (655360, 128, 32), (13
     run("f16_lma_linear_wgrad_tc", x, dy); t0.record()
     for _ in range(10): run("f16_lma_linear_wgrad_tc", x, dy)
     t1.record(); torch.cuda.synchronize()
-    print("flush=%s rows=%d k=%d n=%d: max err / max|dW|: tc %.2e  slab %.2e   (%.1f us incl. sync)" % (os.environ.get("F16_WG_FLUSH", "256"), rows, k, n, out[0], out[1], t0.elapsed_time(t1) * 100))
+    print("flush=%s rows=%d k=%d n=%d: max err / max|dW|: tc %.2e  slab %.2e   (%.1f us incl. sync)" % (os.environ.get("F16_WG_FLUSH", "64 (default)"), rows, k, n, out[0], out[1], t0.elapsed_time(t1) * 100))

@@ -66,7 +66,8 @@ struct LinArgs {
   int64_t rows, tiles;
   int kg;          // features per row of x (= row pitch of x and w)
   int kp;          // kg rounded up to a multiple of 8 (MMA k-steps); the padding columns are zero
-  int n;           // out features = UMMA N, a multiple of 32
+  int n;           // out features of this launch = UMMA N, a multiple of 32
+  int ldy;         // row pitch of y in floats (>= n: a launch may cover a group of the layer's output columns)
   uint32_t tmem_cols;
 };
 
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(THREADS, 1) linear_tc_kernel(const LinArgs a, 
         for (int i = 0; i < 8; ++i) {
           const int r = (lane >> 3) + 4 * i;
           const float4 o = *reinterpret_cast<const float4*>(stage + (uint32_t)r * EPI_ROW + 16u * (lane & 7));
-          if (row0 + r < a.rows) *reinterpret_cast<float4*>(a.y + (size_t)(row0 + r) * a.n + c0 + 4 * (lane & 7)) = o;
+          if (row0 + r < a.rows) *reinterpret_cast<float4*>(a.y + (size_t)(row0 + r) * a.ldy + c0 + 4 * (lane & 7)) = o;
         }
         __syncwarp();
       }
@@ -302,28 +303,32 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 size_t smem_needed(int kp, int n) { return OFF_B + 2 * (size_t)((kp + 31) / 32) * n * 128 + TAIL_BYTES; }
 }  // namespace
 
-extern "C" int f16_lma_linear_supported(int in_features, int out_features) {
-  if (out_features < 32 || out_features > 256 || out_features % 32) return 0;
-  if (in_features <= 0) return 0;
-  if (in_features > 32 && in_features % 32) return 0;
+// the widest group of output columns (a multiple of 32) whose W, in both parts, fits next to the rings
+static int max_group(int in_features) {
   const int kp = (in_features + 7) / 8 * 8;
-  return smem_needed(kp, out_features) <= SMEM_LIMIT ? 1 : 0;
+  const size_t per32 = 2 * (size_t)((kp + 31) / 32) * 32 * 128;
+  const size_t room = SMEM_LIMIT - OFF_B - TAIL_BYTES;
+  int g = (int)(room / per32) * 32;
+  return g > 256 ? 256 : g;
 }
 
-extern "C" int f16_lma_linear_forward(int64_t rows, int in_features, int out_features, const float* x, const float* weight,
-                                      const float* bias, float* y, void* stream) {
-  if (rows <= 0) return f16_internal_fail("f16_lma_linear_forward: rows must be positive");
-  if (!x || !weight || !y) return f16_internal_fail("f16_lma_linear_forward: NULL pointer");
-  if (!f16_lma_linear_supported(in_features, out_features))
-    return f16_internal_fail("f16_lma_linear_forward: unsupported shape (out features a multiple of 32 up to 256; in features <= 32 or a multiple of 32; W must fit shared memory)");
-  if ((((uintptr_t)y) & 15) || (((uintptr_t)x) & 15) || (bias && (((uintptr_t)bias) & 15)))
-    return f16_internal_fail("f16_lma_linear_forward: x, y and bias must be 16-byte aligned");
+extern "C" int f16_lma_linear_supported(int in_features, int out_features) {
+  if (out_features < 32 || out_features % 32) return 0;
+  if (in_features <= 0) return 0;
+  if (in_features > 32 && in_features % 32) return 0;
+  if (max_group(in_features) < 32) return 0;
+  // layers wider than one group are computed in column groups (x is read once per group): at most four
+  return (out_features + max_group(in_features) - 1) / max_group(in_features) <= 4 ? 1 : 0;
+}
+
+static int launch_group(int64_t rows, int in_features, int n, int ldy, const float* x, const float* weight, const float* bias, float* y,
+                        cudaStream_t stream) {
   LinArgs a;
   a.x = x; a.w = weight; a.bias = bias; a.y = y;
   a.rows = rows; a.tiles = (rows + TILE_M - 1) / TILE_M;
-  a.kg = in_features; a.kp = (in_features + 7) / 8 * 8; a.n = out_features;
+  a.kg = in_features; a.kp = (in_features + 7) / 8 * 8; a.n = n; a.ldy = ldy;
   a.tmem_cols = 32;
-  while ((int)a.tmem_cols < 2 * out_features) a.tmem_cols *= 2;   // two accumulators
+  while ((int)a.tmem_cols < 2 * n) a.tmem_cols *= 2;              // two accumulators
   const bool vec = in_features % 32 == 0;
   // 1 KB of slack for the 1024-byte alignment of the operand atoms; the largest shapes get what is left below the
   // per-block limit (the kernel checks that its carve-up fits and traps otherwise)
@@ -365,9 +370,30 @@ extern "C" int f16_lma_linear_forward(int64_t rows, int in_features, int out_fea
   }
   int64_t grid = sms;                                             // one persistent CTA per SM
   if (grid > a.tiles) grid = a.tiles;
-  kern<<<(unsigned)grid, THREADS, smem, (cudaStream_t)stream>>>(a, tmap);
+  kern<<<(unsigned)grid, THREADS, smem, stream>>>(a, tmap);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return f16_internal_fail(cudaGetErrorString(e));
   f16_internal_count_launch();
+  return 0;
+}
+
+extern "C" int f16_lma_linear_forward(int64_t rows, int in_features, int out_features, const float* x, const float* weight,
+                                      const float* bias, float* y, void* stream) {
+  if (rows <= 0) return f16_internal_fail("f16_lma_linear_forward: rows must be positive");
+  if (!x || !weight || !y) return f16_internal_fail("f16_lma_linear_forward: NULL pointer");
+  if (!f16_lma_linear_supported(in_features, out_features))
+    return f16_internal_fail("f16_lma_linear_forward: unsupported shape (out features a multiple of 32; in features <= 32 or a multiple of 32; W must fit shared memory in at most four column groups)");
+  if ((((uintptr_t)y) & 15) || (((uintptr_t)x) & 15) || (((uintptr_t)weight) & 15) || (bias && (((uintptr_t)bias) & 15)))
+    return f16_internal_fail("f16_lma_linear_forward: x, weight, y and bias must be 16-byte aligned");
+  // column groups: as even as the 32-column granularity allows
+  const int gmax = max_group(in_features);
+  const int groups = (out_features + gmax - 1) / gmax;
+  const int per = ((out_features / 32 + groups - 1) / groups) * 32;
+  for (int c0 = 0; c0 < out_features; c0 += per) {
+    const int n = out_features - c0 < per ? out_features - c0 : per;
+    const int rc = launch_group(rows, in_features, n, out_features, x, weight + (size_t)c0 * in_features, bias ? bias + c0 : nullptr, y + c0,
+                                (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   return 0;
 }

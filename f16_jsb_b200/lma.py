@@ -204,7 +204,8 @@ class _LinearFn(torch.autograd.Function):
     (dx = dy W, the same kernel with W^T as the weight) run on the tensor cores with split TF32 operands
     (csrc/f16_lma_linear.cu: FP32-accurate, 4.4-5.1 TB/s where the library's FP32 GEMMs reach 1.0-1.9); the weight /
     bias gradients, whose reduction axis is the batch, come from csrc/f16_lma_wgrad.cu (include/f16_lma.h). Shapes the
-    tensor-core kernel does not build (the 4- and 1-wide output heads, 160 -> 128) stay torch matmuls."""
+    tensor-core kernels do not build (the 4- and 1-wide output heads; for the weight gradient also 17 input features and
+    160 -> 128) stay torch matmuls / the FP32 slab kernel."""
 
     use_tc = os.environ.get("F16_LMA_TC", "1") != "0"        # class-wide switches (A/B measurements, tests)
     use_wgrad_tc = os.environ.get("F16_LMA_WGRAD_TC", "1") != "0"

@@ -53,9 +53,10 @@ int f16_lma_linear_wgrad(int64_t rows, int in_features, int out_features, const 
  * as called by the reference's Linear modules (jsbsim_gym/LMA_features.py:221-279,315-385; SB3 MlpExtractor,
  * stable_baselines3/common/torch_layers.py). tcgen05.mma kind::tf32 with both operands split into a TF32 head and an
  * FP32 remainder (three MMAs per k-step), FP32 accumulation in tensor memory: FP32-accurate like a reordered FP32 sum.
- * Row-major float32, contiguous; y and bias 16-byte aligned. Shapes: out_features a multiple of 16 up to 256;
- * in_features <= 32, or a multiple of 32 (then x 16-byte aligned) - f16_lma_linear_supported says whether a shape is
- * built (the caller keeps the library GEMM for the others: the 4- and 1-wide output heads). */
+ * Row-major float32, contiguous; x, weight, y and bias 16-byte aligned. Shapes: out_features a multiple of 32;
+ * in_features <= 32, or a multiple of 32 - f16_lma_linear_supported says whether a shape is built (the caller keeps the
+ * library GEMM for the others: the 4- and 1-wide output heads). Layers whose W, in both parts, does not fit shared memory
+ * next to the rings (160 -> 128, 128 -> 160) are computed in up to four groups of output columns, one launch each. */
 int f16_lma_linear_supported(int in_features, int out_features);
 int f16_lma_linear_forward(int64_t rows, int in_features, int out_features, const float* x, const float* weight,
                            const float* bias, float* y, void* stream);

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 # (in_features, out_features): forward shapes of the policy, then the input-gradient shapes (weight = W^T)
 SHAPES = [(17, 64), (128, 32), (32, 96), (32, 32), (32, 128), (160, 64), (64, 64), (128, 64),
-          (96, 32), (64, 160), (64, 128), (8, 32), (24, 64), (32, 256)]
+          (96, 32), (64, 160), (64, 128), (8, 32), (24, 64), (32, 256), (160, 128), (128, 160), (64, 256)]
 
 
 def _call(x, w, b):
@@ -51,7 +51,7 @@ def test_linear_tc_refuses_unsupported_shapes():
     L = _lib.load()
     assert L.f16_lma_linear_supported(64, 4) == 0 and L.f16_lma_linear_supported(64, 1) == 0
     assert L.f16_lma_linear_supported(40, 32) == 0 and L.f16_lma_linear_supported(32, 48) == 0
-    assert L.f16_lma_linear_supported(160, 128) == 0          # W (both parts) would not fit shared memory
+    assert L.f16_lma_linear_supported(160, 320) == 0          # more than four column groups
     x = torch.zeros((8, 64), device="cuda")
     w = torch.zeros((4, 64), device="cuda")
     y = torch.zeros((8, 4), device="cuda")

@@ -121,10 +121,11 @@ def test_tensor_core_linear_shape_support_is_host_logic():
     from f16_jsb_b200 import _lib
     L = _lib.load()
     built = [(17, 64), (128, 32), (32, 96), (32, 32), (32, 128), (160, 64), (64, 64), (128, 64),    # forward
-             (96, 32), (64, 160), (64, 128), (32, 128)]                                             # input gradients (W^T)
+             (96, 32), (64, 160), (64, 128), (32, 128),                                             # input gradients (W^T)
+             (160, 128), (128, 160), (64, 256)]                                                     # in column groups
     for k, n in built:
         assert L.f16_lma_linear_supported(k, n) == 1, (k, n)
-    for k, n in [(64, 4), (64, 1), (160, 128), (128, 160), (40, 32), (32, 48), (32, 0), (0, 32), (32, 288)]:
+    for k, n in [(64, 4), (64, 1), (40, 32), (32, 48), (32, 0), (0, 32), (160, 320)]:
         assert L.f16_lma_linear_supported(k, n) == 0, (k, n)
     assert L.f16_lma_linear_forward(0, 32, 32, None, None, None, None, None) != 0
     assert b"rows must be positive" in L.f16_last_error()

@@ -94,9 +94,14 @@ def load():
     L.f16_lma_linear_supported.argtypes = [i32, i32]
     L.f16_lma_linear_wgrad_tc.argtypes = [i64, i32, i32, vp, vp, vp, vp, vp]
     L.f16_lma_linear_wgrad_tc_supported.argtypes = [i32, i32]
+    L.f16_lma_embed_act_forward.argtypes = [i64, i32, i32, vp, vp, vp, C.c_float, u64, vp]
+    L.f16_lma_embed_act_backward.argtypes = [i64, i32, vp, vp, vp, C.c_float, u64, vp]
+    L.f16_lma_dropout_add_forward.argtypes = [i64, vp, vp, vp, C.c_float, u64, vp]
+    L.f16_lma_dropout_backward.argtypes = [i64, vp, vp, C.c_float, u64, vp]
     for name in ("f16_lma_attention_forward", "f16_lma_attention_backward", "f16_lma_attention_mask", "f16_lma_layernorm_forward",
                  "f16_lma_layernorm_backward", "f16_lma_linear_wgrad", "f16_lma_linear_forward", "f16_lma_linear_supported",
-                 "f16_lma_linear_wgrad_tc", "f16_lma_linear_wgrad_tc_supported"):
+                 "f16_lma_linear_wgrad_tc", "f16_lma_linear_wgrad_tc_supported", "f16_lma_embed_act_forward",
+                 "f16_lma_embed_act_backward", "f16_lma_dropout_add_forward", "f16_lma_dropout_backward"):
         getattr(L, name).restype = i32
     L.f16_features17.restype = i32
     for name in ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather"):

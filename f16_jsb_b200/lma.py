@@ -142,6 +142,90 @@ def latent_attention(qkv: torch.Tensor, heads: int, dropout_p: float = 0.0) -> t
     return F.scaled_dot_product_attention(q, k, v, dropout_p=dropout_p).transpose(1, 2).reshape(b, t, d)
 
 
+def _new_seed() -> int:
+    return int(torch.empty((), dtype=torch.int64).random_())
+
+
+def _stream(t: torch.Tensor):
+    import ctypes as C
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+class _DropoutAddFn(torch.autograd.Function):
+    """z + dropout(x) in one pass (csrc/f16_lma_elementwise.cu); the mask is regenerated from the seed in the backward."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, z: torch.Tensor, p: float):
+        import ctypes as C
+
+        from . import _lib
+        x, z = x.contiguous(), z.contiguous()
+        y = torch.empty_like(x)
+        seed = _new_seed()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().f16_lma_dropout_add_forward(x.numel(), C.c_void_p(x.data_ptr()), C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr()),
+                                                               float(p), seed, _stream(x)), "f16_lma_dropout_add_forward")
+        ctx.meta = (float(p), seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        import ctypes as C
+
+        from . import _lib
+        p, seed = ctx.meta
+        dy = dy.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(dy)
+            with torch.cuda.device(dy.device):
+                _lib.check(_lib.load().f16_lma_dropout_backward(dy.numel(), C.c_void_p(dy.data_ptr()), C.c_void_p(dx.data_ptr()), p, seed, _stream(dy)),
+                           "f16_lma_dropout_backward")
+        return dx, (dy if ctx.needs_input_grad[1] else None), None
+
+
+def dropout_add(x: torch.Tensor, z: torch.Tensor, p: float, training: bool) -> torch.Tensor:
+    """z + dropout(x, p). Training on CUDA float32 tensors goes through the fused kernel; anything else through torch."""
+    if (training and p > 0 and x.is_cuda and x.dtype == torch.float32 and z.dtype == torch.float32 and x.shape == z.shape
+            and x.numel() % 8 == 0 and _LinearFn.use_fused_elementwise):
+        return _DropoutAddFn.apply(x, z, p)
+    return z + F.dropout(x, p, training)
+
+
+class _EmbedActFn(torch.autograd.Function):
+    """dropout(relu(a) + positions) in one pass; backward da = keep * dy * (a > 0) from the saved pre-activation."""
+
+    @staticmethod
+    def forward(ctx, a: torch.Tensor, pos: torch.Tensor, p: float):
+        import ctypes as C
+
+        from . import _lib
+        a, pos = a.contiguous(), pos.contiguous()
+        seq, ch = pos.shape
+        y = torch.empty_like(a)
+        seed = _new_seed()
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.load().f16_lma_embed_act_forward(a.numel() // ch, ch, seq, C.c_void_p(a.data_ptr()), C.c_void_p(pos.data_ptr()),
+                                                             C.c_void_p(y.data_ptr()), float(p), seed, _stream(a)), "f16_lma_embed_act_forward")
+        ctx.save_for_backward(a)
+        ctx.meta = (float(p), seed, ch)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy: torch.Tensor):
+        import ctypes as C
+
+        from . import _lib
+        (a,) = ctx.saved_tensors
+        p, seed, ch = ctx.meta
+        dy = dy.contiguous()
+        da = torch.empty_like(a)
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.load().f16_lma_embed_act_backward(a.numel() // ch, ch, C.c_void_p(a.data_ptr()), C.c_void_p(dy.data_ptr()),
+                                                              C.c_void_p(da.data_ptr()), p, seed, _stream(a)), "f16_lma_embed_act_backward")
+        return da, None, None
+
+
 class _Attention(nn.Module):
     def __init__(self, dim: int, heads: int, dropout: float, bias: bool):
         super().__init__()
@@ -149,9 +233,12 @@ class _Attention(nn.Module):
         self.c_attn = Linear(dim, 3 * dim, bias=bias)
         self.c_proj = Linear(dim, dim, bias=bias)
 
-    def forward(self, z: torch.Tensor) -> torch.Tensor:
-        y = latent_attention(self.c_attn(z), self.heads, self.p if self.training else 0.0)
-        return F.dropout(self.c_proj(y), self.p, self.training)
+    def forward(self, z: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """drop(proj(attention(z))), or residual + that in one pass when a residual is given."""
+        y = self.c_proj(latent_attention(self.c_attn(z), self.heads, self.p if self.training else 0.0))
+        if residual is None:
+            return F.dropout(y, self.p, self.training)
+        return dropout_add(y, residual, self.p, self.training)
 
 
 class _MLP(nn.Module):
@@ -161,8 +248,11 @@ class _MLP(nn.Module):
         self.c_fc = Linear(dim, hidden, bias=bias)
         self.c_proj = Linear(hidden, dim, bias=bias)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        return F.dropout(self.c_proj(F.gelu(self.c_fc(x))), self.p, self.training)
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        y = self.c_proj(F.gelu(self.c_fc(x)))
+        if residual is None:
+            return F.dropout(y, self.p, self.training)
+        return dropout_add(y, residual, self.p, self.training)
 
 
 def _linear_tc(x2: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
@@ -209,6 +299,7 @@ class _LinearFn(torch.autograd.Function):
 
     use_tc = os.environ.get("F16_LMA_TC", "1") != "0"        # class-wide switches (A/B measurements, tests)
     use_wgrad_tc = os.environ.get("F16_LMA_WGRAD_TC", "1") != "0"
+    use_fused_elementwise = os.environ.get("F16_LMA_FUSED_ELEMENTWISE", "1") != "0"
 
     @staticmethod
     def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]):
@@ -334,8 +425,8 @@ class _Block(nn.Module):
         self.mlp = _MLP(cfg.d_new, cfg.ff_hidden, cfg.dropout, cfg.bias)
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
-        z = z + self.attn(self.ln_1(z))
-        return z + self.mlp(self.ln_2(z))
+        z = self.attn(self.ln_1(z), residual=z)
+        return self.mlp(self.ln_2(z), residual=z)
 
 
 class _InitialTransform(nn.Module):
@@ -349,7 +440,12 @@ class _InitialTransform(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         c = self.cfg
         b = x.shape[0]
-        y = F.dropout(F.relu(self.input_embedding(x)) + self.positions, c.dropout, self.training)
+        a = self.input_embedding(x)
+        if (self.training and c.dropout > 0 and a.is_cuda and a.dtype == torch.float32 and c.embed_dim % 8 == 0 and torch.is_grad_enabled()
+                and _LinearFn.use_fused_elementwise):
+            y = _EmbedActFn.apply(a, self.positions, c.dropout)
+        else:
+            y = F.dropout(F.relu(a) + self.positions, c.dropout, self.training)
         # head stacking (split the 64 channels in 4 heads, lay the heads one after the other along the
         # sequence) and re-chunking into L' tokens of C' values is a single permutation of the 640 values
         h = c.num_heads_stacking

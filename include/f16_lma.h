@@ -71,6 +71,20 @@ int f16_lma_linear_forward(int64_t rows, int in_features, int out_features, cons
 int f16_lma_linear_wgrad_tc_supported(int in_features, int out_features);
 int f16_lma_linear_wgrad_tc(int64_t rows, int in_features, int out_features, const float* x, const float* dy, float* dweight,
                             float* dbias, void* stream);
+
+/* The two fused elementwise steps of the extractor's training pass (csrc/f16_lma_elementwise.cu). The keep mask is a function
+ * of (seed, element index): the backward calls regenerate it from the same dropout_p and seed instead of reading a stored
+ * mask; kept elements are scaled by 1 / (1 - p'), p' = round(p * 65536) / 65536. float32, contiguous, 16-byte aligned.
+ *   embed activation (_InitialTransform: ReLU, sinusoidal positions, embedding dropout - jsbsim_gym/LMA_features.py:221-279):
+ *     y[r][c] = keep * (max(a[r][c], 0) + pos[r mod seq_len][c]),   da[r][c] = keep * dy[r][c] * (a[r][c] > 0);  channels % 8 == 0
+ *   residual dropout (LMA block: z + drop(attn(ln(z))), z + drop(mlp(ln(z))) - :386-407):
+ *     y = z + keep * x,   dx = keep * dy (dz = dy is the caller's);  n % 8 == 0 */
+int f16_lma_embed_act_forward(int64_t rows, int channels, int seq_len, const float* a, const float* pos, float* y, float dropout_p,
+                              uint64_t seed, void* stream);
+int f16_lma_embed_act_backward(int64_t rows, int channels, const float* a, const float* dy, float* da, float dropout_p, uint64_t seed,
+                               void* stream);
+int f16_lma_dropout_add_forward(int64_t n, const float* x, const float* z, float* y, float dropout_p, uint64_t seed, void* stream);
+int f16_lma_dropout_backward(int64_t n, const float* dy, float* dx, float dropout_p, uint64_t seed, void* stream);
 #ifdef __cplusplus
 }
 #endif

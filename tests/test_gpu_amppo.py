@@ -240,3 +240,90 @@ def test_linear_weight_gradient_kernel_matches_torch(rows, fin, fout, bias):
         # sums of `rows` products of unit-variance numbers in float32: error ~ sqrt(rows) * 6e-8 * sqrt(rows)
         tol = 2e-6 * max(1.0, float(r.abs().max()))
         assert torch.allclose(a.double(), r, rtol=0, atol=tol), (float((a.double() - r).abs().max()), tol)
+
+
+@pytest.mark.parametrize("shape,p", [((3, 10, 64), 0.0), ((4099, 10, 64), 0.1), ((70000, 5, 32), 0.1), ((1000, 5, 32), 0.5)])
+def test_fused_dropout_kernels_match_torch(shape, p):
+    """csrc/f16_lma_elementwise.cu through its autograd wiring (lma.dropout_add, lma._EmbedActFn) against plain torch
+    float32 ops of the same step (jsbsim_gym/LMA_features.py:221-279 embedding activation, :386-407 residual dropout).
+    The keep mask is the kernels' own (read off a forward of ones); with it the results must agree to one rounding, the
+    backward must regenerate the same mask, and the keep rate must be 1 - p."""
+    from f16_jsb_b200.lma import _DropoutAddFn, _EmbedActFn
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(shape, generator=g, device="cuda").requires_grad_(True)
+    z = torch.randn(shape, generator=g, device="cuda").requires_grad_(True)
+    dy = torch.randn(shape, generator=g, device="cuda")
+    scale = 1.0 / (1.0 - round(p * 65536) / 65536)
+
+    import ctypes as C
+
+    from f16_jsb_b200 import _lib
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ones, zeros = torch.ones(shape, device="cuda"), torch.zeros(shape, device="cuda")
+
+    def mask_of(seed):                     # keep factors (0 or 1 / (1 - p')) of a seed, read off 0 + keep * 1
+        out = torch.empty_like(ones)
+        _lib.check(_lib.load().f16_lma_dropout_add_forward(ones.numel(), C.c_void_p(ones.data_ptr()), C.c_void_p(zeros.data_ptr()),
+                                                           C.c_void_p(out.data_ptr()), float(p), seed, stream), "mask probe")
+        assert set(out.unique().tolist()) <= {0.0, float(np.float32(scale))}
+        return out
+
+    # residual dropout: y = z + keep * x
+    y = _DropoutAddFn.apply(x, z, p)
+    seed = y.grad_fn.meta[1]
+    m = mask_of(seed)
+    # the kernel's multiply-add is one FMA, torch's two rounded operations: equal to one rounding of the product
+    assert torch.allclose(y.detach(), z.detach() + x.detach() * m, rtol=2e-7, atol=2e-7)
+    if p == 0:
+        assert bool((m == 1).all())
+    elif x.numel() > 100000:
+        assert abs(float((m > 0).float().mean()) - (1 - p)) < 0.005
+        assert not torch.equal(m, mask_of(seed + 1))
+    gx, gz = torch.autograd.grad(y, (x, z), dy)
+    assert torch.equal(gx, dy * m) and torch.equal(gz, dy)
+    # embedding activation: y = keep * (relu(a) + pos[t]), da = keep * dy * (a > 0)
+    t, ch = shape[1], shape[2]
+    pos = torch.randn((t, ch), generator=g, device="cuda") + 3.0        # > 0 almost surely is not needed: the mask is read off ones
+    a = x.detach().clone().requires_grad_(True)
+    ye = _EmbedActFn.apply(a, pos, p)
+    seed_e = ye.grad_fn.meta[1]
+    probe = mask_of(seed_e)
+    assert torch.equal(ye.detach(), (torch.relu(a.detach()) + pos) * probe)       # both kernels key the mask by (seed, element / 8)
+    (ga,) = torch.autograd.grad(ye, a, dy)
+    assert torch.equal(ga, torch.where(a.detach() > 0, dy * probe, torch.zeros_like(dy)))
+
+
+def test_block_with_fused_dropout_equals_unfused_at_p0_and_trains():
+    """The extractor wired through the fused paths: at p = 0 both settings of the switch take the torch ops (dropout is
+    the identity; outputs equal), at p = 0.1 the fused kernels run (their autograd nodes are in the graph), the outputs
+    differ from eval mode and every gradient is finite."""
+    from f16_jsb_b200.lma import LMAConfig, LMAExtractor, _LinearFn
+    torch.manual_seed(0)
+    obs = torch.randn((257, 10, 15), device="cuda")
+    res = {}
+    for fused in (True, False):
+        _LinearFn.use_fused_elementwise = fused
+        try:
+            torch.manual_seed(1)
+            net = LMAExtractor(LMAConfig(dropout=0.0)).cuda().train()
+            out = net(obs)
+            out.square().sum().backward()
+            res[fused] = (out.detach().clone(), [q.grad.clone() for q in net.parameters() if q.grad is not None])
+        finally:
+            _LinearFn.use_fused_elementwise = True
+    assert torch.equal(res[True][0], res[False][0])
+    for ga, gb in zip(res[True][1], res[False][1]):
+        assert torch.allclose(ga, gb, rtol=1e-5, atol=1e-6 * max(1.0, float(gb.abs().max())))
+    net = LMAExtractor(LMAConfig(dropout=0.1)).cuda().train()
+    out = net(obs)
+    names, todo = set(), [out.grad_fn]
+    while todo:
+        f = todo.pop()
+        if f is not None and f not in names:
+            names.add(f)
+            todo.extend(n for n, _ in f.next_functions)
+    names = {type(f).__name__ for f in names}
+    assert any("DropoutAddFn" in n for n in names) and any("EmbedActFn" in n for n in names), names
+    out.square().sum().backward()
+    assert all(bool(torch.isfinite(q.grad).all()) for q in net.parameters() if q.grad is not None)
+    assert not torch.equal(out.detach(), net.eval()(obs).detach())

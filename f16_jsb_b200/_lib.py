@@ -98,6 +98,14 @@ def load():
     L.f16_lma_embed_act_backward.argtypes = [i64, i32, vp, vp, vp, C.c_float, u64, vp]
     L.f16_lma_dropout_add_forward.argtypes = [i64, vp, vp, vp, C.c_float, u64, vp]
     L.f16_lma_dropout_backward.argtypes = [i64, vp, vp, C.c_float, u64, vp]
+    L.f16_lma_policy_packed_size.argtypes = []
+    L.f16_lma_policy_packed_size.restype = i64
+    L.f16_lma_policy_entries.argtypes = []
+    L.f16_lma_policy_entries.restype = i32
+    L.f16_lma_policy_entry.argtypes = [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
+    L.f16_lma_policy_entry.restype = i32
+    L.f16_lma_policy_forward.argtypes = [i64, vp, vp, i64] + [vp] * 10
+    L.f16_lma_policy_forward.restype = i32
     for name in ("f16_lma_attention_forward", "f16_lma_attention_backward", "f16_lma_attention_mask", "f16_lma_layernorm_forward",
                  "f16_lma_layernorm_backward", "f16_lma_linear_wgrad", "f16_lma_linear_forward", "f16_lma_linear_supported",
                  "f16_lma_linear_wgrad_tc", "f16_lma_linear_wgrad_tc_supported", "f16_lma_embed_act_forward",

@@ -26,7 +26,7 @@ import torch.nn.functional as F
 
 from .constants import ACTION_HIGH, ACTION_LOW
 from .dag import DAG
-from .lma import LMAActorCritic, LMAConfig
+from .lma import LMAActorCritic, LMAConfig, PolicyForwardKernel
 from .rollout import GpuRolloutBuffer
 
 
@@ -116,6 +116,7 @@ class AMPPOConfig:
     seed: int = 1
     cuda_graph: bool = True           # replay the rollout's policy forward (~50 small launches) as one CUDA graph
     tf32: bool = False                # TF32 tensor-core matmuls for the policy (the reference computes in FP32)
+    fused_policy_forward: bool = True  # rollout: the whole policy forward as one kernel (reference-shaped policies only)
 
 
 class AMPPO:
@@ -141,6 +142,9 @@ class AMPPO:
         self._obs = None
         self._episode_starts = None
         self._graph = None
+        self._fused_act = None
+        if c.fused_policy_forward and self.device.type == "cuda" and PolicyForwardKernel.supported(self.policy):
+            self._fused_act = PolicyForwardKernel(self.policy, self.act_low, self.act_high)
         if c.tf32:
             torch.backends.cuda.matmul.allow_tf32 = True
         self.num_timesteps = 0
@@ -149,6 +153,9 @@ class AMPPO:
 
     # ------------------------------------------------------------------ rollout (on_policy_algorithm.py:162-275)
     def _act(self, obs: torch.Tensor):
+        if self._fused_act is not None:          # one launch for the whole forward (csrc/f16_lma_policy.cu)
+            noise = torch.randn((obs.shape[0], 4), dtype=torch.float32, device=self.device)
+            return self._fused_act(obs, noise)
         actions, values, log_probs = self.policy(obs)
         clipped = torch.maximum(torch.minimum(actions, self.act_high), self.act_low)              # :216
         return actions, values, log_probs, clipped
@@ -175,6 +182,8 @@ class AMPPO:
             self._obs = env.reset()
             self._episode_starts = torch.ones(env.num_envs, dtype=torch.uint8, device=self.device)
         self.policy.eval()
+        if self._fused_act is not None:
+            self._fused_act.refresh()            # the update moved the weights: re-pack them (in place, the graph keeps its pointers)
         if c.cuda_graph and self._graph is None:
             self._capture_act()
         self.buffer.reset()

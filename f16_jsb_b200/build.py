@@ -8,9 +8,10 @@ LIB_PATH = os.path.join(_HERE, "libf16b200.so")
 SOURCES = [os.path.join(_HERE, "csrc", "f16_b200.cu"), os.path.join(_HERE, "csrc", "f16_rollout.cu"),
            os.path.join(_HERE, "csrc", "f16_features.cu"), os.path.join(_HERE, "csrc", "f16_hostwin.cu"),
            os.path.join(_HERE, "csrc", "f16_lma_attention.cu"), os.path.join(_HERE, "csrc", "f16_lma_norm.cu"),
-           os.path.join(_HERE, "csrc", "f16_lma_wgrad.cu"), os.path.join(_HERE, "csrc", "f16_lma_linear.cu"), os.path.join(_HERE, "csrc", "f16_lma_wgrad_tc.cu"), os.path.join(_HERE, "csrc", "f16_lma_elementwise.cu")]
+           os.path.join(_HERE, "csrc", "f16_lma_wgrad.cu"), os.path.join(_HERE, "csrc", "f16_lma_linear.cu"), os.path.join(_HERE, "csrc", "f16_lma_wgrad_tc.cu"), os.path.join(_HERE, "csrc", "f16_lma_elementwise.cu"),
+           os.path.join(_HERE, "csrc", "f16_lma_policy.cu")]
 DEPS = [os.path.join(_HERE, "csrc", f) for f in
-        ("f16_b200.cu", "f16_rollout.cu", "f16_features.cu", "f16_hostwin.cu", "f16_lma_attention.cu", "f16_lma_norm.cu", "f16_lma_wgrad.cu", "f16_lma_linear.cu", "f16_lma_wgrad_tc.cu", "f16_lma_elementwise.cu", "f16_tc_common.cuh", "f16_model.cuh", "f16_ground.cuh", "f16_env.cuh", "f16_host_setup.h", "f16_model_data.h")] + [
+        ("f16_b200.cu", "f16_rollout.cu", "f16_features.cu", "f16_hostwin.cu", "f16_lma_attention.cu", "f16_lma_norm.cu", "f16_lma_wgrad.cu", "f16_lma_linear.cu", "f16_lma_wgrad_tc.cu", "f16_lma_elementwise.cu", "f16_lma_policy.cu", "f16_tc_common.cuh", "f16_model.cuh", "f16_ground.cuh", "f16_env.cuh", "f16_host_setup.h", "f16_model_data.h")] + [
     os.path.join(os.path.dirname(_HERE), "include", f) for f in ("f16_b200.h", "f16_rollout.h", "f16_features.h", "f16_hostwin.h", "f16_lma.h", "f16_state_fields.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

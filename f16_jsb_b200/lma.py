@@ -545,3 +545,90 @@ class LMAActorCritic(nn.Module):
     def predict_values(self, obs: torch.Tensor) -> torch.Tensor:
         f = self.features_extractor(obs)
         return self.value_net(self.mlp_extractor.value_net(f)).squeeze(-1)
+
+
+class PolicyForwardKernel:
+    """ActorCriticPolicy.forward for the rollout (policies.py:636-658) as one launch of f16_lma_policy_forward
+    (csrc/f16_lma_policy.cu): (N, 10, 15) observations -> actions, values, log_probs, clipped actions.
+
+    The kernel reads the parameters from one packed buffer (transposed Linear weights); `refresh()` re-packs it in place
+    from the module - call it whenever the optimizer has moved the weights (once per rollout). Buffers are allocated once,
+    so a CUDA graph that captured `__call__` stays valid. Only the reference run's shape is built (`supported`)."""
+
+    @staticmethod
+    def supported(policy: "LMAActorCritic") -> bool:
+        c = policy.features_extractor.cfg
+        pi = [m.out_features for m in policy.mlp_extractor.policy_net if isinstance(m, nn.Linear)]
+        vf = [m.out_features for m in policy.mlp_extractor.value_net if isinstance(m, nn.Linear)]
+        acts = {type(m) for net in (policy.mlp_extractor.policy_net, policy.mlp_extractor.value_net) for m in net if not isinstance(m, nn.Linear)}
+        p = next(policy.parameters())
+        return ((c.seq_len, c.in_features, c.embed_dim, c.num_heads_stacking, c.num_heads_latent, c.ff_hidden, c.num_layers, c.bias)
+                == (10, 17, 64, 4, 4, 128, 2, True) and (c.l_new, c.c_new, c.d_new) == (5, 128, 32) and pi == [64, 64] and vf == [128, 64]
+                and acts == {nn.Tanh} and policy.action_net.out_features == 4 and p.is_cuda and p.dtype == torch.float32)
+
+    def __init__(self, policy: "LMAActorCritic", act_low: torch.Tensor, act_high: torch.Tensor):
+        import ctypes as C
+
+        from . import _lib
+        if not PolicyForwardKernel.supported(policy):
+            raise ValueError("f16_lma_policy_forward is built for the reference run's policy shape on a CUDA device (train.py:21-32,84)")
+        self.policy = policy
+        self.device = next(policy.parameters()).device
+        L = _lib.load()
+        self.packed = torch.zeros(int(L.f16_lma_policy_packed_size()), dtype=torch.float32, device=self.device)
+        core = policy.features_extractor.lma_extractor
+        it = core.initial_transform
+        mods = [it.positions, it.input_embedding, it.embed_layer_2]
+        for blk in core.lma_blocks:
+            mods += [blk.ln_1, blk.attn.c_attn, blk.attn.c_proj, blk.ln_2, blk.mlp.c_fc, blk.mlp.c_proj]
+        mods += [policy.mlp_extractor.policy_net[0], policy.mlp_extractor.policy_net[2], policy.action_net,
+                 policy.mlp_extractor.value_net[0], policy.mlp_extractor.value_net[2], policy.value_net]
+        assert len(mods) == L.f16_lma_policy_entries()
+        self._plan = []                              # (source tensor getter, destination view, transpose)
+        for i, m in enumerate(mods):
+            fin, fout, wo, bo = C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
+            _lib.check(L.f16_lma_policy_entry(i, C.byref(fin), C.byref(fout), C.byref(wo), C.byref(bo)), "f16_lma_policy_entry")
+            fin, fout, wo, bo = fin.value, fout.value, wo.value, bo.value
+            if isinstance(m, torch.Tensor):          # the position table
+                assert tuple(m.shape) == (fin, fout) and bo < 0
+                self._plan.append((m, self.packed[wo:wo + fin * fout].view(fin, fout), False))
+            elif isinstance(m, nn.Linear):
+                assert (m.in_features, m.out_features) == (fin, fout) and m.bias is not None, (i, m)
+                self._plan.append((m.weight, self.packed[wo:wo + fin * fout].view(fin, fout), True))
+                self._plan.append((m.bias, self.packed[bo:bo + fout], False))
+            else:                                    # _Norm
+                assert fout == 0 and m.weight.numel() == fin and m.bias is not None, (i, m)
+                self._plan.append((m.weight, self.packed[wo:wo + fin], False))
+                self._plan.append((m.bias, self.packed[bo:bo + fin], False))
+        self.act_low = act_low.to(self.device, torch.float32).contiguous()
+        self.act_high = act_high.to(self.device, torch.float32).contiguous()
+        self._out = {}
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self) -> None:
+        for src, dst, transpose in self._plan:
+            dst.copy_(src.t() if transpose else src)
+
+    @torch.no_grad()
+    def __call__(self, obs: torch.Tensor, noise: Optional[torch.Tensor] = None, features: bool = False):
+        """-> actions (N, 4), values (N,), log_probs (N,), clipped (N, 4) [, features (N, 160)]; noise (N, 4) standard normal
+        draws, or None for the deterministic action (the mean). Outputs are reused from call to call for a given N."""
+        import ctypes as C
+
+        from . import _lib
+        assert obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous() and tuple(obs.shape[1:]) == (10, NUM_FEATURES), obs.shape
+        n = obs.shape[0]
+        if n not in self._out:
+            e = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)      # noqa: E731
+            self._out[n] = (e(n, 4), e(n), e(n), e(n, 4), e(n, self.policy.features_extractor.features_dim))
+        actions, values, log_probs, clipped, feats = self._out[n]
+        if noise is not None:
+            assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous() and tuple(noise.shape) == (n, 4)
+        p = lambda t: C.c_void_p(t.data_ptr() if t is not None else 0)                  # noqa: E731
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().f16_lma_policy_forward(
+                n, p(obs), p(self.packed), self.packed.numel(), p(noise), p(self.policy.log_std), p(self.act_low), p(self.act_high),
+                p(actions), p(clipped), p(values), p(log_probs), p(feats if features else None),
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "f16_lma_policy_forward")
+        return (actions, values, log_probs, clipped) + ((feats,) if features else ())

@@ -85,6 +85,26 @@ int f16_lma_embed_act_backward(int64_t rows, int channels, const float* a, const
                                void* stream);
 int f16_lma_dropout_add_forward(int64_t n, const float* x, const float* z, float* y, float dropout_p, uint64_t seed, void* stream);
 int f16_lma_dropout_backward(int64_t n, const float* dy, float* dx, float dropout_p, uint64_t seed, void* stream);
+
+/* The rollout's policy forward in one kernel (csrc/f16_lma_policy.cu): what ActorCriticPolicy.forward computes once per env-step
+ * while a rollout is collected (stable_baselines3/common/on_policy_algorithm.py:203-216 -> common/policies.py:636-658) for the
+ * reference run's policy (train.py:21-32,84): feature transform (jsbsim_gym/features.py:37-67), LMA extractor
+ * (jsbsim_gym/LMA_features.py:221-279,315-407; inference: dropout is the identity), pi [64,64] / vf [128,64] tanh MLPs, mean and
+ * value heads, actions = mean + exp(log_std) * noise (noise NULL: actions = mean), log-probability of the diagonal Gaussian
+ * (common/distributions.py:125-190), and the clip to [act_low, act_high] (on_policy_algorithm.py:216; clipped may be NULL).
+ *   obs [n][10][15] -> actions [n][4], clipped [n][4], values [n], log_probs [n], features [n][160] (NULL unless wanted)
+ * The parameters come as one packed float32 buffer of f16_lma_policy_packed_size() floats; f16_lma_policy_entry(i) gives, for entry
+ * i of f16_lma_policy_entries(), the shape and the offsets at which the caller stores it: Linear layers as the TRANSPOSED weight
+ * [in][out] followed by the bias [out]; LayerNorms (out_features 0) as weight [in] and bias [in]; entry 0 is the sinusoidal position
+ * table [10][64] (bias_offset -1). Order: positions, input_embedding, embed_layer_2, per block {ln_1, attn.c_attn, attn.c_proj, ln_2,
+ * mlp.c_fc, mlp.c_proj} x 2, policy_net.0, policy_net.2, action_net, value_net.0, value_net.2, value head.
+ * Only this shape is built (LMAConfigRL defaults of train.py); FP32 FMA arithmetic, sums re-ordered against torch's. */
+int64_t f16_lma_policy_packed_size(void);
+int f16_lma_policy_entries(void);
+int f16_lma_policy_entry(int index, int* in_features, int* out_features, int64_t* weight_offset, int64_t* bias_offset);
+int f16_lma_policy_forward(int64_t n_envs, const float* obs, const float* packed, int64_t packed_len, const float* noise,
+                           const float* log_std, const float* act_low, const float* act_high, float* actions, float* clipped,
+                           float* values, float* log_probs, float* features, void* stream);
 #ifdef __cplusplus
 }
 #endif

@@ -79,3 +79,32 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower() or f in ("f16_model.cuh", "f16_env.cuh", "f16_host_setup.h"), f
                 assert "f16_oracle" not in src and "libf16oracle" not in src and "hostsim.so" not in src, f
+
+
+def test_policy_forward_parameter_layout():
+    """f16_lma_policy_entry (include/f16_lma.h): the packed buffer is tiled exactly by the entries, in the documented order, with
+    the reference run's layer shapes (train.py:21-32,84); bad arguments are refused before any device work."""
+    from f16_jsb_b200 import _lib
+    L = _lib.load()
+    n = L.f16_lma_policy_entries()
+    cursor, shapes = 0, []
+    for i in range(n):
+        fin, fout, wo, bo = C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
+        assert L.f16_lma_policy_entry(i, C.byref(fin), C.byref(fout), C.byref(wo), C.byref(bo)) == 0
+        shapes.append((fin.value, fout.value))
+        assert wo.value == cursor
+        if bo.value < 0:                      # the position table
+            cursor += fin.value * fout.value
+        elif fout.value == 0:                 # LayerNorm: weight, bias
+            assert bo.value == cursor + fin.value
+            cursor += 2 * fin.value
+        else:                                 # Linear: transposed weight, bias
+            assert bo.value == cursor + fin.value * fout.value
+            cursor += fin.value * fout.value + fout.value
+    assert cursor == L.f16_lma_policy_packed_size()
+    block = [(32, 0), (32, 96), (32, 32), (32, 0), (32, 128), (128, 32)]
+    assert shapes == [(10, 64), (17, 64), (128, 32)] + block + block + [(160, 64), (64, 64), (64, 4), (160, 128), (128, 64), (64, 1)]
+    assert L.f16_lma_policy_entry(n, None, None, None, None) != 0
+    assert L.f16_lma_policy_forward(0, *([None] * 2), 0, *([None] * 10)) != 0
+    assert L.f16_lma_policy_forward(4, *([None] * 2), L.f16_lma_policy_packed_size() - 1, *([None] * 10)) != 0
+    assert b"packed_len" in L.f16_last_error()

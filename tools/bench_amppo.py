@@ -31,10 +31,12 @@ def main():
     ap.add_argument("--no-am-ppo", action="store_true")
     ap.add_argument("--tf32", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-fused-forward", action="store_true", help="rollout policy forward through the torch modules instead of f16_lma_policy_forward")
     args = ap.parse_args()
     env = F16BatchedEnv(args.envs, mode="fp32", seed=0)
     cfg = AMPPOConfig(n_steps=args.n_steps, batch_size=args.batch_size, n_epochs=args.n_epochs, optimizer=args.optimizer,
-                      use_am_ppo=not args.no_am_ppo, tf32=args.tf32, cuda_graph=not args.no_graph)
+                      use_am_ppo=not args.no_am_ppo, tf32=args.tf32, cuda_graph=not args.no_graph,
+                      fused_policy_forward=not args.no_fused_forward)
     algo = AMPPO(env, cfg)
     rows = []
     for it in range(args.iterations + 1):          # iteration 0 is the warm-up
@@ -54,7 +56,7 @@ def main():
     st = env.stats()
     print(json.dumps({
         "workload": "BASELINE configs[4]: AM-PPO (n_steps %d, LMA extractor, %s) rollout + update on GPU env observations" % (args.n_steps, args.optimizer),
-        "tf32": args.tf32, "cuda_graph": not args.no_graph, "envs": args.envs, "n_steps": args.n_steps, "batch_size": args.batch_size, "n_epochs": args.n_epochs,
+        "tf32": args.tf32, "cuda_graph": not args.no_graph, "fused_policy_forward": algo._fused_act is not None, "envs": args.envs, "n_steps": args.n_steps, "batch_size": args.batch_size, "n_epochs": args.n_epochs,
         "transitions_per_iteration": n, "rollout_s": roll, "update_s": upd,
         "rollout_env_steps_per_s": n / roll, "update_samples_per_s": n * args.n_epochs / upd,
         "overall_env_steps_per_s": n / (roll + upd), "last_stats": algo.last_stats,

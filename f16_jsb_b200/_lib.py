@@ -94,8 +94,8 @@ def load():
     L.f16_lma_linear_supported.argtypes = [i32, i32]
     L.f16_lma_linear_wgrad_tc.argtypes = [i64, i32, i32, vp, vp, vp, vp, vp]
     L.f16_lma_linear_wgrad_tc_supported.argtypes = [i32, i32]
-    L.f16_lma_embed_act_forward.argtypes = [i64, i32, i32, vp, vp, vp, C.c_float, u64, vp]
-    L.f16_lma_embed_act_backward.argtypes = [i64, i32, vp, vp, vp, C.c_float, u64, vp]
+    L.f16_lma_embed_act_forward.argtypes = [i64, i32, i32, i32, vp, vp, vp, C.c_float, u64, vp]
+    L.f16_lma_embed_act_backward.argtypes = [i64, i32, i32, i32, vp, vp, vp, C.c_float, u64, vp]
     L.f16_lma_dropout_add_forward.argtypes = [i64, vp, vp, vp, C.c_float, u64, vp]
     L.f16_lma_dropout_backward.argtypes = [i64, vp, vp, C.c_float, u64, vp]
     L.f16_lma_policy_packed_size.argtypes = []

@@ -193,22 +193,24 @@ def dropout_add(x: torch.Tensor, z: torch.Tensor, p: float, training: bool) -> t
 
 
 class _EmbedActFn(torch.autograd.Function):
-    """dropout(relu(a) + positions) in one pass; backward da = keep * dy * (a > 0) from the saved pre-activation."""
+    """dropout(relu(a) + positions) in one pass; backward da = keep * dy * (a > 0) from the saved pre-activation. With
+    stack_heads = H > 1 the result (B, T, C) comes back head-stacked - y.view(B, T, H, C/H).permute(0, 2, 1, 3) flattened to
+    (B, T * C) - and the backward reads dy in that order: the permutation copies are never made."""
 
     @staticmethod
-    def forward(ctx, a: torch.Tensor, pos: torch.Tensor, p: float):
+    def forward(ctx, a: torch.Tensor, pos: torch.Tensor, p: float, stack_heads: int = 1):
         import ctypes as C
 
         from . import _lib
         a, pos = a.contiguous(), pos.contiguous()
         seq, ch = pos.shape
-        y = torch.empty_like(a)
+        y = torch.empty_like(a) if stack_heads == 1 else torch.empty((a.numel() // (seq * ch), seq * ch), dtype=a.dtype, device=a.device)
         seed = _new_seed()
         with torch.cuda.device(a.device):
-            _lib.check(_lib.load().f16_lma_embed_act_forward(a.numel() // ch, ch, seq, C.c_void_p(a.data_ptr()), C.c_void_p(pos.data_ptr()),
+            _lib.check(_lib.load().f16_lma_embed_act_forward(a.numel() // ch, ch, seq, stack_heads, C.c_void_p(a.data_ptr()), C.c_void_p(pos.data_ptr()),
                                                              C.c_void_p(y.data_ptr()), float(p), seed, _stream(a)), "f16_lma_embed_act_forward")
         ctx.save_for_backward(a)
-        ctx.meta = (float(p), seed, ch)
+        ctx.meta = (float(p), seed, ch, seq, stack_heads)
         return y
 
     @staticmethod
@@ -217,13 +219,13 @@ class _EmbedActFn(torch.autograd.Function):
 
         from . import _lib
         (a,) = ctx.saved_tensors
-        p, seed, ch = ctx.meta
+        p, seed, ch, seq, stack_heads = ctx.meta
         dy = dy.contiguous()
         da = torch.empty_like(a)
         with torch.cuda.device(a.device):
-            _lib.check(_lib.load().f16_lma_embed_act_backward(a.numel() // ch, ch, C.c_void_p(a.data_ptr()), C.c_void_p(dy.data_ptr()),
+            _lib.check(_lib.load().f16_lma_embed_act_backward(a.numel() // ch, ch, seq, stack_heads, C.c_void_p(a.data_ptr()), C.c_void_p(dy.data_ptr()),
                                                               C.c_void_p(da.data_ptr()), p, seed, _stream(a)), "f16_lma_embed_act_backward")
-        return da, None, None
+        return da, None, None, None
 
 
 class _Attention(nn.Module):
@@ -441,15 +443,15 @@ class _InitialTransform(nn.Module):
         c = self.cfg
         b = x.shape[0]
         a = self.input_embedding(x)
-        if (self.training and c.dropout > 0 and a.is_cuda and a.dtype == torch.float32 and c.embed_dim % 8 == 0 and torch.is_grad_enabled()
-                and _LinearFn.use_fused_elementwise):
-            y = _EmbedActFn.apply(a, self.positions, c.dropout)
-        else:
-            y = F.dropout(F.relu(a) + self.positions, c.dropout, self.training)
         # head stacking (split the 64 channels in 4 heads, lay the heads one after the other along the
         # sequence) and re-chunking into L' tokens of C' values is a single permutation of the 640 values
         h = c.num_heads_stacking
-        y = y.view(b, c.seq_len, h, c.embed_dim // h).permute(0, 2, 1, 3).reshape(b, c.l_new, c.c_new)
+        if (self.training and c.dropout > 0 and a.is_cuda and a.dtype == torch.float32 and (c.embed_dim // h) % 8 == 0 and torch.is_grad_enabled()
+                and _LinearFn.use_fused_elementwise):
+            y = _EmbedActFn.apply(a, self.positions, c.dropout, h).view(b, c.l_new, c.c_new)      # written in stacked order
+        else:
+            y = F.dropout(F.relu(a) + self.positions, c.dropout, self.training)
+            y = y.view(b, c.seq_len, h, c.embed_dim // h).permute(0, 2, 1, 3).reshape(b, c.l_new, c.c_new)
         return F.relu(self.embed_layer_2(y))
 
 

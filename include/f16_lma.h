@@ -77,12 +77,15 @@ int f16_lma_linear_wgrad_tc(int64_t rows, int in_features, int out_features, con
  * mask; kept elements are scaled by 1 / (1 - p'), p' = round(p * 65536) / 65536. float32, contiguous, 16-byte aligned.
  *   embed activation (_InitialTransform: ReLU, sinusoidal positions, embedding dropout - jsbsim_gym/LMA_features.py:221-279):
  *     y[r][c] = keep * (max(a[r][c], 0) + pos[r mod seq_len][c]),   da[r][c] = keep * dy[r][c] * (a[r][c] > 0);  channels % 8 == 0
+ *     With stack_heads = H > 1, y and dy are in the head-stacked order the extractor re-chunks into latent tokens (:255-270):
+ *     element (b, t, h * channels/H + c) at b * seq_len * channels + h * seq_len * channels/H + t * channels/H + c - the
+ *     view / permute / reshape copy is not materialised, forward or backward. a, da and the keep mask keep the natural order.
  *   residual dropout (LMA block: z + drop(attn(ln(z))), z + drop(mlp(ln(z))) - :386-407):
  *     y = z + keep * x,   dx = keep * dy (dz = dy is the caller's);  n % 8 == 0 */
-int f16_lma_embed_act_forward(int64_t rows, int channels, int seq_len, const float* a, const float* pos, float* y, float dropout_p,
-                              uint64_t seed, void* stream);
-int f16_lma_embed_act_backward(int64_t rows, int channels, const float* a, const float* dy, float* da, float dropout_p, uint64_t seed,
-                               void* stream);
+int f16_lma_embed_act_forward(int64_t rows, int channels, int seq_len, int stack_heads, const float* a, const float* pos, float* y,
+                              float dropout_p, uint64_t seed, void* stream);
+int f16_lma_embed_act_backward(int64_t rows, int channels, int seq_len, int stack_heads, const float* a, const float* dy, float* da,
+                               float dropout_p, uint64_t seed, void* stream);
 int f16_lma_dropout_add_forward(int64_t n, const float* x, const float* z, float* y, float dropout_p, uint64_t seed, void* stream);
 int f16_lma_dropout_backward(int64_t n, const float* dy, float* dx, float dropout_p, uint64_t seed, void* stream);
 

@@ -291,6 +291,19 @@ def test_fused_dropout_kernels_match_torch(shape, p):
     assert torch.equal(ye.detach(), (torch.relu(a.detach()) + pos) * probe)       # both kernels key the mask by (seed, element / 8)
     (ga,) = torch.autograd.grad(ye, a, dy)
     assert torch.equal(ga, torch.where(a.detach() > 0, dy * probe, torch.zeros_like(dy)))
+    # head-stacked output (the permutation of LMA_features.py:255-270 folded into the store / the backward's load)
+    for heads in (2, 4):
+        if (ch // heads) % 8:
+            continue
+        stack = lambda v: v.view(shape[0], t, heads, ch // heads).permute(0, 2, 1, 3).reshape(shape[0], t * ch)      # noqa: E731
+        a2 = x.detach().clone().requires_grad_(True)
+        ys = _EmbedActFn.apply(a2, pos, p, heads)
+        assert ys.shape == (shape[0], t * ch)
+        m2 = mask_of(ys.grad_fn.meta[1])
+        assert torch.equal(ys.detach(), stack((torch.relu(a2.detach()) + pos) * m2))
+        dys = stack(dy).contiguous()
+        (ga2,) = torch.autograd.grad(ys, a2, dys)
+        assert torch.equal(ga2, torch.where(a2.detach() > 0, dy * m2, torch.zeros_like(dy)))
 
 
 def test_block_with_fused_dropout_equals_unfused_at_p0_and_trains():

@@ -246,8 +246,9 @@ def amppo_iteration(dev, args):
             "episodes_finished": st["episodes"], "last_update": stats,
             "note": "hand-written: env step, rollout store + GAE + stack-rebuilding gather, feature transform, latent attention, LayerNorm, "
                     "and the Linear layers' forward, input and weight gradients on the tensor cores (tcgen05.mma kind::tf32 with split operands, "
-                    "FP32-accurate, csrc/f16_lma_linear.cu, csrc/f16_lma_wgrad_tc.cu); library calls left: the 4- and 1-wide output heads, the 160 -> 128 value layer, "
-                    "elementwise activations / dropout, and the rollout's small-batch policy forward (DESIGN.md 4a)"}
+                    "FP32-accurate, csrc/f16_lma_linear.cu, csrc/f16_lma_wgrad_tc.cu), the embedding activation and residual dropouts (regenerated Philox mask, "
+                    "csrc/f16_lma_elementwise.cu) and the rollout's whole policy forward as one kernel (csrc/f16_lma_policy.cu); torch ops left in the update: "
+                    "the 4- and 1-wide output heads, GELU / tanh, the loss and the optimizer's multi-tensor ops (DESIGN.md 4a)"}
 
 
 def run_ours(args):

@@ -83,6 +83,8 @@ def load():
     L.f16_rollout_add.argtypes = [i64, i64, i64] + [vp] * 15
     L.f16_rollout_gae.argtypes = [i64, i64, C.c_float, C.c_float] + [vp] * 8
     L.f16_rollout_gather.argtypes = [i64, i64, i64] + [vp] * 15
+    L.f16_rollout_park_truncated.argtypes = [i64, i64, i64] + [vp] * 6
+    L.f16_rollout_park_truncated.restype = i32
     L.f16_features17.argtypes = [i64, vp, vp, vp]
     L.f16_lma_attention_forward.argtypes = [i64, i32, i32, i32, vp, vp, C.c_float, u64, vp]
     L.f16_lma_attention_backward.argtypes = [i64, i32, i32, i32, vp, vp, vp, C.c_float, u64, vp]
@@ -143,4 +145,4 @@ EXPORTED_SYMBOLS = (
     "f16_last_error", "f16_version")
 HOSTWIN_SYMBOLS = ("f16_hostwin_create", "f16_hostwin_destroy", "f16_hostwin_detach", "f16_hostwin_gather", "f16_hostwin_layout", "f16_hostwin_action_buffer", "f16_hostwin_reset",
                    "f16_hostwin_step", "f16_hostwin_timing", "f16_hostwin_numa_node", "f16_hostwin_fill", "f16_hostwin_push")
-ROLLOUT_SYMBOLS = ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather", "f16_features17")
+ROLLOUT_SYMBOLS = ("f16_rollout_add", "f16_rollout_gae", "f16_rollout_gather", "f16_rollout_park_truncated", "f16_features17")

@@ -223,6 +223,16 @@ class AMPPO:
 
     def _note_truncations(self, step: int, truncated: torch.Tensor) -> None:
         self._truncation_store()
+        if truncated.is_cuda and truncated.dtype == torch.uint8 and self.env.terminal_obs.is_contiguous():
+            import ctypes as C
+
+            from . import _lib
+            p = lambda t: C.c_void_p(t.data_ptr())          # noqa: E731
+            with torch.cuda.device(self.device):            # one launch: slots are handed out by an atomic counter on the device
+                _lib.check(_lib.load().f16_rollout_park_truncated(
+                    self.env.num_envs, step, self._tr_cap, p(truncated), p(self.env.terminal_obs), p(self._tr_obs), p(self._tr_flat), p(self._tr_count),
+                    C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)), "f16_rollout_park_truncated")
+            return
         tr = truncated.to(torch.int64)
         slot = torch.where(tr > 0, self._tr_count + torch.cumsum(tr, 0) - 1, self._tr_cap)      # non-truncated rows go to the spare slot
         self._tr_obs.index_copy_(0, slot, self.env.terminal_obs)
@@ -233,6 +243,8 @@ class AMPPO:
         if getattr(self, "_tr_obs", None) is None:
             return
         n = int(self._tr_count.item())
+        if n > self._tr_cap:
+            raise RuntimeError("more truncated episodes (%d) than an env can have in one rollout (%d)" % (n, self._tr_cap))
         if n:
             v = self.policy.predict_values(self._tr_obs[:n])
             self.buffer.rewards.view(-1).index_add_(0, self._tr_flat[:n], self.cfg.gamma * v)      # rewards are (step, env)

@@ -25,7 +25,7 @@ extern "C" void f16_internal_count_launch(void);
 
 namespace {
 constexpr int E = 16;                    // envs per CTA
-constexpr int NT = 256;                  // threads per CTA
+constexpr int NT = 128;                  // threads per CTA
 constexpr int T = 10, FI = 15, FO = 17;  // frames per observation, floats per frame, features per frame
 constexpr int EMB = 64, HS = 4;          // embedding width, heads of the head stacking
 constexpr int LT = 5, CN = 128, D = 32;  // latent tokens, their input width, latent width
@@ -50,17 +50,24 @@ constexpr int O_VF0 = O_ACT + lin_size(PI1, ACT);
 constexpr int O_VF1 = O_VF0 + lin_size(FEAT, VF0);
 constexpr int O_VAL = O_VF1 + lin_size(VF0, VF1);
 constexpr int PACKED = O_VAL + lin_size(VF1, 1);
+static_assert(O_EMBED % 4 == 0 && O_EMBED2 % 4 == 0 && O_BLOCK0 % 4 == 0 && BLOCK_SIZE % 4 == 0 && B_ATTN % 4 == 0 && B_PROJ % 4 == 0 && B_FC % 4 == 0 &&
+              B_MPROJ % 4 == 0 && O_PI0 % 4 == 0 && O_PI1 % 4 == 0 && O_ACT % 4 == 0 && O_VF0 % 4 == 0 && O_VF1 % 4 == 0,
+              "transposed weights are read as float4: 16-byte aligned offsets");
 
-// shared memory (floats): the stacked embedding and the MLP's hidden layer share one region, the features and the heads'
-// hidden layers live where q | k | v do
-constexpr int S_TOK = 0;                       // [E][640] = [E*LT][CN]; later h [E*LT][FF]
-constexpr int S_Z = S_TOK + E * T * EMB;       // [E*LT][D] residual stream = [E][160] features
-constexpr int S_LN = S_Z + E * LT * D;         // [E*LT][D]
-constexpr int S_ATT = S_LN + E * LT * D;       // [E*LT][D]
-constexpr int S_QKV = S_ATT + E * LT * D;      // [E*LT][3D]; earlier the frames / features [E*T][FO] + [E*T][FI]; later the heads
-constexpr int S_TOTAL = S_QKV + E * LT * 3 * D;
-static_assert(E * T * (FO + FI) <= E * LT * 3 * D, "frames and features must fit the q|k|v region");
-static_assert(E * (PI0 + PI1 + VF0 + VF1 + ACT) <= E * LT * 3 * D, "head activations must fit the q|k|v region");
+// shared memory (floats). Rows are padded by four floats (strides 132 / 36 / 100 / 68): the four rows a warp's row groups read
+// at a time then sit in different banks. The stacked embedding and the MLP's hidden layer share one region, the frames /
+// features and the heads' hidden layers live where q | k | v do.
+constexpr int PAD = 4;
+constexpr int TS = CN + PAD, ZS = D + PAD, QS = 3 * D + PAD;      // 132, 36, 100
+constexpr int S_TOK = 0;                       // [E*LT][TS] stacked embedding; later h [E*LT][FF + PAD]
+constexpr int S_Z = S_TOK + E * LT * TS;       // [E*LT][ZS] residual stream; env e's 160 features = its 5 rows
+constexpr int S_LN = S_Z + E * LT * ZS;        // [E*LT][ZS]
+constexpr int S_ATT = S_LN + E * LT * ZS;      // [E*LT][ZS]
+constexpr int S_QKV = S_ATT + E * LT * ZS;     // [E*LT][QS]; earlier the frames / features [E*T][FO] + [E*T][FI]; later the heads
+constexpr int S_TOTAL = S_QKV + E * LT * QS;
+static_assert(FF == CN, "the MLP's hidden layer reuses the stacked embedding's rows");
+static_assert(E * T * (FO + FI) <= E * LT * QS, "frames and features must fit the q|k|v region");
+static_assert(E * ((PI0 + PAD) + (PI1 + PAD) + (VF0 + PAD) + (VF1 + PAD) + ACT) <= E * LT * QS, "head activations must fit the q|k|v region");
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_TANH = 3 };
 
@@ -72,53 +79,99 @@ __device__ __forceinline__ float activate(float v) {
   return v;
 }
 
-// out(r, n) = act(sum_k in[r * IS + k] * wt[k * N + n] + bias[n]) for r < ROWS, handed to `store(r, n, value)`.
-// N columns x G = NT / N row groups; a thread accumulates RC rows of its column at a time (rows g, g + G, ...).
-template <int K, int N, int ROWS, int IS, int RC, int A, class Store>
+// out(r, n .. n + CC - 1) = act(sum_k in(r, k) * wt[k * N + n ..] + bias[n ..]) for r < ROWS, handed to `store(r, n, values)`.
+// A thread owns CC adjacent output columns (N / CC column threads x G = NT / (N / CC) row groups) and accumulates RC rows at a
+// time (rows g, g + G, ...): per four input features CC x 4 weights come as four 128-bit loads (a warp's column threads read one
+// contiguous span, row groups share it), each row's four inputs as one 128-bit shared-memory load shared by the row group:
+// RC + 4 loads per 4 * RC * CC FMAs. in(r, k) = in[r * IS + k], or with SEG > 0 in[r * IS + (k / SEG) * (SEG + PAD) + k % SEG]
+// (a row made of padded SEG-wide pieces: the 160 features of an env are its five 32-wide latent rows).
+template <int K, int N, int ROWS, int IS, int RC, int CC, int A, int SEG = 0, class Store>
 __device__ __forceinline__ void dense(const float* __restrict__ in, const float* __restrict__ wt, const float* __restrict__ bias, Store store) {
-  constexpr int G = NT / N;
-  static_assert(G >= 1, "at most NT output columns");
-  const int n = threadIdx.x % N, g = threadIdx.x / N;
+  static_assert(N % CC == 0 && (CC == 4 || CC == 1), "column tile");
+  constexpr int NC = N / CC;
+  constexpr int G = NT / NC;
+  static_assert(G >= 1, "at most NT column threads");
+  const int nc = threadIdx.x % NC, g = threadIdx.x / NC;
   if (g >= G) return;
-  const float bn = __ldg(bias + n);
-  for (int r0 = g; r0 < ROWS; r0 += G * RC) {
-    float acc[RC];
+  const int n = nc * CC;
+  float bn[CC];
 #pragma unroll
-    for (int i = 0; i < RC; ++i) acc[i] = 0.0f;
+  for (int c = 0; c < CC; ++c) bn[c] = __ldg(bias + n + c);
+  for (int r0 = g; r0 < ROWS; r0 += G * RC) {
+    float acc[RC][CC];
+#pragma unroll
+    for (int i = 0; i < RC; ++i)
+#pragma unroll
+      for (int c = 0; c < CC; ++c) acc[i][c] = 0.0f;
     if constexpr (K % 4 == 0 && IS % 4 == 0) {
 #pragma unroll 2
       for (int k = 0; k < K; k += 4) {
-        const float w0 = __ldg(wt + (k + 0) * N + n), w1 = __ldg(wt + (k + 1) * N + n), w2 = __ldg(wt + (k + 2) * N + n),
-                    w3 = __ldg(wt + (k + 3) * N + n);
+        float w[4][CC];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (CC == 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(wt + (k + j) * N + n));
+            w[j][0] = v.x; w[j][1] = v.y; w[j][2] = v.z; w[j][3] = v.w;
+          } else {
+            w[j][0] = __ldg(wt + (k + j) * N + n);
+          }
+        }
+        const int ko = SEG > 0 ? (k / SEG) * (SEG + PAD) + k % SEG : k;
 #pragma unroll
         for (int i = 0; i < RC; ++i) {
           const int r = r0 + i * G;
           if (r < ROWS) {
-            const float4 x = *reinterpret_cast<const float4*>(in + r * IS + k);
-            acc[i] = fmaf(x.x, w0, acc[i]);
-            acc[i] = fmaf(x.y, w1, acc[i]);
-            acc[i] = fmaf(x.z, w2, acc[i]);
-            acc[i] = fmaf(x.w, w3, acc[i]);
+            const float4 x = *reinterpret_cast<const float4*>(in + r * IS + ko);
+#pragma unroll
+            for (int c = 0; c < CC; ++c) {
+              acc[i][c] = fmaf(x.x, w[0][c], acc[i][c]);
+              acc[i][c] = fmaf(x.y, w[1][c], acc[i][c]);
+              acc[i][c] = fmaf(x.z, w[2][c], acc[i][c]);
+              acc[i][c] = fmaf(x.w, w[3][c], acc[i][c]);
+            }
           }
         }
       }
     } else {
+      static_assert(SEG == 0, "segmented rows need K % 4 == 0");
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const float w = __ldg(wt + k * N + n);
+        float w[CC];
+        if constexpr (CC == 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(wt + k * N + n));
+          w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+          w[0] = __ldg(wt + k * N + n);
+        }
 #pragma unroll
         for (int i = 0; i < RC; ++i) {
           const int r = r0 + i * G;
-          if (r < ROWS) acc[i] = fmaf(in[r * IS + k], w, acc[i]);
+          if (r < ROWS) {
+            const float x = in[r * IS + k];
+#pragma unroll
+            for (int c = 0; c < CC; ++c) acc[i][c] = fmaf(x, w[c], acc[i][c]);
+          }
         }
       }
     }
 #pragma unroll
     for (int i = 0; i < RC; ++i) {
       const int r = r0 + i * G;
-      if (r < ROWS) store(r, n, activate<A>(acc[i] + bn));
+      if (r < ROWS) {
+        float v[CC];
+#pragma unroll
+        for (int c = 0; c < CC; ++c) v[c] = activate<A>(acc[i][c] + bn[c]);
+        store(r, n, v);
+      }
     }
   }
+}
+
+__device__ __forceinline__ void put4(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void add4(float* p, const float* v) {
+  float4 o = *reinterpret_cast<float4*>(p);
+  o.x += v[0]; o.y += v[1]; o.z += v[2]; o.w += v[3];
+  *reinterpret_cast<float4*>(p) = o;
 }
 
 // LayerNorm over rows of D = 32 channels (class LayerNorm, LMA_features.py:172-185: biased variance, eps 1e-5): a warp per row
@@ -127,7 +180,7 @@ __device__ __forceinline__ void layernorm_rows(const float* __restrict__ x, cons
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float wl = __ldg(w + lane), bl = __ldg(b + lane);
   for (int r = warp; r < rows; r += NT / 32) {
-    const float v = x[r * D + lane];
+    const float v = x[r * ZS + lane];
     float s = v;
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -136,7 +189,7 @@ __device__ __forceinline__ void layernorm_rows(const float* __restrict__ x, cons
     float q = d * d;
 #pragma unroll
     for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    y[r * D + lane] = d * rsqrtf(q * (1.0f / D) + 1e-5f) * wl + bl;
+    y[r * ZS + lane] = d * rsqrtf(q * (1.0f / D) + 1e-5f) * wl + bl;
   }
 }
 
@@ -144,16 +197,16 @@ __device__ __forceinline__ void layernorm_rows(const float* __restrict__ x, cons
 __device__ __forceinline__ void attention_rows(const float* __restrict__ qkv, float* __restrict__ y, int envs) {
   for (int w = threadIdx.x; w < envs * HEADS * LT; w += NT) {
     const int e = w / (HEADS * LT), h = (w / LT) % HEADS, i = w % LT;
-    const float* base = qkv + e * LT * 3 * D + h * DH;
+    const float* base = qkv + e * LT * QS + h * DH;
     float q[DH];
 #pragma unroll
-    for (int d = 0; d < DH; ++d) q[d] = base[i * 3 * D + d];
+    for (int d = 0; d < DH; ++d) q[d] = base[i * QS + d];
     float s[LT], mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < LT; ++j) {
       float a = 0.0f;
 #pragma unroll
-      for (int d = 0; d < DH; ++d) a = fmaf(q[d], base[j * 3 * D + D + d], a);
+      for (int d = 0; d < DH; ++d) a = fmaf(q[d], base[j * QS + D + d], a);
       s[j] = a * 0.35355339059327376220f;
       mx = fmaxf(mx, s[j]);
     }
@@ -168,10 +221,10 @@ __device__ __forceinline__ void attention_rows(const float* __restrict__ qkv, fl
     for (int j = 0; j < LT; ++j) {
       const float p = s[j] * inv;
 #pragma unroll
-      for (int d = 0; d < DH; ++d) o[d] = fmaf(p, base[j * 3 * D + 2 * D + d], o[d]);
+      for (int d = 0; d < DH; ++d) o[d] = fmaf(p, base[j * QS + 2 * D + d], o[d]);
     }
 #pragma unroll
-    for (int d = 0; d < DH; ++d) y[(e * LT + i) * D + h * DH + d] = o[d];
+    for (int d = 0; d < DH; ++d) y[(e * LT + i) * ZS + h * DH + d] = o[d];
   }
 }
 
@@ -230,48 +283,51 @@ __global__ void __launch_bounds__(NT, 2) lma_policy_forward_kernel(PolicyArgs a)
     __syncthreads();
     // embedding + ReLU + positions, written head-stacked: (t, h, c) -> flat h * 160 + t * 16 + c of the env's 640 values,
     // which read as LT tokens of CN values (LMA_features.py:221-279)
-    dense<FO, EMB, E * T, FO, 8, ACT_RELU>(feat, P + O_EMBED, P + O_EMBED + FO * EMB, [&](int r, int n, float v) {
+    dense<FO, EMB, E * T, FO, 10, 4, ACT_RELU>(feat, P + O_EMBED, P + O_EMBED + FO * EMB, [&](int r, int n, const float* v) {
       const int e = r / T, t = r % T;
-      tok[e * (T * EMB) + (n / (EMB / HS)) * (T * (EMB / HS)) + t * (EMB / HS) + (n % (EMB / HS))] = v + __ldg(P + O_POS + t * EMB + n);
+      const int j = (n / (EMB / HS)) * (T * (EMB / HS)) + t * (EMB / HS) + (n % (EMB / HS));
+      const float4 ps = __ldg(reinterpret_cast<const float4*>(P + O_POS + t * EMB + n));
+      const float o[4] = {v[0] + ps.x, v[1] + ps.y, v[2] + ps.z, v[3] + ps.w};
+      put4(tok + (e * LT + j / CN) * TS + j % CN, o);
     });
     __syncthreads();
-    dense<CN, D, E * LT, CN, 10, ACT_RELU>(tok, P + O_EMBED2, P + O_EMBED2 + CN * D, [&](int r, int n, float v) { z[r * D + n] = v; });
+    dense<CN, D, E * LT, TS, 5, 4, ACT_RELU>(tok, P + O_EMBED2, P + O_EMBED2 + CN * D, [&](int r, int n, const float* v) { put4(z + r * ZS + n, v); });
     __syncthreads();
 #pragma unroll 1
     for (int blk = 0; blk < BLOCKS; ++blk) {
       const float* B = P + O_BLOCK0 + blk * BLOCK_SIZE;
       layernorm_rows(z, B + B_LN1, B + B_LN1 + D, ln, E * LT);
       __syncthreads();
-      dense<D, 3 * D, E * LT, D, 8, ACT_NONE>(ln, B + B_ATTN, B + B_ATTN + D * 3 * D, [&](int r, int n, float v) { qkv[r * 3 * D + n] = v; });
+      dense<D, 3 * D, E * LT, ZS, 8, 4, ACT_NONE>(ln, B + B_ATTN, B + B_ATTN + D * 3 * D, [&](int r, int n, const float* v) { put4(qkv + r * QS + n, v); });
       __syncthreads();
       attention_rows(qkv, att, E);
       __syncthreads();
-      dense<D, D, E * LT, D, 10, ACT_NONE>(att, B + B_PROJ, B + B_PROJ + D * D, [&](int r, int n, float v) { z[r * D + n] += v; });
+      dense<D, D, E * LT, ZS, 5, 4, ACT_NONE>(att, B + B_PROJ, B + B_PROJ + D * D, [&](int r, int n, const float* v) { add4(z + r * ZS + n, v); });
       __syncthreads();
       layernorm_rows(z, B + B_LN2, B + B_LN2 + D, ln, E * LT);
       __syncthreads();
-      dense<D, FF, E * LT, D, 8, ACT_GELU>(ln, B + B_FC, B + B_FC + D * FF, [&](int r, int n, float v) { tok[r * FF + n] = v; });
+      dense<D, FF, E * LT, ZS, 10, 4, ACT_GELU>(ln, B + B_FC, B + B_FC + D * FF, [&](int r, int n, const float* v) { put4(tok + r * TS + n, v); });
       __syncthreads();
-      dense<FF, D, E * LT, FF, 10, ACT_NONE>(tok, B + B_MPROJ, B + B_MPROJ + FF * D, [&](int r, int n, float v) { z[r * D + n] += v; });
+      dense<FF, D, E * LT, TS, 5, 4, ACT_NONE>(tok, B + B_MPROJ, B + B_MPROJ + FF * D, [&](int r, int n, const float* v) { add4(z + r * ZS + n, v); });
       __syncthreads();
     }
     if (a.features)
-      for (int i = threadIdx.x; i < envs * FEAT; i += NT) a.features[e0 * FEAT + i] = z[i];
-    // heads: z is [E][160]
-    float* p0 = qkv;
-    float* p1 = p0 + E * PI0;
-    float* v0 = p1 + E * PI1;
-    float* v1 = v0 + E * VF0;
-    float* mean = v1 + E * VF1;
-    dense<FEAT, PI0, E, FEAT, 4, ACT_TANH>(z, P + O_PI0, P + O_PI0 + FEAT * PI0, [&](int r, int n, float v) { p0[r * PI0 + n] = v; });
-    dense<FEAT, VF0, E, FEAT, 8, ACT_TANH>(z, P + O_VF0, P + O_VF0 + FEAT * VF0, [&](int r, int n, float v) { v0[r * VF0 + n] = v; });
+      for (int i = threadIdx.x; i < envs * FEAT; i += NT) a.features[e0 * FEAT + i] = z[(i / D) * ZS + i % D];
+    // heads: env e's 160 features are its LT rows of z
+    float* p0 = qkv;                           // [E][PI0 + PAD]
+    float* p1 = p0 + E * (PI0 + PAD);          // [E][PI1 + PAD]
+    float* v0 = p1 + E * (PI1 + PAD);          // [E][VF0 + PAD]
+    float* v1 = v0 + E * (VF0 + PAD);          // [E][VF1 + PAD]
+    float* mean = v1 + E * (VF1 + PAD);        // [E][ACT]
+    dense<FEAT, PI0, E, LT * ZS, 2, 4, ACT_TANH, D>(z, P + O_PI0, P + O_PI0 + FEAT * PI0, [&](int r, int n, const float* v) { put4(p0 + r * (PI0 + PAD) + n, v); });
+    dense<FEAT, VF0, E, LT * ZS, 4, 4, ACT_TANH, D>(z, P + O_VF0, P + O_VF0 + FEAT * VF0, [&](int r, int n, const float* v) { put4(v0 + r * (VF0 + PAD) + n, v); });
     __syncthreads();
-    dense<PI0, PI1, E, PI0, 4, ACT_TANH>(p0, P + O_PI1, P + O_PI1 + PI0 * PI1, [&](int r, int n, float v) { p1[r * PI1 + n] = v; });
-    dense<VF0, VF1, E, VF0, 4, ACT_TANH>(v0, P + O_VF1, P + O_VF1 + VF0 * VF1, [&](int r, int n, float v) { v1[r * VF1 + n] = v; });
+    dense<PI0, PI1, E, PI0 + PAD, 2, 4, ACT_TANH>(p0, P + O_PI1, P + O_PI1 + PI0 * PI1, [&](int r, int n, const float* v) { put4(p1 + r * (PI1 + PAD) + n, v); });
+    dense<VF0, VF1, E, VF0 + PAD, 2, 4, ACT_TANH>(v0, P + O_VF1, P + O_VF1 + VF0 * VF1, [&](int r, int n, const float* v) { put4(v1 + r * (VF1 + PAD) + n, v); });
     __syncthreads();
-    dense<PI1, ACT, E, PI1, 1, ACT_NONE>(p1, P + O_ACT, P + O_ACT + PI1 * ACT, [&](int r, int n, float v) { mean[r * ACT + n] = v; });
-    dense<VF1, 1, E, VF1, 1, ACT_NONE>(v1, P + O_VAL, P + O_VAL + VF1, [&](int r, int, float v) {
-      if (r < envs) a.values[e0 + r] = v;
+    dense<PI1, ACT, E, PI1 + PAD, 1, 4, ACT_NONE>(p1, P + O_ACT, P + O_ACT + PI1 * ACT, [&](int r, int n, const float* v) { put4(mean + r * ACT + n, v); });
+    dense<VF1, 1, E, VF1 + PAD, 1, 1, ACT_NONE>(v1, P + O_VAL, P + O_VAL + VF1, [&](int r, int, const float* v) {
+      if (r < envs) a.values[e0 + r] = v[0];
     });
     __syncthreads();
     // sample, log-probability (common/distributions.py:125-190: Normal(mean, exp(log_std)), summed over the action), clip

@@ -103,6 +103,24 @@ __global__ void rollout_gather_kernel(int64_t n, int64_t T, int64_t batch, const
   }
 }
 
+// a warp per env: the terminal observation of an env cut by the time limit goes to the next free slot of the side buffer
+__global__ void __launch_bounds__(256) park_truncated_kernel(int64_t n, int64_t step, int64_t capacity, int obs_floats,
+                                                             const uint8_t* __restrict__ truncated, const float* __restrict__ terminal_obs,
+                                                             float* __restrict__ parked_obs, int64_t* __restrict__ parked_flat,
+                                                             unsigned long long* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
+    if (!truncated[e]) continue;
+    unsigned long long slot = 0;
+    if (lane == 0) slot = atomicAdd(count, 1ull);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if ((int64_t)slot >= capacity) continue;               // the count keeps running: the caller sees the overflow
+    for (int i = lane; i < obs_floats; i += 32) parked_obs[slot * obs_floats + i] = terminal_obs[e * obs_floats + i];
+    if (lane == 0) parked_flat[slot] = step * n + e;
+  }
+}
+
 int check(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return f16_internal_fail(cudaGetErrorString(e));
@@ -150,6 +168,17 @@ int f16_rollout_gather(int64_t n, int64_t T, int64_t batch, const int64_t* indic
                                                                  advantages, returns, obs_out, actions_out, values_out, log_probs_out,
                                                                  advantages_out, returns_out);
   return check("rollout_gather");
+}
+
+int f16_rollout_park_truncated(int64_t n, int64_t step, int64_t capacity, const uint8_t* truncated, const float* terminal_obs,
+                               float* parked_obs, int64_t* parked_flat, int64_t* count, void* stream) {
+  if (n <= 0 || step < 0 || capacity <= 0) return f16_internal_fail("f16_rollout_park_truncated: bad sizes");
+  if (!truncated || !terminal_obs || !parked_obs || !parked_flat || !count) return f16_internal_fail("f16_rollout_park_truncated: NULL pointer");
+  unsigned grid = (unsigned)((n + 7) / 8);
+  if (grid > 148u * 8u) grid = 148u * 8u;
+  park_truncated_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, step, capacity, STACK * FR, truncated, terminal_obs, parked_obs, parked_flat,
+                                                                 (unsigned long long*)count);
+  return check("rollout_park_truncated");
 }
 
 }  // extern "C"

@@ -39,6 +39,15 @@ int f16_rollout_gather(int64_t n_envs, int64_t T, int64_t batch, const int64_t* 
                        const float* advantages, const float* returns, float* obs_out, float* actions_out,
                        float* values_out, float* log_probs_out, float* advantages_out, float* returns_out, void* stream);
 
+/* Time-limit bootstrap, first half (stable_baselines3/common/on_policy_algorithm.py:236-245: reward += gamma * V(terminal
+ * observation) for episodes cut by the time limit). The policy is frozen during a rollout, so the terminal observations can be
+ * valued once after the last step instead of inside the loop: for every env with truncated[env] != 0 this call copies
+ * terminal_obs[env] ([N][10][15]) to parked_obs[slot] and writes parked_flat[slot] = step * n_envs + env (the flat [T][N] index
+ * of the reward to adjust), slot = (*count)++ on the device. *count keeps running past `capacity` (entries beyond it are
+ * dropped; the caller checks). One launch, no host synchronisation. */
+int f16_rollout_park_truncated(int64_t n_envs, int64_t step, int64_t capacity, const uint8_t* truncated, const float* terminal_obs,
+                               float* parked_obs, int64_t* parked_flat, int64_t* count, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,13 +5,16 @@
 // (jsbsim_gym/features.py:37-67), the LMA extractor (jsbsim_gym/LMA_features.py:221-279 initial transform, :315-407 two
 // blocks of latent attention + MLP), the two tanh MLPs (train.py:84: pi [64,64], vf [128,64]), the 4-wide mean and 1-wide
 // value heads, the diagonal-Gaussian sample, its log-probability and the clip to the action box. In torch that is ~50
-// launches of 2-5 us kernels on a few thousand rows (library FP32 GEMMs at 32x32 tiles, measured 0.36 ms per step at 4 096
-// envs even when replayed as a CUDA graph); here a CTA takes 16 envs through the whole network with every activation in
-// shared memory (100 KB: two CTAs per SM) and the weights (58 K floats, transposed once per rollout by the caller so that
-// consecutive threads read consecutive output columns) served by L1 / L2.
+// launches of 2-5 us kernels on a few thousand rows (library FP32 GEMMs at 32x32 tiles, measured 0.29 ms per step at 4 096
+// envs even when replayed as a CUDA graph); here a CTA of 128 threads takes 16 envs through the whole network with every
+// activation in shared memory (87 KB + a 24 KB weight stage: two CTAs per SM). The weights (75 K floats, transposed once per
+// rollout by the caller so that consecutive threads read consecutive output columns) are staged layer by layer: the next
+// layer's travel from L2 in registers while the current layer's FMAs run, and are stored to shared memory between two
+// barriers (reading them straight from global memory left every k-step waiting on L2: 2.6 long-scoreboard stalls per issued
+// instruction at 7 warps per SM, profiles/).
 //
-// Dense layers: a thread owns one output column and a strip of rows; per four input features it reads four weights (coalesced)
-// and, per row, one 128-bit shared-memory broadcast - RC rows x 4 FMAs per RC + 4 loads. FP32 FMA throughout (the reference
+// Dense layers: a thread owns four adjacent output columns and up to ten rows; per four input features it reads 4 x 4 weights
+// and, per row, four inputs as 128-bit shared-memory loads - RC + 4 loads per 16 RC FMAs. FP32 FMA throughout (the reference
 // computes in FP32; sums are re-ordered, nothing is rounded to TF32). LayerNorm: one warp per 32-channel row. Attention: one
 // thread per (env, head, query) over the five latent tokens.
 #include <cuda_runtime.h>
@@ -55,19 +58,37 @@ static_assert(O_EMBED % 4 == 0 && O_EMBED2 % 4 == 0 && O_BLOCK0 % 4 == 0 && BLOC
               "transposed weights are read as float4: 16-byte aligned offsets");
 
 // shared memory (floats). Rows are padded by four floats (strides 132 / 36 / 100 / 68): the four rows a warp's row groups read
-// at a time then sit in different banks. The stacked embedding and the MLP's hidden layer share one region, the frames /
-// features and the heads' hidden layers live where q | k | v do.
+// at a time then sit in different banks. Regions are reused as their contents die: the stacked embedding, q | k | v and the
+// MLP's hidden layer share R0; LayerNorm output and attention output share LA; frames / features and the heads' hidden layers
+// share MISC. WS holds the weights of the layer (or K-chunk of a layer) being computed.
 constexpr int PAD = 4;
 constexpr int TS = CN + PAD, ZS = D + PAD, QS = 3 * D + PAD;      // 132, 36, 100
-constexpr int S_TOK = 0;                       // [E*LT][TS] stacked embedding; later h [E*LT][FF + PAD]
-constexpr int S_Z = S_TOK + E * LT * TS;       // [E*LT][ZS] residual stream; env e's 160 features = its 5 rows
-constexpr int S_LN = S_Z + E * LT * ZS;        // [E*LT][ZS]
-constexpr int S_ATT = S_LN + E * LT * ZS;      // [E*LT][ZS]
-constexpr int S_QKV = S_ATT + E * LT * ZS;     // [E*LT][QS]; earlier the frames / features [E*T][FO] + [E*T][FI]; later the heads
-constexpr int S_TOTAL = S_QKV + E * LT * QS;
+constexpr int HEAD_FLOATS = E * ((PI0 + PAD) + (PI1 + PAD) + (VF0 + PAD) + (VF1 + PAD) + ACT);
+constexpr int MISC_FLOATS = HEAD_FLOATS > E * T * (FO + FI) ? HEAD_FLOATS : E * T * (FO + FI);
+constexpr int WS_FLOATS = 6144;                // 24 KB: the largest staged piece is 5 120 floats
+constexpr int WS_PER_THREAD = WS_FLOATS / 4 / NT;      // float4 registers a thread carries for the next piece
+constexpr int S_R0 = 0;                        // [E*LT][TS]
+constexpr int S_Z = S_R0 + E * LT * TS;        // [E*LT][ZS] residual stream; env e's 160 features = its 5 rows
+constexpr int S_LA = S_Z + E * LT * ZS;        // [E*LT][ZS]
+constexpr int S_MISC = S_LA + E * LT * ZS;
+constexpr int S_WS = S_MISC + MISC_FLOATS;
+constexpr int S_TOTAL = S_WS + WS_FLOATS;
 static_assert(FF == CN, "the MLP's hidden layer reuses the stacked embedding's rows");
-static_assert(E * T * (FO + FI) <= E * LT * QS, "frames and features must fit the q|k|v region");
-static_assert(E * ((PI0 + PAD) + (PI1 + PAD) + (VF0 + PAD) + (VF1 + PAD) + ACT) <= E * LT * QS, "head activations must fit the q|k|v region");
+static_assert(QS <= TS, "q | k | v rows fit the stacked embedding's rows");
+static_assert(S_Z % 4 == 0 && S_LA % 4 == 0 && S_MISC % 4 == 0 && S_WS % 4 == 0 && WS_FLOATS % (4 * NT) == 0, "128-bit accesses");
+static_assert(2 * (S_TOTAL * 4 + 1024) <= 227 * 1024, "two CTAs per SM");
+
+#ifndef F16_POL_PIPE
+#define F16_POL_PIPE 1          // explicit two-deep software pipeline of the k-steps; 0: plain unrolled loop (A/B in profiles/)
+#endif
+#ifndef F16_POL_UNROLL
+#define F16_POL_UNROLL 2
+#endif
+#ifndef F16_POL_RC_FC
+#define F16_POL_RC_FC 5         // rows per pass of the 32 -> 128 layer (10: fewer weight reads, more registers in flight)
+#endif
+
+constexpr int POL_UNROLL = F16_POL_UNROLL;
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_TANH = 3 };
 
@@ -79,21 +100,140 @@ __device__ __forceinline__ float activate(float v) {
   return v;
 }
 
-// out(r, n .. n + CC - 1) = act(sum_k in(r, k) * wt[k * N + n ..] + bias[n ..]) for r < ROWS, handed to `store(r, n, values)`.
-// A thread owns CC adjacent output columns (N / CC column threads x G = NT / (N / CC) row groups) and accumulates RC rows at a
-// time (rows g, g + G, ...): per four input features CC x 4 weights come as four 128-bit loads (a warp's column threads read one
-// contiguous span, row groups share it), each row's four inputs as one 128-bit shared-memory load shared by the row group:
-// RC + 4 loads per 4 * RC * CC FMAs. in(r, k) = in[r * IS + k], or with SEG > 0 in[r * IS + (k / SEG) * (SEG + PAD) + k % SEG]
-// (a row made of padded SEG-wide pieces: the 160 features of an env are its five 32-wide latent rows).
-template <int K, int N, int ROWS, int IS, int RC, int CC, int A, int SEG = 0, class Store>
-__device__ __forceinline__ void dense(const float* __restrict__ in, const float* __restrict__ wt, const float* __restrict__ bias, Store store) {
+// The weights of the next piece travel through registers: loaded from global memory (L2) before the current piece is computed,
+// stored to WS after it - their latency hides under the FMAs instead of stalling every k-step of a thinly occupied SM.
+struct Prefetch {
+  float4 r[WS_PER_THREAD];
+  __device__ __forceinline__ void load(const float* __restrict__ src, int floats) {
+#pragma unroll
+    for (int i = 0; i < WS_PER_THREAD; ++i) {
+      const int j = threadIdx.x + i * NT;
+      if (4 * j < floats) r[i] = __ldg(reinterpret_cast<const float4*>(src) + j);
+    }
+  }
+  __device__ __forceinline__ void store(float* __restrict__ ws, int floats) const {
+#pragma unroll
+    for (int i = 0; i < WS_PER_THREAD; ++i) {
+      const int j = threadIdx.x + i * NT;
+      if (4 * j < floats) reinterpret_cast<float4*>(ws)[j] = r[i];
+    }
+  }
+};
+
+// One piece of a dense layer: acc(r, n .. n + CC - 1) += sum over the piece's KC input features k0 .. k0 + KC - 1 of
+// in(r, k) * ws[(k - k0) * N + n ..], for the RC rows r0, r0 + G, ... of this thread. A thread owns CC adjacent output columns
+// (N / CC column threads x G = NT / (N / CC) row groups): per four input features the CC x 4 weights come as four 128-bit
+// shared-memory loads (a warp's column threads read one contiguous span, its row groups share it) and each row's four inputs
+// as one more: RC + 4 loads per 4 * RC * CC FMAs. in(r, k) = in[r * IS + k], or with SEG > 0
+// in[r * IS + (k / SEG) * (SEG + PAD) + k % SEG] (a row made of padded SEG-wide pieces: the 160 features of an env are its five
+// 32-wide latent rows).
+template <int KC, int N, int ROWS, int IS, int RC, int CC, int SEG>
+__device__ __forceinline__ void dense_piece(const float* __restrict__ in, const float* __restrict__ ws, int k0, int r0, int n, float (&acc)[RC][CC]) {
+  constexpr int G = NT / (N / CC);
+  if constexpr (KC % 4 == 0 && IS % 4 == 0) {
+#if F16_POL_PIPE
+    // two k-steps in flight: the loads of step k + 1 are issued before the FMAs of step k (a scheduler holds two warps here:
+    // shared-memory latency is not hidden by other warps)
+    float4 xa[RC], xb[RC], wa[4], wb[4];
+    auto fetch = [&](int k, float4 (&x)[RC], float4 (&w)[4]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if constexpr (CC == 4) w[j] = *reinterpret_cast<const float4*>(ws + (k + j) * N + n);
+        else w[j] = make_float4(ws[(k + j) * N + n], 0.f, 0.f, 0.f);
+      }
+      const int kg = k0 + k;
+      const int ko = SEG > 0 ? (kg / SEG) * (SEG + PAD) + kg % SEG : kg;
+#pragma unroll
+      for (int i = 0; i < RC; ++i) {
+        const int r = r0 + i * G;
+        x[i] = r < ROWS ? *reinterpret_cast<const float4*>(in + r * IS + ko) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto fmas = [&](const float4 (&x)[RC], const float4 (&w)[4]) {
+#pragma unroll
+      for (int i = 0; i < RC; ++i) {
+        const float wv[4][4] = {{w[0].x, w[0].y, w[0].z, w[0].w}, {w[1].x, w[1].y, w[1].z, w[1].w}, {w[2].x, w[2].y, w[2].z, w[2].w},
+                                {w[3].x, w[3].y, w[3].z, w[3].w}};
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          acc[i][c] = fmaf(x[i].x, wv[0][c], acc[i][c]);
+          acc[i][c] = fmaf(x[i].y, wv[1][c], acc[i][c]);
+          acc[i][c] = fmaf(x[i].z, wv[2][c], acc[i][c]);
+          acc[i][c] = fmaf(x[i].w, wv[3][c], acc[i][c]);
+        }
+      }
+    };
+    fetch(0, xa, wa);
+#pragma unroll 1
+    for (int k = 0; k < KC; k += 8) {
+      if (k + 4 < KC) fetch(k + 4, xb, wb);
+      fmas(xa, wa);
+      if (k + 8 < KC) fetch(k + 8, xa, wa);
+      if (k + 4 < KC) fmas(xb, wb);
+    }
+#else
+#pragma unroll POL_UNROLL
+    for (int k = 0; k < KC; k += 4) {
+      float w[4][CC];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if constexpr (CC == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(ws + (k + j) * N + n);
+          w[j][0] = v.x; w[j][1] = v.y; w[j][2] = v.z; w[j][3] = v.w;
+        } else {
+          w[j][0] = ws[(k + j) * N + n];
+        }
+      }
+      const int kg = k0 + k;
+      const int ko = SEG > 0 ? (kg / SEG) * (SEG + PAD) + kg % SEG : kg;
+#pragma unroll
+      for (int i = 0; i < RC; ++i) {
+        const int r = r0 + i * G;
+        if (r < ROWS) {
+          const float4 x = *reinterpret_cast<const float4*>(in + r * IS + ko);
+#pragma unroll
+          for (int c = 0; c < CC; ++c) {
+            acc[i][c] = fmaf(x.x, w[0][c], acc[i][c]);
+            acc[i][c] = fmaf(x.y, w[1][c], acc[i][c]);
+            acc[i][c] = fmaf(x.z, w[2][c], acc[i][c]);
+            acc[i][c] = fmaf(x.w, w[3][c], acc[i][c]);
+          }
+        }
+      }
+    }
+#endif
+  } else {
+    static_assert(SEG == 0, "segmented rows need KC % 4 == 0");
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      float w[CC];
+      if constexpr (CC == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(ws + k * N + n);
+        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+      } else {
+        w[0] = ws[k * N + n];
+      }
+#pragma unroll
+      for (int i = 0; i < RC; ++i) {
+        const int r = r0 + i * G;
+        if (r < ROWS) {
+          const float x = in[r * IS + k0 + k];
+#pragma unroll
+          for (int c = 0; c < CC; ++c) acc[i][c] = fmaf(x, w[c], acc[i][c]);
+        }
+      }
+    }
+  }
+}
+
+// A whole layer whose weights ([K][N], transposed) are in WS: out(r, n ..) = act(acc + bias) handed to `store(r, n, values)`.
+template <int K, int N, int ROWS, int IS, int RC, int CC, int A, class Store>
+__device__ __forceinline__ void dense(const float* __restrict__ in, const float* __restrict__ ws, const float* __restrict__ bias, Store store) {
   static_assert(N % CC == 0 && (CC == 4 || CC == 1), "column tile");
-  constexpr int NC = N / CC;
-  constexpr int G = NT / NC;
+  constexpr int NC = N / CC, G = NT / NC;
   static_assert(G >= 1, "at most NT column threads");
-  const int nc = threadIdx.x % NC, g = threadIdx.x / NC;
+  const int nc = threadIdx.x % NC, g = threadIdx.x / NC, n = nc * CC;
   if (g >= G) return;
-  const int n = nc * CC;
   float bn[CC];
 #pragma unroll
   for (int c = 0; c < CC; ++c) bn[c] = __ldg(bias + n + c);
@@ -103,57 +243,7 @@ __device__ __forceinline__ void dense(const float* __restrict__ in, const float*
     for (int i = 0; i < RC; ++i)
 #pragma unroll
       for (int c = 0; c < CC; ++c) acc[i][c] = 0.0f;
-    if constexpr (K % 4 == 0 && IS % 4 == 0) {
-#pragma unroll 2
-      for (int k = 0; k < K; k += 4) {
-        float w[4][CC];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if constexpr (CC == 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(wt + (k + j) * N + n));
-            w[j][0] = v.x; w[j][1] = v.y; w[j][2] = v.z; w[j][3] = v.w;
-          } else {
-            w[j][0] = __ldg(wt + (k + j) * N + n);
-          }
-        }
-        const int ko = SEG > 0 ? (k / SEG) * (SEG + PAD) + k % SEG : k;
-#pragma unroll
-        for (int i = 0; i < RC; ++i) {
-          const int r = r0 + i * G;
-          if (r < ROWS) {
-            const float4 x = *reinterpret_cast<const float4*>(in + r * IS + ko);
-#pragma unroll
-            for (int c = 0; c < CC; ++c) {
-              acc[i][c] = fmaf(x.x, w[0][c], acc[i][c]);
-              acc[i][c] = fmaf(x.y, w[1][c], acc[i][c]);
-              acc[i][c] = fmaf(x.z, w[2][c], acc[i][c]);
-              acc[i][c] = fmaf(x.w, w[3][c], acc[i][c]);
-            }
-          }
-        }
-      }
-    } else {
-      static_assert(SEG == 0, "segmented rows need K % 4 == 0");
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        float w[CC];
-        if constexpr (CC == 4) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(wt + k * N + n));
-          w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        } else {
-          w[0] = __ldg(wt + k * N + n);
-        }
-#pragma unroll
-        for (int i = 0; i < RC; ++i) {
-          const int r = r0 + i * G;
-          if (r < ROWS) {
-            const float x = in[r * IS + k];
-#pragma unroll
-            for (int c = 0; c < CC; ++c) acc[i][c] = fmaf(x, w[c], acc[i][c]);
-          }
-        }
-      }
-    }
+    dense_piece<K, N, ROWS, IS, RC, CC, 0>(in, ws, 0, r0, n, acc);
 #pragma unroll
     for (int i = 0; i < RC; ++i) {
       const int r = r0 + i * G;
@@ -228,6 +318,27 @@ __device__ __forceinline__ void attention_rows(const float* __restrict__ qkv, fl
   }
 }
 
+// the 17 features of one frame (jsbsim_gym/features.py:37-67)
+__device__ __forceinline__ void frame_features(const float* __restrict__ o, float* __restrict__ y) {
+  const float dx = o[12] - o[0], dy = o[13] - o[1], dz = o[14] - o[2];
+  const float distance = sqrtf(dx * dx + dy * dy);
+  const float rel = atan2f(dy, dx) - o[11];
+  float ca, sa, cb, sb, cp, sp, ct, st, cr, sr;
+  sincosf(o[4], &sa, &ca);
+  sincosf(o[5], &sb, &cb);
+  sincosf(o[9], &sp, &cp);
+  sincosf(o[10], &st, &ct);
+  sincosf(rel, &sr, &cr);
+  y[0] = 1.0f / (1.0f + distance * 1e-3f);
+  y[1] = dz / 15000.0f;
+  y[2] = o[2] / 15000.0f;
+  y[3] = o[3];
+  y[4] = o[6]; y[5] = o[7]; y[6] = o[8];
+  y[7] = ca; y[8] = cb; y[9] = sa; y[10] = sb;
+  y[11] = cp; y[12] = ct; y[13] = sp; y[14] = st;
+  y[15] = cr; y[16] = sr;
+}
+
 struct PolicyArgs {
   int64_t n;
   const float* obs;       // [n][T][FI]
@@ -243,95 +354,139 @@ struct PolicyArgs {
   float* features;        // [n][FEAT] or NULL (tests)
 };
 
+// K-chunks of the two wide head layers (their weights do not fit WS in one piece)
+constexpr int PI0_KC = 80, VF0_KC = 40, VF1_KC = 64;
+static_assert(PI0_KC * PI0 <= WS_FLOATS && VF0_KC * VF0 <= WS_FLOATS && VF1_KC * VF1 <= WS_FLOATS && CN * D <= WS_FLOATS && D * FF <= WS_FLOATS &&
+              FF * D <= WS_FLOATS && D * 3 * D <= WS_FLOATS && FO * EMB <= WS_FLOATS && PI0 * PI1 <= WS_FLOATS, "every staged piece fits WS");
+
 __global__ void __launch_bounds__(NT, 2) lma_policy_forward_kernel(PolicyArgs a) {
   extern __shared__ __align__(16) float sm[];
-  float* tok = sm + S_TOK;
+  float* r0buf = sm + S_R0;              // stacked embedding [E*LT][TS] -> q | k | v [E*LT][QS] -> hidden [E*LT][TS]
   float* z = sm + S_Z;
-  float* ln = sm + S_LN;
-  float* att = sm + S_ATT;
-  float* qkv = sm + S_QKV;
-  float* feat = qkv;                     // [E*T][FO]
-  float* frames = qkv + E * T * FO;      // [E*T][FI]
+  float* la = sm + S_LA;
+  float* misc = sm + S_MISC;
+  float* ws = sm + S_WS;
+  float* feat = misc;                    // [E*T][FO]
+  float* frames = misc + E * T * FO;     // [E*T][FI]
+  float* p0 = misc;                      // [E][PI0 + PAD]
+  float* p1 = p0 + E * (PI0 + PAD);      // [E][PI1 + PAD]
+  float* v0 = p1 + E * (PI1 + PAD);      // [E][VF0 + PAD]
+  float* v1 = v0 + E * (VF0 + PAD);      // [E][VF1 + PAD]
+  float* mean = v1 + E * (VF1 + PAD);    // [E][ACT]
   const float* P = a.p;
+  Prefetch pf;
 
+  // A stage: the previous stage's FMAs are done with WS -> `pre` work that only touches activations, the prefetched weights go
+  // to WS, the weights after them start their trip -> barrier -> the layer's FMAs. Two barriers per stage.
+#define F16_STAGE(pre, cur_floats, next_src, next_floats, compute) \
+  __syncthreads();                                                 \
+  pre;                                                             \
+  pf.store(ws, (cur_floats));                                      \
+  pf.load((next_src), (next_floats));                              \
+  __syncthreads();                                                 \
+  compute;
+
+  pf.load(P + O_EMBED, FO * EMB);
   for (int64_t e0 = (int64_t)blockIdx.x * E; e0 < a.n; e0 += (int64_t)gridDim.x * E) {
     const int envs = (int)((a.n - e0) < E ? (a.n - e0) : E);
-    // frames in (coalesced), one thread per frame: the 17 features (jsbsim_gym/features.py:37-67)
     for (int i = threadIdx.x; i < E * T * FI; i += NT) frames[i] = (i < envs * T * FI) ? a.obs[e0 * T * FI + i] : 0.0f;
-    __syncthreads();
-    for (int f = threadIdx.x; f < E * T; f += NT) {
-      const float* o = frames + f * FI;
-      const float dx = o[12] - o[0], dy = o[13] - o[1], dz = o[14] - o[2];
-      const float distance = sqrtf(dx * dx + dy * dy);
-      const float rel = atan2f(dy, dx) - o[11];
-      float ca, sa, cb, sb, cp, sp, ct, st, cr, sr;
-      sincosf(o[4], &sa, &ca);
-      sincosf(o[5], &sb, &cb);
-      sincosf(o[9], &sp, &cp);
-      sincosf(o[10], &st, &ct);
-      sincosf(rel, &sr, &cr);
-      float* y = feat + f * FO;
-      y[0] = 1.0f / (1.0f + distance * 1e-3f);
-      y[1] = dz / 15000.0f;
-      y[2] = o[2] / 15000.0f;
-      y[3] = o[3];
-      y[4] = o[6]; y[5] = o[7]; y[6] = o[8];
-      y[7] = ca; y[8] = cb; y[9] = sa; y[10] = sb;
-      y[11] = cp; y[12] = ct; y[13] = sp; y[14] = st;
-      y[15] = cr; y[16] = sr;
-    }
-    __syncthreads();
     // embedding + ReLU + positions, written head-stacked: (t, h, c) -> flat h * 160 + t * 16 + c of the env's 640 values,
     // which read as LT tokens of CN values (LMA_features.py:221-279)
-    dense<FO, EMB, E * T, FO, 10, 4, ACT_RELU>(feat, P + O_EMBED, P + O_EMBED + FO * EMB, [&](int r, int n, const float* v) {
-      const int e = r / T, t = r % T;
-      const int j = (n / (EMB / HS)) * (T * (EMB / HS)) + t * (EMB / HS) + (n % (EMB / HS));
-      const float4 ps = __ldg(reinterpret_cast<const float4*>(P + O_POS + t * EMB + n));
-      const float o[4] = {v[0] + ps.x, v[1] + ps.y, v[2] + ps.z, v[3] + ps.w};
-      put4(tok + (e * LT + j / CN) * TS + j % CN, o);
-    });
-    __syncthreads();
-    dense<CN, D, E * LT, TS, 5, 4, ACT_RELU>(tok, P + O_EMBED2, P + O_EMBED2 + CN * D, [&](int r, int n, const float* v) { put4(z + r * ZS + n, v); });
-    __syncthreads();
+    F16_STAGE(for (int f = threadIdx.x; f < E * T; f += NT) frame_features(frames + f * FI, feat + f * FO),
+              FO * EMB, P + O_EMBED2, CN * D,
+              (dense<FO, EMB, E * T, FO, 10, 4, ACT_RELU>(feat, ws, P + O_EMBED + FO * EMB, [&](int r, int n, const float* v) {
+                const int e = r / T, t = r % T;
+                const int j = (n / (EMB / HS)) * (T * (EMB / HS)) + t * (EMB / HS) + (n % (EMB / HS));
+                const float4 ps = __ldg(reinterpret_cast<const float4*>(P + O_POS + t * EMB + n));
+                const float o[4] = {v[0] + ps.x, v[1] + ps.y, v[2] + ps.z, v[3] + ps.w};
+                put4(r0buf + (e * LT + j / CN) * TS + j % CN, o);
+              })))
+    F16_STAGE(, CN * D, P + O_BLOCK0 + B_ATTN, D * 3 * D,
+              (dense<CN, D, E * LT, TS, 5, 4, ACT_RELU>(r0buf, ws, P + O_EMBED2 + CN * D, [&](int r, int n, const float* v) { put4(z + r * ZS + n, v); })))
 #pragma unroll 1
     for (int blk = 0; blk < BLOCKS; ++blk) {
       const float* B = P + O_BLOCK0 + blk * BLOCK_SIZE;
-      layernorm_rows(z, B + B_LN1, B + B_LN1 + D, ln, E * LT);
-      __syncthreads();
-      dense<D, 3 * D, E * LT, ZS, 8, 4, ACT_NONE>(ln, B + B_ATTN, B + B_ATTN + D * 3 * D, [&](int r, int n, const float* v) { put4(qkv + r * QS + n, v); });
-      __syncthreads();
-      attention_rows(qkv, att, E);
-      __syncthreads();
-      dense<D, D, E * LT, ZS, 5, 4, ACT_NONE>(att, B + B_PROJ, B + B_PROJ + D * D, [&](int r, int n, const float* v) { add4(z + r * ZS + n, v); });
-      __syncthreads();
-      layernorm_rows(z, B + B_LN2, B + B_LN2 + D, ln, E * LT);
-      __syncthreads();
-      dense<D, FF, E * LT, ZS, 10, 4, ACT_GELU>(ln, B + B_FC, B + B_FC + D * FF, [&](int r, int n, const float* v) { put4(tok + r * TS + n, v); });
-      __syncthreads();
-      dense<FF, D, E * LT, TS, 5, 4, ACT_NONE>(tok, B + B_MPROJ, B + B_MPROJ + FF * D, [&](int r, int n, const float* v) { add4(z + r * ZS + n, v); });
-      __syncthreads();
+      const float* after = blk + 1 < BLOCKS ? B + BLOCK_SIZE + B_ATTN : P + O_PI0;         // what follows this block's last layer
+      const int after_floats = blk + 1 < BLOCKS ? D * 3 * D : PI0_KC * PI0;
+      F16_STAGE(layernorm_rows(z, B + B_LN1, B + B_LN1 + D, la, E * LT), D * 3 * D, B + B_PROJ, D * D,
+                (dense<D, 3 * D, E * LT, ZS, 8, 4, ACT_NONE>(la, ws, B + B_ATTN + D * 3 * D, [&](int r, int n, const float* v) { put4(r0buf + r * QS + n, v); })))
+      F16_STAGE(attention_rows(r0buf, la, E), D * D, B + B_FC, D * FF,
+                (dense<D, D, E * LT, ZS, 5, 4, ACT_NONE>(la, ws, B + B_PROJ + D * D, [&](int r, int n, const float* v) { add4(z + r * ZS + n, v); })))
+      F16_STAGE(layernorm_rows(z, B + B_LN2, B + B_LN2 + D, la, E * LT), D * FF, B + B_MPROJ, FF * D,
+                (dense<D, FF, E * LT, ZS, F16_POL_RC_FC, 4, ACT_GELU>(la, ws, B + B_FC + D * FF, [&](int r, int n, const float* v) { put4(r0buf + r * TS + n, v); })))
+      F16_STAGE(, FF * D, after, after_floats,
+                (dense<FF, D, E * LT, TS, 5, 4, ACT_NONE>(r0buf, ws, B + B_MPROJ + FF * D, [&](int r, int n, const float* v) { add4(z + r * ZS + n, v); })))
     }
-    if (a.features)
-      for (int i = threadIdx.x; i < envs * FEAT; i += NT) a.features[e0 * FEAT + i] = z[(i / D) * ZS + i % D];
-    // heads: env e's 160 features are its LT rows of z
-    float* p0 = qkv;                           // [E][PI0 + PAD]
-    float* p1 = p0 + E * (PI0 + PAD);          // [E][PI1 + PAD]
-    float* v0 = p1 + E * (PI1 + PAD);          // [E][VF0 + PAD]
-    float* v1 = v0 + E * (VF0 + PAD);          // [E][VF1 + PAD]
-    float* mean = v1 + E * (VF1 + PAD);        // [E][ACT]
-    dense<FEAT, PI0, E, LT * ZS, 2, 4, ACT_TANH, D>(z, P + O_PI0, P + O_PI0 + FEAT * PI0, [&](int r, int n, const float* v) { put4(p0 + r * (PI0 + PAD) + n, v); });
-    dense<FEAT, VF0, E, LT * ZS, 4, 4, ACT_TANH, D>(z, P + O_VF0, P + O_VF0 + FEAT * VF0, [&](int r, int n, const float* v) { put4(v0 + r * (VF0 + PAD) + n, v); });
-    __syncthreads();
-    dense<PI0, PI1, E, PI0 + PAD, 2, 4, ACT_TANH>(p0, P + O_PI1, P + O_PI1 + PI0 * PI1, [&](int r, int n, const float* v) { put4(p1 + r * (PI1 + PAD) + n, v); });
-    dense<VF0, VF1, E, VF0 + PAD, 2, 4, ACT_TANH>(v0, P + O_VF1, P + O_VF1 + VF0 * VF1, [&](int r, int n, const float* v) { put4(v1 + r * (VF1 + PAD) + n, v); });
-    __syncthreads();
-    dense<PI1, ACT, E, PI1 + PAD, 1, 4, ACT_NONE>(p1, P + O_ACT, P + O_ACT + PI1 * ACT, [&](int r, int n, const float* v) { put4(mean + r * ACT + n, v); });
-    dense<VF1, 1, E, VF1 + PAD, 1, 1, ACT_NONE>(v1, P + O_VAL, P + O_VAL + VF1, [&](int r, int, const float* v) {
-      if (r < envs) a.values[e0 + r] = v[0];
-    });
-    __syncthreads();
+    // heads: env e's 160 features are its LT rows of z. The two 160-wide layers run in K-chunks with the accumulators kept in
+    // registers across the chunks (one row pass each).
+    {
+      constexpr int NC = PI0 / 4, G = NT / NC, RC = E / G;
+      static_assert(RC * G == E, "one row pass");
+      const int n = (threadIdx.x % NC) * 4, g = threadIdx.x / NC;
+      float acc[RC][4] = {};
+#pragma unroll
+      for (int ch = 0; ch < FEAT / PI0_KC; ++ch) {
+        const bool last = ch + 1 == FEAT / PI0_KC;
+        F16_STAGE(if (ch == 0 && a.features) for (int i = threadIdx.x; i < envs * FEAT; i += NT) a.features[e0 * FEAT + i] = z[(i / D) * ZS + i % D],
+                  PI0_KC * PI0, last ? P + O_VF0 : P + O_PI0 + (ch + 1) * PI0_KC * PI0, last ? VF0_KC * VF0 : PI0_KC * PI0,
+                  (dense_piece<PI0_KC, PI0, E, LT * ZS, RC, 4, D>(z, ws, ch * PI0_KC, g, n, acc)))
+      }
+#pragma unroll
+      for (int i = 0; i < RC; ++i) {
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = tanhf(acc[i][c] + __ldg(P + O_PI0 + FEAT * PI0 + n + c));
+        put4(p0 + (g + i * G) * (PI0 + PAD) + n, v);
+      }
+    }
+    {
+      constexpr int NC = VF0 / 4, G = NT / NC, RC = E / G;
+      static_assert(RC * G == E, "one row pass");
+      const int n = (threadIdx.x % NC) * 4, g = threadIdx.x / NC;
+      float acc[RC][4] = {};
+#pragma unroll
+      for (int ch = 0; ch < FEAT / VF0_KC; ++ch) {
+        const bool last = ch + 1 == FEAT / VF0_KC;
+        F16_STAGE(, VF0_KC * VF0, last ? P + O_PI1 : P + O_VF0 + (ch + 1) * VF0_KC * VF0, last ? PI0 * PI1 : VF0_KC * VF0,
+                  (dense_piece<VF0_KC, VF0, E, LT * ZS, RC, 4, D>(z, ws, ch * VF0_KC, g, n, acc)))
+      }
+#pragma unroll
+      for (int i = 0; i < RC; ++i) {
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = tanhf(acc[i][c] + __ldg(P + O_VF0 + FEAT * VF0 + n + c));
+        put4(v0 + (g + i * G) * (VF0 + PAD) + n, v);
+      }
+    }
+    F16_STAGE(, PI0 * PI1, P + O_VF1, VF1_KC * VF1,
+              (dense<PI0, PI1, E, PI0 + PAD, 2, 4, ACT_TANH>(p0, ws, P + O_PI1 + PI0 * PI1, [&](int r, int n, const float* v) { put4(p1 + r * (PI1 + PAD) + n, v); })))
+    {
+      constexpr int NC = VF1 / 4, G = NT / NC, RC = E / G;
+      static_assert(RC * G == E, "one row pass");
+      const int n = (threadIdx.x % NC) * 4, g = threadIdx.x / NC;
+      float acc[RC][4] = {};
+#pragma unroll
+      for (int ch = 0; ch < VF0 / VF1_KC; ++ch) {
+        const bool last = ch + 1 == VF0 / VF1_KC;
+        F16_STAGE(, VF1_KC * VF1, last ? P + O_ACT : P + O_VF1 + (ch + 1) * VF1_KC * VF1, last ? PI1 * ACT : VF1_KC * VF1,
+                  (dense_piece<VF1_KC, VF1, E, VF0 + PAD, RC, 4, 0>(v0, ws, ch * VF1_KC, g, n, acc)))
+      }
+#pragma unroll
+      for (int i = 0; i < RC; ++i) {
+        float v[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = tanhf(acc[i][c] + __ldg(P + O_VF1 + VF0 * VF1 + n + c));
+        put4(v1 + (g + i * G) * (VF1 + PAD) + n, v);
+      }
+    }
+    F16_STAGE(, PI1 * ACT, P + O_VAL, VF1,
+              (dense<PI1, ACT, E, PI1 + PAD, 1, 4, ACT_NONE>(p1, ws, P + O_ACT + PI1 * ACT, [&](int r, int n, const float* v) { put4(mean + r * ACT + n, v); })))
+    F16_STAGE(, VF1, P + O_EMBED, FO * EMB,
+              (dense<VF1, 1, E, VF1 + PAD, 1, 1, ACT_NONE>(v1, ws, P + O_VAL + VF1, [&](int r, int, const float* v) {
+                if (r < envs) a.values[e0 + r] = v[0];
+              })))
     // sample, log-probability (common/distributions.py:125-190: Normal(mean, exp(log_std)), summed over the action), clip
-    if (threadIdx.x < envs) {
+    if (threadIdx.x < envs) {            // mean was written by this stage's predecessor, two barriers ago
       const int r = threadIdx.x;
       float lp = 0.0f;
 #pragma unroll
@@ -345,8 +500,9 @@ __global__ void __launch_bounds__(NT, 2) lma_policy_forward_kernel(PolicyArgs a)
       }
       a.log_probs[e0 + r] = lp;
     }
-    __syncthreads();
+    __syncthreads();                     // MISC (mean) and WS are free for the next tile
   }
+#undef F16_STAGE
 }
 
 struct Entry { int in, out, w, b; };

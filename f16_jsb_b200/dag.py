@@ -115,7 +115,12 @@ class DAG(Optimizer):
             scale = (alpha / s_t / (norms + h["eps"])).unbind()              # alpha / s_t / (||g|| + eps), one scalar per tensor
             scaled = torch._foreach_mul(grads, list(scale))
             if self.global_step % self.sat_every == 0:
-                st["sat"] = torch.stack([(t.abs() > h["tau"]).float().mean() for t in scaled])
+                # fraction of |scaled| above tau per tensor (sgd.py: (x.abs() > tau).float().mean()) from one flat pass and a
+                # prefix sum instead of four launches per parameter tensor; counts are integers < 2^24: exact in float32
+                if "ends" not in st or st["ends"].numel() != len(params):
+                    st["ends"] = torch.cumsum(st["d"].to(torch.int64), 0) - 1
+                hits = torch.cumsum((torch.cat([t.reshape(-1) for t in scaled]).abs_() > h["tau"]).to(torch.int32), 0)[st["ends"]]
+                st["sat"] = torch.diff(hits, prepend=hits.new_zeros(1)).to(torch.float32) / st["d"]
             torch._foreach_tanh_(scaled)
             updates = torch._foreach_mul(scaled, (self.k_val * self._s_t).to(torch.float32))
             if group["weight_decay"]:

@@ -302,6 +302,7 @@ class _LinearFn(torch.autograd.Function):
     use_tc = os.environ.get("F16_LMA_TC", "1") != "0"        # class-wide switches (A/B measurements, tests)
     use_wgrad_tc = os.environ.get("F16_LMA_WGRAD_TC", "1") != "0"
     use_fused_elementwise = os.environ.get("F16_LMA_FUSED_ELEMENTWISE", "1") != "0"
+    pad_narrow_wgrad = os.environ.get("F16_LMA_PAD_NARROW_WGRAD", "1") != "0"
 
     @staticmethod
     def forward(ctx, x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]):
@@ -338,11 +339,22 @@ class _LinearFn(torch.autograd.Function):
             db = torch.empty(weight.shape[0], dtype=weight.dtype, device=weight.device) if ctx.has_bias else None
             stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
             tc = (_LinearFn.use_wgrad_tc and _wgrad_tc_supported(k, n) and x2.data_ptr() % 16 == 0 and dy2.data_ptr() % 16 == 0)
-            fn = "f16_lma_linear_wgrad_tc" if tc else "f16_lma_linear_wgrad"
+            # the 17-feature embedding: rows of 68 bytes cannot be fetched by TMA, and the FP32 slab kernel needs 300 us for this
+            # layer's 1.3 M rows; a zero-padded 32-wide copy (one pass, ~45 us) lets the tensor-core kernel take it (~100 us)
+            pad = (not tc and _LinearFn.use_wgrad_tc and _LinearFn.pad_narrow_wgrad and k < 32 and x2.shape[0] >= 65536
+                   and _wgrad_tc_supported(32, n) and dy2.data_ptr() % 16 == 0)
+            if pad:
+                x2 = F.pad(x2, (0, 32 - k))
+                dw_out = torch.empty((n, 32), dtype=weight.dtype, device=weight.device)
+            else:
+                dw_out = dw
+            fn = "f16_lma_linear_wgrad_tc" if (tc or pad) else "f16_lma_linear_wgrad"
             with torch.cuda.device(x.device):
                 _lib.check(getattr(_lib.load(), fn)(x2.shape[0], x2.shape[1], dy2.shape[1], C.c_void_p(x2.data_ptr()),
-                                                    C.c_void_p(dy2.data_ptr()), C.c_void_p(dw.data_ptr()),
+                                                    C.c_void_p(dy2.data_ptr()), C.c_void_p(dw_out.data_ptr()),
                                                     C.c_void_p(db.data_ptr() if db is not None else 0), stream), fn)
+            if pad:
+                dw.copy_(dw_out[:, :k])
         return dx, dw, db
 
 

@@ -217,11 +217,12 @@ def test_layernorm32_kernels_match_torch(rows, bias):
         assert torch.allclose(a.double(), r.double(), rtol=0, atol=tol * max(1.0, scale)), float((a.double() - r.double()).abs().max())
 
 
-@pytest.mark.parametrize("rows,fin,fout,bias", [(4096, 17, 64, True), (5 * 4099, 128, 32, True), (131072, 32, 96, True), (65536, 32, 128, False),
+@pytest.mark.parametrize("rows,fin,fout,bias", [(4096, 17, 64, True), (70001, 17, 64, True), (1310720, 17, 64, True), (5 * 4099, 128, 32, True), (131072, 32, 96, True), (65536, 32, 128, False),
                                                  (40000, 160, 64, True), (40000, 160, 128, True), (50000, 64, 4, True), (50001, 64, 1, True)])
 def test_linear_weight_gradient_kernel_matches_torch(rows, fin, fout, bias):
-    """csrc/f16_lma_wgrad.cu through the autograd wiring of lma.Linear, against a float64 torch reference: every
-    layer shape of the policy (train.py:21-32,84), ragged row counts."""
+    """csrc/f16_lma_wgrad.cu / f16_lma_wgrad_tc.cu through the autograd wiring of lma.Linear, against a float64 torch
+    reference: every layer shape of the policy (train.py:21-32,84), ragged row counts; the 17-feature embedding at
+    >= 65 536 rows goes to the tensor-core kernel through a zero-padded 32-wide copy."""
     from f16_jsb_b200.lma import Linear
     g = torch.Generator(device="cuda").manual_seed(5)
     lin = Linear(fin, fout, bias=bias).cuda()

@@ -2,7 +2,8 @@
 """Small runs of the fused policy forward and the elementwise dropout kernels for compute-sanitizer:
     compute-sanitizer --tool memcheck  python tools/sanitize_policy.py
     compute-sanitizer --tool racecheck python tools/sanitize_policy.py
-Ragged tiles (37 and 300 envs: partial CTAs, several tiles per CTA are covered by the grid-stride loop at 5 000)."""
+(compute-sanitizer is closed on the shared B200 pool; run plainly the script is the small-case runner: it prints the worst
+difference against the torch modules.) Ragged tiles (37 and 300 envs: partial CTAs, several tiles per CTA are covered by the grid-stride loop at 5 000)."""
 import os
 import sys
 

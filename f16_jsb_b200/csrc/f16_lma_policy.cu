@@ -14,9 +14,10 @@
 // instruction at 7 warps per SM, profiles/).
 //
 // Dense layers: a thread owns four adjacent output columns and up to ten rows; per four input features it reads 4 x 4 weights
-// and, per row, four inputs as 128-bit shared-memory loads - RC + 4 loads per 16 RC FMAs. FP32 FMA throughout (the reference
-// computes in FP32; sums are re-ordered, nothing is rounded to TF32). LayerNorm: one warp per 32-channel row. Attention: one
-// thread per (env, head, query) over the five latent tokens.
+// and, per row, four inputs as 128-bit shared-memory loads and issues 8 packed FMAs per row (fma.rn.f32x2 on the partial sums
+// over even and odd input features; the weights are staged pair-interleaved so that no operand needs packing). FP32 throughout
+// (the reference computes in FP32; sums are re-ordered, nothing is rounded to TF32). LayerNorm: one warp per 32-channel row.
+// Attention: one thread per (env, head, query) over the five latent tokens.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -78,17 +79,9 @@ static_assert(QS <= TS, "q | k | v rows fit the stacked embedding's rows");
 static_assert(S_Z % 4 == 0 && S_LA % 4 == 0 && S_MISC % 4 == 0 && S_WS % 4 == 0 && WS_FLOATS % (4 * NT) == 0, "128-bit accesses");
 static_assert(2 * (S_TOTAL * 4 + 1024) <= 227 * 1024, "two CTAs per SM");
 
-#ifndef F16_POL_PIPE
-#define F16_POL_PIPE 1          // explicit two-deep software pipeline of the k-steps; 0: plain unrolled loop (A/B in profiles/)
-#endif
-#ifndef F16_POL_UNROLL
-#define F16_POL_UNROLL 2
-#endif
 #ifndef F16_POL_RC_FC
 #define F16_POL_RC_FC 5         // rows per pass of the 32 -> 128 layer (10: fewer weight reads, more registers in flight)
 #endif
-
-constexpr int POL_UNROLL = F16_POL_UNROLL;
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_TANH = 3 };
 
@@ -120,113 +113,75 @@ struct Prefetch {
   }
 };
 
-// One piece of a dense layer: acc(r, n .. n + CC - 1) += sum over the piece's KC input features k0 .. k0 + KC - 1 of
-// in(r, k) * ws[(k - k0) * N + n ..], for the RC rows r0, r0 + G, ... of this thread. A thread owns CC adjacent output columns
-// (N / CC column threads x G = NT / (N / CC) row groups): per four input features the CC x 4 weights come as four 128-bit
-// shared-memory loads (a warp's column threads read one contiguous span, its row groups share it) and each row's four inputs
-// as one more: RC + 4 loads per 4 * RC * CC FMAs. in(r, k) = in[r * IS + k], or with SEG > 0
-// in[r * IS + (k / SEG) * (SEG + PAD) + k % SEG] (a row made of padded SEG-wide pieces: the 160 features of an env are its five
-// 32-wide latent rows).
-template <int KC, int N, int ROWS, int IS, int RC, int CC, int SEG>
-__device__ __forceinline__ void dense_piece(const float* __restrict__ in, const float* __restrict__ ws, int k0, int r0, int n, float (&acc)[RC][CC]) {
-  constexpr int G = NT / (N / CC);
-  if constexpr (KC % 4 == 0 && IS % 4 == 0) {
-#if F16_POL_PIPE
-    // two k-steps in flight: the loads of step k + 1 are issued before the FMAs of step k (a scheduler holds two warps here:
-    // shared-memory latency is not hidden by other warps)
-    float4 xa[RC], xb[RC], wa[4], wb[4];
-    auto fetch = [&](int k, float4 (&x)[RC], float4 (&w)[4]) {
+// Packed FP32: fma.rn.f32x2 does two FMAs per issued instruction (d.lo = a.lo * b.lo + c.lo, d.hi likewise).
+using u64 = unsigned long long;
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float sum2(u64 v) { return __uint_as_float((unsigned)v) + __uint_as_float((unsigned)(v >> 32)); }
+
+// One piece of a dense layer on packed FMAs: for the RC rows r0, r0 + G, ... of this thread and its four adjacent output columns
+// n .. n + 3, acc(r, c) += (sum over even k, sum over odd k) of in(r, k) * W(k, n + c), k = k0 .. k0 + KC - 1 - the two halves of a
+// 64-bit accumulator are the partial sums over the even and the odd input features (added at the end, sum2). The inputs' pairs
+// (k, k + 1) are the halves of a 128-bit shared-memory load as they lie; the weights are staged PAIR-INTERLEAVED so that theirs
+// are too: element (k, n) of a layer with N outputs sits at
+//     (k / 2) * 2N + ((n % 4) / 2) * N + (n / 4) * 4 + (n % 2) * 2 + k % 2
+// i.e. per pair of input features first every column thread's (n, n + 1) x (k, k + 1) quad, then every thread's (n + 2, n + 3)
+// quad: a thread's four 128-bit loads per four input features are contiguous across the column threads (no bank conflicts,
+// row groups share them). Per four input features: 4 + RC loads, 8 RC packed FMAs = 16 RC FMAs, no packing instructions.
+// The k-steps are software-pipelined two deep (a scheduler holds two warps here: other warps do not hide shared-memory latency).
+// in(r, k) = in[r * IS + k], or with SEG > 0 in[r * IS + (k / SEG) * (SEG + PAD) + k % SEG] (a row made of padded SEG-wide
+// pieces: the 160 features of an env are its five 32-wide latent rows).
+template <int KC, int N, int ROWS, int IS, int RC, int SEG>
+__device__ __forceinline__ void dense_piece2(const float* __restrict__ in, const float* __restrict__ ws, int k0, int r0, int n, u64 (&acc)[RC][4]) {
+  static_assert(KC % 4 == 0 && IS % 4 == 0 && N % 4 == 0, "128-bit loads");
+  constexpr int G = NT / (N / 4);
+  constexpr bool FULL = ROWS % G == 0 && (ROWS / G) % RC == 0;      // every (thread, pass, i) is a row: no predicates
+  const float* wcol = ws + n;                                        // (n / 4) * 4
+  ulonglong2 xa[RC], xb[RC], wa[4], wb[4];
+  auto fetch = [&](int k, ulonglong2 (&x)[RC], ulonglong2 (&w)[4]) {
+    const float* wp = wcol + (k >> 1) * (2 * N);
+    w[0] = *reinterpret_cast<const ulonglong2*>(wp);                 // (k, k+1) x (n, n+1)
+    w[1] = *reinterpret_cast<const ulonglong2*>(wp + N);             // (k, k+1) x (n+2, n+3)
+    w[2] = *reinterpret_cast<const ulonglong2*>(wp + 2 * N);         // (k+2, k+3) x (n, n+1)
+    w[3] = *reinterpret_cast<const ulonglong2*>(wp + 3 * N);         // (k+2, k+3) x (n+2, n+3)
+    const int kg = k0 + k;
+    const int ko = SEG > 0 ? (kg / SEG) * (SEG + PAD) + kg % SEG : kg;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if constexpr (CC == 4) w[j] = *reinterpret_cast<const float4*>(ws + (k + j) * N + n);
-        else w[j] = make_float4(ws[(k + j) * N + n], 0.f, 0.f, 0.f);
-      }
-      const int kg = k0 + k;
-      const int ko = SEG > 0 ? (kg / SEG) * (SEG + PAD) + kg % SEG : kg;
+    for (int i = 0; i < RC; ++i) {
+      const int r = r0 + i * G;
+      if (FULL || r < ROWS) x[i] = *reinterpret_cast<const ulonglong2*>(in + r * IS + ko);
+      else x[i] = make_ulonglong2(0ull, 0ull);
+    }
+  };
+  auto fmas = [&](const ulonglong2 (&x)[RC], const ulonglong2 (&w)[4]) {
 #pragma unroll
-      for (int i = 0; i < RC; ++i) {
-        const int r = r0 + i * G;
-        x[i] = r < ROWS ? *reinterpret_cast<const float4*>(in + r * IS + ko) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto fmas = [&](const float4 (&x)[RC], const float4 (&w)[4]) {
-#pragma unroll
-      for (int i = 0; i < RC; ++i) {
-        const float wv[4][4] = {{w[0].x, w[0].y, w[0].z, w[0].w}, {w[1].x, w[1].y, w[1].z, w[1].w}, {w[2].x, w[2].y, w[2].z, w[2].w},
-                                {w[3].x, w[3].y, w[3].z, w[3].w}};
-#pragma unroll
-        for (int c = 0; c < CC; ++c) {
-          acc[i][c] = fmaf(x[i].x, wv[0][c], acc[i][c]);
-          acc[i][c] = fmaf(x[i].y, wv[1][c], acc[i][c]);
-          acc[i][c] = fmaf(x[i].z, wv[2][c], acc[i][c]);
-          acc[i][c] = fmaf(x[i].w, wv[3][c], acc[i][c]);
-        }
-      }
-    };
-    fetch(0, xa, wa);
+    for (int i = 0; i < RC; ++i) {
+      acc[i][0] = fma2(x[i].x, w[0].x, acc[i][0]);
+      acc[i][1] = fma2(x[i].x, w[0].y, acc[i][1]);
+      acc[i][2] = fma2(x[i].x, w[1].x, acc[i][2]);
+      acc[i][3] = fma2(x[i].x, w[1].y, acc[i][3]);
+      acc[i][0] = fma2(x[i].y, w[2].x, acc[i][0]);
+      acc[i][1] = fma2(x[i].y, w[2].y, acc[i][1]);
+      acc[i][2] = fma2(x[i].y, w[3].x, acc[i][2]);
+      acc[i][3] = fma2(x[i].y, w[3].y, acc[i][3]);
+    }
+  };
+  fetch(0, xa, wa);
 #pragma unroll 1
-    for (int k = 0; k < KC; k += 8) {
-      if (k + 4 < KC) fetch(k + 4, xb, wb);
-      fmas(xa, wa);
-      if (k + 8 < KC) fetch(k + 8, xa, wa);
-      if (k + 4 < KC) fmas(xb, wb);
-    }
-#else
-#pragma unroll POL_UNROLL
-    for (int k = 0; k < KC; k += 4) {
-      float w[4][CC];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if constexpr (CC == 4) {
-          const float4 v = *reinterpret_cast<const float4*>(ws + (k + j) * N + n);
-          w[j][0] = v.x; w[j][1] = v.y; w[j][2] = v.z; w[j][3] = v.w;
-        } else {
-          w[j][0] = ws[(k + j) * N + n];
-        }
-      }
-      const int kg = k0 + k;
-      const int ko = SEG > 0 ? (kg / SEG) * (SEG + PAD) + kg % SEG : kg;
-#pragma unroll
-      for (int i = 0; i < RC; ++i) {
-        const int r = r0 + i * G;
-        if (r < ROWS) {
-          const float4 x = *reinterpret_cast<const float4*>(in + r * IS + ko);
-#pragma unroll
-          for (int c = 0; c < CC; ++c) {
-            acc[i][c] = fmaf(x.x, w[0][c], acc[i][c]);
-            acc[i][c] = fmaf(x.y, w[1][c], acc[i][c]);
-            acc[i][c] = fmaf(x.z, w[2][c], acc[i][c]);
-            acc[i][c] = fmaf(x.w, w[3][c], acc[i][c]);
-          }
-        }
-      }
-    }
-#endif
-  } else {
-    static_assert(SEG == 0, "segmented rows need KC % 4 == 0");
-#pragma unroll
-    for (int k = 0; k < KC; ++k) {
-      float w[CC];
-      if constexpr (CC == 4) {
-        const float4 v = *reinterpret_cast<const float4*>(ws + k * N + n);
-        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-      } else {
-        w[0] = ws[k * N + n];
-      }
-#pragma unroll
-      for (int i = 0; i < RC; ++i) {
-        const int r = r0 + i * G;
-        if (r < ROWS) {
-          const float x = in[r * IS + k0 + k];
-#pragma unroll
-          for (int c = 0; c < CC; ++c) acc[i][c] = fmaf(x, w[c], acc[i][c]);
-        }
-      }
-    }
+  for (int k = 0; k < KC; k += 8) {
+    if (k + 4 < KC) fetch(k + 4, xb, wb);
+    fmas(xa, wa);
+    if (k + 8 < KC) fetch(k + 8, xa, wa);
+    if (k + 4 < KC) fmas(xb, wb);
   }
 }
 
-// A whole layer whose weights ([K][N], transposed) are in WS: out(r, n ..) = act(acc + bias) handed to `store(r, n, values)`.
+// A whole layer whose weights are in WS: out(r, n ..) = act(acc + bias) handed to `store(r, n, values)`. Layers with an even
+// number of inputs and a multiple of four outputs run on packed FMAs (pair-interleaved weights, dense_piece2); the 17-feature
+// embedding and the 1-wide value head keep plain [K][N] weights and scalar FMAs.
 template <int K, int N, int ROWS, int IS, int RC, int CC, int A, class Store>
 __device__ __forceinline__ void dense(const float* __restrict__ in, const float* __restrict__ ws, const float* __restrict__ bias, Store store) {
   static_assert(N % CC == 0 && (CC == 4 || CC == 1), "column tile");
@@ -238,19 +193,50 @@ __device__ __forceinline__ void dense(const float* __restrict__ in, const float*
 #pragma unroll
   for (int c = 0; c < CC; ++c) bn[c] = __ldg(bias + n + c);
   for (int r0 = g; r0 < ROWS; r0 += G * RC) {
-    float acc[RC][CC];
+    float out[RC][CC];
+    if constexpr (CC == 4 && K % 4 == 0 && IS % 4 == 0) {
+      u64 acc[RC][4];
 #pragma unroll
-    for (int i = 0; i < RC; ++i)
+      for (int i = 0; i < RC; ++i)
 #pragma unroll
-      for (int c = 0; c < CC; ++c) acc[i][c] = 0.0f;
-    dense_piece<K, N, ROWS, IS, RC, CC, 0>(in, ws, 0, r0, n, acc);
+        for (int c = 0; c < 4; ++c) acc[i][c] = 0ull;
+      dense_piece2<K, N, ROWS, IS, RC, 0>(in, ws, 0, r0, n, acc);
+#pragma unroll
+      for (int i = 0; i < RC; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) out[i][c] = sum2(acc[i][c]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < RC; ++i)
+#pragma unroll
+        for (int c = 0; c < CC; ++c) out[i][c] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        float w[CC];
+        if constexpr (CC == 4) {
+          const float4 v = *reinterpret_cast<const float4*>(ws + k * N + n);
+          w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+          w[0] = ws[k * N + n];
+        }
+#pragma unroll
+        for (int i = 0; i < RC; ++i) {
+          const int r = r0 + i * G;
+          if (r < ROWS) {
+            const float x = in[r * IS + k];
+#pragma unroll
+            for (int c = 0; c < CC; ++c) out[i][c] = fmaf(x, w[c], out[i][c]);
+          }
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < RC; ++i) {
       const int r = r0 + i * G;
       if (r < ROWS) {
         float v[CC];
 #pragma unroll
-        for (int c = 0; c < CC; ++c) v[c] = activate<A>(acc[i][c] + bn[c]);
+        for (int c = 0; c < CC; ++c) v[c] = activate<A>(out[i][c] + bn[c]);
         store(r, n, v);
       }
     }
@@ -356,6 +342,7 @@ struct PolicyArgs {
 
 // K-chunks of the two wide head layers (their weights do not fit WS in one piece)
 constexpr int PI0_KC = 80, VF0_KC = 40, VF1_KC = 64;
+static_assert(PI0_KC % 4 == 0 && VF0_KC % 4 == 0 && VF1_KC % 4 == 0, "chunks are whole k-steps");
 static_assert(PI0_KC * PI0 <= WS_FLOATS && VF0_KC * VF0 <= WS_FLOATS && VF1_KC * VF1 <= WS_FLOATS && CN * D <= WS_FLOATS && D * FF <= WS_FLOATS &&
               FF * D <= WS_FLOATS && D * 3 * D <= WS_FLOATS && FO * EMB <= WS_FLOATS && PI0 * PI1 <= WS_FLOATS, "every staged piece fits WS");
 
@@ -423,19 +410,19 @@ __global__ void __launch_bounds__(NT, 2) lma_policy_forward_kernel(PolicyArgs a)
       constexpr int NC = PI0 / 4, G = NT / NC, RC = E / G;
       static_assert(RC * G == E, "one row pass");
       const int n = (threadIdx.x % NC) * 4, g = threadIdx.x / NC;
-      float acc[RC][4] = {};
+      u64 acc[RC][4] = {};
 #pragma unroll
       for (int ch = 0; ch < FEAT / PI0_KC; ++ch) {
         const bool last = ch + 1 == FEAT / PI0_KC;
         F16_STAGE(if (ch == 0 && a.features) for (int i = threadIdx.x; i < envs * FEAT; i += NT) a.features[e0 * FEAT + i] = z[(i / D) * ZS + i % D],
                   PI0_KC * PI0, last ? P + O_VF0 : P + O_PI0 + (ch + 1) * PI0_KC * PI0, last ? VF0_KC * VF0 : PI0_KC * PI0,
-                  (dense_piece<PI0_KC, PI0, E, LT * ZS, RC, 4, D>(z, ws, ch * PI0_KC, g, n, acc)))
+                  (dense_piece2<PI0_KC, PI0, E, LT * ZS, RC, D>(z, ws, ch * PI0_KC, g, n, acc)))
       }
 #pragma unroll
       for (int i = 0; i < RC; ++i) {
         float v[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = tanhf(acc[i][c] + __ldg(P + O_PI0 + FEAT * PI0 + n + c));
+        for (int c = 0; c < 4; ++c) v[c] = tanhf(sum2(acc[i][c]) + __ldg(P + O_PI0 + FEAT * PI0 + n + c));
         put4(p0 + (g + i * G) * (PI0 + PAD) + n, v);
       }
     }
@@ -443,18 +430,18 @@ __global__ void __launch_bounds__(NT, 2) lma_policy_forward_kernel(PolicyArgs a)
       constexpr int NC = VF0 / 4, G = NT / NC, RC = E / G;
       static_assert(RC * G == E, "one row pass");
       const int n = (threadIdx.x % NC) * 4, g = threadIdx.x / NC;
-      float acc[RC][4] = {};
+      u64 acc[RC][4] = {};
 #pragma unroll
       for (int ch = 0; ch < FEAT / VF0_KC; ++ch) {
         const bool last = ch + 1 == FEAT / VF0_KC;
         F16_STAGE(, VF0_KC * VF0, last ? P + O_PI1 : P + O_VF0 + (ch + 1) * VF0_KC * VF0, last ? PI0 * PI1 : VF0_KC * VF0,
-                  (dense_piece<VF0_KC, VF0, E, LT * ZS, RC, 4, D>(z, ws, ch * VF0_KC, g, n, acc)))
+                  (dense_piece2<VF0_KC, VF0, E, LT * ZS, RC, D>(z, ws, ch * VF0_KC, g, n, acc)))
       }
 #pragma unroll
       for (int i = 0; i < RC; ++i) {
         float v[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = tanhf(acc[i][c] + __ldg(P + O_VF0 + FEAT * VF0 + n + c));
+        for (int c = 0; c < 4; ++c) v[c] = tanhf(sum2(acc[i][c]) + __ldg(P + O_VF0 + FEAT * VF0 + n + c));
         put4(v0 + (g + i * G) * (VF0 + PAD) + n, v);
       }
     }
@@ -464,18 +451,18 @@ __global__ void __launch_bounds__(NT, 2) lma_policy_forward_kernel(PolicyArgs a)
       constexpr int NC = VF1 / 4, G = NT / NC, RC = E / G;
       static_assert(RC * G == E, "one row pass");
       const int n = (threadIdx.x % NC) * 4, g = threadIdx.x / NC;
-      float acc[RC][4] = {};
+      u64 acc[RC][4] = {};
 #pragma unroll
       for (int ch = 0; ch < VF0 / VF1_KC; ++ch) {
         const bool last = ch + 1 == VF0 / VF1_KC;
         F16_STAGE(, VF1_KC * VF1, last ? P + O_ACT : P + O_VF1 + (ch + 1) * VF1_KC * VF1, last ? PI1 * ACT : VF1_KC * VF1,
-                  (dense_piece<VF1_KC, VF1, E, VF0 + PAD, RC, 4, 0>(v0, ws, ch * VF1_KC, g, n, acc)))
+                  (dense_piece2<VF1_KC, VF1, E, VF0 + PAD, RC, 0>(v0, ws, ch * VF1_KC, g, n, acc)))
       }
 #pragma unroll
       for (int i = 0; i < RC; ++i) {
         float v[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[c] = tanhf(acc[i][c] + __ldg(P + O_VF1 + VF0 * VF1 + n + c));
+        for (int c = 0; c < 4; ++c) v[c] = tanhf(sum2(acc[i][c]) + __ldg(P + O_VF1 + VF0 * VF1 + n + c));
         put4(v1 + (g + i * G) * (VF1 + PAD) + n, v);
       }
     }

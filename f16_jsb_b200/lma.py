@@ -608,7 +608,10 @@ class PolicyForwardKernel:
                 self._plan.append((m, self.packed[wo:wo + fin * fout].view(fin, fout), False))
             elif isinstance(m, nn.Linear):
                 assert (m.in_features, m.out_features) == (fin, fout) and m.bias is not None, (i, m)
-                self._plan.append((m.weight, self.packed[wo:wo + fin * fout].view(fin, fout), True))
+                if fin % 2 == 0 and fout % 4 == 0:      # pair-interleaved for the packed FMAs (include/f16_lma.h)
+                    self._plan.append((m.weight, self.packed[wo:wo + fin * fout].view(fin // 2, 2, fout // 4, 2, 2), "pairs"))
+                else:
+                    self._plan.append((m.weight, self.packed[wo:wo + fin * fout].view(fin, fout), True))
                 self._plan.append((m.bias, self.packed[bo:bo + fout], False))
             else:                                    # _Norm
                 assert fout == 0 and m.weight.numel() == fin and m.bias is not None, (i, m)
@@ -621,8 +624,12 @@ class PolicyForwardKernel:
 
     @torch.no_grad()
     def refresh(self) -> None:
-        for src, dst, transpose in self._plan:
-            dst.copy_(src.t() if transpose else src)
+        for src, dst, how in self._plan:
+            if how == "pairs":      # W[n][k] -> [k / 2][(n % 4) / 2][n / 4][n % 2][k % 2]
+                k2, _, nc, _, _ = dst.shape
+                dst.copy_(src.view(nc, 2, 2, k2, 2).permute(3, 1, 0, 2, 4))
+            else:
+                dst.copy_(src.t() if how else src)
 
     @torch.no_grad()
     def __call__(self, obs: torch.Tensor, noise: Optional[torch.Tensor] = None, features: bool = False):

@@ -98,8 +98,11 @@ int f16_lma_dropout_backward(int64_t n, const float* dy, float* dx, float dropou
  *   obs [n][10][15] -> actions [n][4], clipped [n][4], values [n], log_probs [n], features [n][160] (NULL unless wanted)
  * The parameters come as one packed float32 buffer of f16_lma_policy_packed_size() floats; f16_lma_policy_entry(i) gives, for entry
  * i of f16_lma_policy_entries(), the shape and the offsets at which the caller stores it: Linear layers as the TRANSPOSED weight
- * [in][out] followed by the bias [out]; LayerNorms (out_features 0) as weight [in] and bias [in]; entry 0 is the sinusoidal position
- * table [10][64] (bias_offset -1). Order: positions, input_embedding, embed_layer_2, per block {ln_1, attn.c_attn, attn.c_proj, ln_2,
+ * followed by the bias [out]; LayerNorms (out_features 0) as weight [in] and bias [in]; entry 0 is the sinusoidal position
+ * table [10][64] (bias_offset -1). Transposed weight of a layer with an even number of inputs and a multiple of four outputs:
+ * PAIR-INTERLEAVED for the packed FP32 FMAs - W[out = n][in = k] at weight_offset +
+ *     (k / 2) * 2 * out_features + ((n % 4) / 2) * out_features + (n / 4) * 4 + (n % 2) * 2 + k % 2;
+ * the other two (17 -> 64 embedding, 64 -> 1 value head): plain [in][out], W[n][k] at weight_offset + k * out_features + n. Order: positions, input_embedding, embed_layer_2, per block {ln_1, attn.c_attn, attn.c_proj, ln_2,
  * mlp.c_fc, mlp.c_proj} x 2, policy_net.0, policy_net.2, action_net, value_net.0, value_net.2, value head.
  * Only this shape is built (LMAConfigRL defaults of train.py); FP32 FMA arithmetic, sums re-ordered against torch's. */
 int64_t f16_lma_policy_packed_size(void);

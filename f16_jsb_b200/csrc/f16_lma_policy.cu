@@ -250,22 +250,26 @@ __device__ __forceinline__ void add4(float* p, const float* v) {
   *reinterpret_cast<float4*>(p) = o;
 }
 
-// LayerNorm over rows of D = 32 channels (class LayerNorm, LMA_features.py:172-185: biased variance, eps 1e-5): a warp per row
+// LayerNorm over rows of D = 32 channels (class LayerNorm, LMA_features.py:172-185: biased variance, eps 1e-5): eight lanes per
+// row (four channels each), four rows per warp at a time - three shuffles per statistic instead of five, and four rows'
+// dependent chains in flight (a warp per row left the scheduler waiting on ten serial shuffles per row)
 __device__ __forceinline__ void layernorm_rows(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                                float* __restrict__ y, int rows) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float wl = __ldg(w + lane), bl = __ldg(b + lane);
-  for (int r = warp; r < rows; r += NT / 32) {
-    const float v = x[r * ZS + lane];
-    float s = v;
+  static_assert(D == 32 && (E * LT) % (NT / 32 * 4) == 0, "eight lanes x four channels per row; whole warps of rows");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane >> 3, c4 = (lane & 7) * 4;
+  const float4 wl = __ldg(reinterpret_cast<const float4*>(w + c4)), bl = __ldg(reinterpret_cast<const float4*>(b + c4));
+  for (int r = warp * 4 + sub; r < rows; r += NT / 32 * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(x + r * ZS + c4);
+    float s = (v.x + v.y) + (v.z + v.w);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int o = 4; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s * (1.0f / D);
-    const float d = v - mean;
-    float q = d * d;
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    float q = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    y[r * ZS + lane] = d * rsqrtf(q * (1.0f / D) + 1e-5f) * wl + bl;
+    for (int o = 4; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rs = rsqrtf(q * (1.0f / D) + 1e-5f);
+    *reinterpret_cast<float4*>(y + r * ZS + c4) = make_float4(d0 * rs * wl.x + bl.x, d1 * rs * wl.y + bl.y, d2 * rs * wl.z + bl.z, d3 * rs * wl.w + bl.w);
   }
 }
 

@@ -132,6 +132,27 @@ def load():
     return L
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device):
+    """`with torch.cuda.device(device)` only when `device` is not already current: with one process per GPU it always is, and the
+    context manager costs several microseconds on each of the ~60 kernel calls of an update step."""
+    import torch
+    idx = device.index
+    if idx is None or torch.cuda.current_device() == idx:
+        return _NO_GUARD
+    return torch.cuda.device(idx)
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().f16_last_error().decode(errors="replace")

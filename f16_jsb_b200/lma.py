@@ -107,7 +107,7 @@ class _LatentAttentionFn(torch.autograd.Function):
         # the mask is a function of (seed, sample, head): the backward kernel regenerates it
         seed = int(torch.empty((), dtype=torch.int64).random_()) if dropout_p > 0 else 0
         stream = C.c_void_p(torch.cuda.current_stream(qkv.device).cuda_stream)
-        with torch.cuda.device(qkv.device):
+        with _lib.device_guard(qkv.device):
             _lib.check(_lib.load().f16_lma_attention_forward(b, t, heads, d // heads, C.c_void_p(qkv.data_ptr()), C.c_void_p(y.data_ptr()),
                                                              float(dropout_p), seed, stream), "f16_lma_attention_forward")
         ctx.save_for_backward(qkv)
@@ -125,7 +125,7 @@ class _LatentAttentionFn(torch.autograd.Function):
         dy = dy.contiguous()
         dqkv = torch.empty_like(qkv)
         stream = C.c_void_p(torch.cuda.current_stream(qkv.device).cuda_stream)
-        with torch.cuda.device(qkv.device):
+        with _lib.device_guard(qkv.device):
             _lib.check(_lib.load().f16_lma_attention_backward(b, t, heads, d3 // 3 // heads, C.c_void_p(qkv.data_ptr()), C.c_void_p(dy.data_ptr()),
                                                               C.c_void_p(dqkv.data_ptr()), p, seed, stream), "f16_lma_attention_backward")
         return dqkv, None, None
@@ -162,7 +162,7 @@ class _DropoutAddFn(torch.autograd.Function):
         x, z = x.contiguous(), z.contiguous()
         y = torch.empty_like(x)
         seed = _new_seed()
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib.check(_lib.load().f16_lma_dropout_add_forward(x.numel(), C.c_void_p(x.data_ptr()), C.c_void_p(z.data_ptr()), C.c_void_p(y.data_ptr()),
                                                                float(p), seed, _stream(x)), "f16_lma_dropout_add_forward")
         ctx.meta = (float(p), seed)
@@ -178,7 +178,7 @@ class _DropoutAddFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(dy)
-            with torch.cuda.device(dy.device):
+            with _lib.device_guard(dy.device):
                 _lib.check(_lib.load().f16_lma_dropout_backward(dy.numel(), C.c_void_p(dy.data_ptr()), C.c_void_p(dx.data_ptr()), p, seed, _stream(dy)),
                            "f16_lma_dropout_backward")
         return dx, (dy if ctx.needs_input_grad[1] else None), None
@@ -206,7 +206,7 @@ class _EmbedActFn(torch.autograd.Function):
         seq, ch = pos.shape
         y = torch.empty_like(a) if stack_heads == 1 else torch.empty((a.numel() // (seq * ch), seq * ch), dtype=a.dtype, device=a.device)
         seed = _new_seed()
-        with torch.cuda.device(a.device):
+        with _lib.device_guard(a.device):
             _lib.check(_lib.load().f16_lma_embed_act_forward(a.numel() // ch, ch, seq, stack_heads, C.c_void_p(a.data_ptr()), C.c_void_p(pos.data_ptr()),
                                                              C.c_void_p(y.data_ptr()), float(p), seed, _stream(a)), "f16_lma_embed_act_forward")
         ctx.save_for_backward(a)
@@ -222,7 +222,7 @@ class _EmbedActFn(torch.autograd.Function):
         p, seed, ch, seq, stack_heads = ctx.meta
         dy = dy.contiguous()
         da = torch.empty_like(a)
-        with torch.cuda.device(a.device):
+        with _lib.device_guard(a.device):
             _lib.check(_lib.load().f16_lma_embed_act_backward(a.numel() // ch, ch, seq, stack_heads, C.c_void_p(a.data_ptr()), C.c_void_p(dy.data_ptr()),
                                                               C.c_void_p(da.data_ptr()), p, seed, _stream(a)), "f16_lma_embed_act_backward")
         return da, None, None, None
@@ -264,7 +264,7 @@ def _linear_tc(x2: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
     from . import _lib
     y = torch.empty((x2.shape[0], weight.shape[0]), dtype=torch.float32, device=x2.device)
     stream = C.c_void_p(torch.cuda.current_stream(x2.device).cuda_stream)
-    with torch.cuda.device(x2.device):
+    with _lib.device_guard(x2.device):
         _lib.check(_lib.load().f16_lma_linear_forward(x2.shape[0], x2.shape[1], weight.shape[0], C.c_void_p(x2.data_ptr()),
                                                       C.c_void_p(weight.data_ptr()), C.c_void_p(bias.data_ptr() if bias is not None else 0),
                                                       C.c_void_p(y.data_ptr()), stream), "f16_lma_linear_forward")
@@ -349,7 +349,7 @@ class _LinearFn(torch.autograd.Function):
             else:
                 dw_out = dw
             fn = "f16_lma_linear_wgrad_tc" if (tc or pad) else "f16_lma_linear_wgrad"
-            with torch.cuda.device(x.device):
+            with _lib.device_guard(x.device):
                 _lib.check(getattr(_lib.load(), fn)(x2.shape[0], x2.shape[1], dy2.shape[1], C.c_void_p(x2.data_ptr()),
                                                     C.c_void_p(dy2.data_ptr()), C.c_void_p(dw_out.data_ptr()),
                                                     C.c_void_p(db.data_ptr() if db is not None else 0), stream), fn)
@@ -384,7 +384,7 @@ class _LayerNorm32Fn(torch.autograd.Function):
         y = torch.empty_like(x)
         rows = x.numel() // 32
         stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib.check(_lib.load().f16_lma_layernorm_forward(rows, 32, C.c_void_p(x.data_ptr()), C.c_void_p(weight.data_ptr()),
                                                              C.c_void_p(bias.data_ptr() if bias is not None else 0), float(eps),
                                                              C.c_void_p(y.data_ptr()), stream), "f16_lma_layernorm_forward")
@@ -404,7 +404,7 @@ class _LayerNorm32Fn(torch.autograd.Function):
         dw = torch.empty_like(weight)
         db = torch.empty_like(weight) if has_bias else None
         stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib.check(_lib.load().f16_lma_layernorm_backward(x.numel() // 32, 32, C.c_void_p(x.data_ptr()), C.c_void_p(weight.data_ptr()),
                                                               C.c_void_p(dy.data_ptr()), eps, C.c_void_p(dx.data_ptr()),
                                                               C.c_void_p(dw.data_ptr()), C.c_void_p(db.data_ptr() if db is not None else 0),
@@ -647,7 +647,7 @@ class PolicyForwardKernel:
         if noise is not None:
             assert noise.is_cuda and noise.dtype == torch.float32 and noise.is_contiguous() and tuple(noise.shape) == (n, 4)
         p = lambda t: C.c_void_p(t.data_ptr() if t is not None else 0)                  # noqa: E731
-        with torch.cuda.device(self.device):
+        with _lib.device_guard(self.device):
             _lib.check(_lib.load().f16_lma_policy_forward(
                 n, p(obs), p(self.packed), self.packed.numel(), p(noise), p(self.policy.log_std), p(self.act_low), p(self.act_high),
                 p(actions), p(clipped), p(values), p(log_probs), p(feats if features else None),

@@ -65,7 +65,7 @@ def modulate_advantages(adv: torch.Tensor, params: Dict[str, float], alpha_state
     eps = params["eps"]
     if group is None:
         norm = torch.linalg.norm(adv)
-        sigma = torch.std(adv) + eps
+        sigma = (torch.std(adv) + eps) if update_ema else None       # only the controller's target needs it
         count = None
     else:
         import torch.distributed as dist
@@ -76,11 +76,11 @@ def modulate_advantages(adv: torch.Tensor, params: Dict[str, float], alpha_state
         norm = torch.sqrt(sums[0]).float()
         sigma = torch.sqrt(((sums[0] - sums[1] * sums[1] / count) / (count - 1)).clamp_min(0)).float() + eps
     alpha_prev, sat_prev = alpha_state[0].clone(), sat_state[0].clone()
-    alpha_hat = params["kappa"] * (norm + eps) / (sigma + eps) * (params["p_star"] / (sat_prev + eps)) ** params["eta"]
     if update_ema:
+        alpha_hat = params["kappa"] * (norm + eps) / (sigma + eps) * (params["p_star"] / (sat_prev + eps)) ** params["eta"]
         alpha = torch.clamp((1 - params["rho"]) * alpha_prev + params["rho"] * alpha_hat, params["alpha_min"], params["alpha_max"])
         alpha_state[0] = alpha.detach()
-    else:
+    else:                      # minibatch calls (ppo.py:331-345): the frozen alpha, no statistics of the controller
         alpha = alpha_prev
     z = alpha * (adv / (norm + eps))
     if update_ema:

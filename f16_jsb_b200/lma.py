@@ -561,35 +561,42 @@ class LMAActorCritic(nn.Module):
         return self.value_net(self.mlp_extractor.value_net(f)).squeeze(-1)
 
 
-class PolicyForwardKernel:
-    """ActorCriticPolicy.forward for the rollout (policies.py:636-658) as one launch of f16_lma_policy_forward
-    (csrc/f16_lma_policy.cu): (N, 10, 15) observations -> actions, values, log_probs, clipped actions.
-
-    The kernel reads the parameters from one packed buffer (transposed Linear weights); `refresh()` re-packs it in place
-    from the module - call it whenever the optimizer has moved the weights (once per rollout). Buffers are allocated once,
-    so a CUDA graph that captured `__call__` stays valid. Only the reference run's shape is built (`supported`)."""
+class PolicyPacker:
+    """The packed parameter buffer f16_lma_policy_forward reads (include/f16_lma.h: layout from f16_lma_policy_entry; Linear
+    weights transposed, pair-interleaved where the kernel uses packed FMAs). Works on any device - the layout is plain index
+    arithmetic - so that it can be checked without a GPU (the layout tests under tests/). `refresh()` re-packs IN PLACE."""
 
     @staticmethod
-    def supported(policy: "LMAActorCritic") -> bool:
+    def shape_supported(policy: "LMAActorCritic") -> bool:
         c = policy.features_extractor.cfg
         pi = [m.out_features for m in policy.mlp_extractor.policy_net if isinstance(m, nn.Linear)]
         vf = [m.out_features for m in policy.mlp_extractor.value_net if isinstance(m, nn.Linear)]
         acts = {type(m) for net in (policy.mlp_extractor.policy_net, policy.mlp_extractor.value_net) for m in net if not isinstance(m, nn.Linear)}
-        p = next(policy.parameters())
         return ((c.seq_len, c.in_features, c.embed_dim, c.num_heads_stacking, c.num_heads_latent, c.ff_hidden, c.num_layers, c.bias)
                 == (10, 17, 64, 4, 4, 128, 2, True) and (c.l_new, c.c_new, c.d_new) == (5, 128, 32) and pi == [64, 64] and vf == [128, 64]
-                and acts == {nn.Tanh} and policy.action_net.out_features == 4 and p.is_cuda and p.dtype == torch.float32)
+                and acts == {nn.Tanh} and policy.action_net.out_features == 4 and next(policy.parameters()).dtype == torch.float32)
 
-    def __init__(self, policy: "LMAActorCritic", act_low: torch.Tensor, act_high: torch.Tensor):
+    @staticmethod
+    def entries():
+        """[(in_features, out_features, weight_offset, bias_offset)] as the library reports them."""
         import ctypes as C
 
         from . import _lib
-        if not PolicyForwardKernel.supported(policy):
-            raise ValueError("f16_lma_policy_forward is built for the reference run's policy shape on a CUDA device (train.py:21-32,84)")
+        L = _lib.load()
+        out = []
+        for i in range(L.f16_lma_policy_entries()):
+            fin, fout, wo, bo = C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
+            _lib.check(L.f16_lma_policy_entry(i, C.byref(fin), C.byref(fout), C.byref(wo), C.byref(bo)), "f16_lma_policy_entry")
+            out.append((fin.value, fout.value, wo.value, bo.value))
+        return out
+
+    def __init__(self, policy: "LMAActorCritic"):
+        from . import _lib
+        if not PolicyPacker.shape_supported(policy):
+            raise ValueError("f16_lma_policy_forward is built for the reference run's policy shape (train.py:21-32,84)")
         self.policy = policy
         self.device = next(policy.parameters()).device
-        L = _lib.load()
-        self.packed = torch.zeros(int(L.f16_lma_policy_packed_size()), dtype=torch.float32, device=self.device)
+        self.packed = torch.zeros(int(_lib.load().f16_lma_policy_packed_size()), dtype=torch.float32, device=self.device)
         core = policy.features_extractor.lma_extractor
         it = core.initial_transform
         mods = [it.positions, it.input_embedding, it.embed_layer_2]
@@ -597,12 +604,10 @@ class PolicyForwardKernel:
             mods += [blk.ln_1, blk.attn.c_attn, blk.attn.c_proj, blk.ln_2, blk.mlp.c_fc, blk.mlp.c_proj]
         mods += [policy.mlp_extractor.policy_net[0], policy.mlp_extractor.policy_net[2], policy.action_net,
                  policy.mlp_extractor.value_net[0], policy.mlp_extractor.value_net[2], policy.value_net]
-        assert len(mods) == L.f16_lma_policy_entries()
-        self._plan = []                              # (source tensor getter, destination view, transpose)
-        for i, m in enumerate(mods):
-            fin, fout, wo, bo = C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
-            _lib.check(L.f16_lma_policy_entry(i, C.byref(fin), C.byref(fout), C.byref(wo), C.byref(bo)), "f16_lma_policy_entry")
-            fin, fout, wo, bo = fin.value, fout.value, wo.value, bo.value
+        ents = PolicyPacker.entries()
+        assert len(mods) == len(ents)
+        self._plan = []                              # (source tensor, destination view, how)
+        for i, (m, (fin, fout, wo, bo)) in enumerate(zip(mods, ents)):
             if isinstance(m, torch.Tensor):          # the position table
                 assert tuple(m.shape) == (fin, fout) and bo < 0
                 self._plan.append((m, self.packed[wo:wo + fin * fout].view(fin, fout), False))
@@ -617,9 +622,6 @@ class PolicyForwardKernel:
                 assert fout == 0 and m.weight.numel() == fin and m.bias is not None, (i, m)
                 self._plan.append((m.weight, self.packed[wo:wo + fin], False))
                 self._plan.append((m.bias, self.packed[bo:bo + fin], False))
-        self.act_low = act_low.to(self.device, torch.float32).contiguous()
-        self.act_high = act_high.to(self.device, torch.float32).contiguous()
-        self._out = {}
         self.refresh()
 
     @torch.no_grad()
@@ -630,6 +632,32 @@ class PolicyForwardKernel:
                 dst.copy_(src.view(nc, 2, 2, k2, 2).permute(3, 1, 0, 2, 4))
             else:
                 dst.copy_(src.t() if how else src)
+
+
+class PolicyForwardKernel:
+    """ActorCriticPolicy.forward for the rollout (policies.py:636-658) as one launch of f16_lma_policy_forward
+    (csrc/f16_lma_policy.cu): (N, 10, 15) observations -> actions, values, log_probs, clipped actions.
+
+    The kernel reads the parameters from one packed buffer (PolicyPacker); `refresh()` re-packs it in place from the module -
+    call it whenever the optimizer has moved the weights (once per rollout). Buffers are allocated once, so a CUDA graph
+    that captured `__call__` stays valid. Only the reference run's shape is built (`supported`)."""
+
+    @staticmethod
+    def supported(policy: "LMAActorCritic") -> bool:
+        return PolicyPacker.shape_supported(policy) and next(policy.parameters()).is_cuda
+
+    def __init__(self, policy: "LMAActorCritic", act_low: torch.Tensor, act_high: torch.Tensor):
+        if not PolicyForwardKernel.supported(policy):
+            raise ValueError("f16_lma_policy_forward is built for the reference run's policy shape on a CUDA device (train.py:21-32,84)")
+        self.policy = policy
+        self._packer = PolicyPacker(policy)
+        self.device, self.packed = self._packer.device, self._packer.packed
+        self.act_low = act_low.to(self.device, torch.float32).contiguous()
+        self.act_high = act_high.to(self.device, torch.float32).contiguous()
+        self._out = {}
+
+    def refresh(self) -> None:
+        self._packer.refresh()
 
     @torch.no_grad()
     def __call__(self, obs: torch.Tensor, noise: Optional[torch.Tensor] = None, features: bool = False):

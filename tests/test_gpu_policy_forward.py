@@ -69,6 +69,28 @@ def test_policy_forward_kernel_matches_the_modules(n):
     assert bool((c2 != a2).any()) or n < 16          # the box is narrower than the noise: the clip is exercised
 
 
+@pytest.mark.parametrize("n", [5, 1000])
+def test_policy_forward_kernel_matches_the_numpy_oracle(n):
+    """The kernel against oracle/policy_forward_oracle.py (float64 NumPy restatement of the reference's forward pass, pinned on
+    the CPU in tests/test_policy_oracle.py) on the very buffer the kernel reads: 2e-5 of the magnitude."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import policy_forward_oracle as oracle
+    from f16_jsb_b200.constants import ACTION_HIGH, ACTION_LOW
+    from f16_jsb_b200.lma import PolicyForwardKernel, PolicyPacker
+    net = _policy(100 + n)
+    fused = PolicyForwardKernel(net, torch.as_tensor(ACTION_LOW).cuda(), torch.as_tensor(ACTION_HIGH).cuda())
+    obs = _observations(n, 7)
+    noise = torch.randn((n, 4), device="cuda", generator=torch.Generator(device="cuda").manual_seed(8))
+    actions, values, log_probs, clipped, feats = [t.cpu().numpy().astype(np.float64) for t in fused(obs, noise, features=True)]
+    want = oracle.forward(obs.cpu().numpy(), fused.packed.cpu().numpy(), PolicyPacker.entries(), net.log_std.detach().cpu().numpy(),
+                          noise.cpu().numpy(), ACTION_LOW, ACTION_HIGH)
+    for name, got, tol in (("features", feats, 2e-5), ("actions", actions, 2e-5), ("values", values, 2e-5), ("log_probs", log_probs, 1e-4),
+                           ("clipped", clipped, 2e-5)):
+        err = float(np.abs(got - want[name]).max())
+        assert err <= tol * max(1.0, float(np.abs(want[name]).max())), (name, err)
+
+
 def test_policy_forward_kernel_follows_the_weights_and_the_golden_extractor():
     """refresh() re-packs in place; with the reference's recorded extractor weights the kernel's features equal the reference
     module's recorded outputs (tests/golden/learner_golden.pt, tools/make_golden_learner.py) to 1e-4."""

@@ -273,6 +273,11 @@ def test_fused_dropout_kernels_match_torch(shape, p):
     y = _DropoutAddFn.apply(x, z, p)
     seed = y.grad_fn.meta[1]
     m = mask_of(seed)
+    # the documented mask function (include/f16_lma.h), restated in NumPy and pinned to Random123's Philox known answers on the CPU
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dropout_mask_oracle
+    assert np.array_equal(m.cpu().numpy().reshape(-1), dropout_mask_oracle.keep_factors(x.numel(), p, seed))
     # the kernel's multiply-add is one FMA, torch's two rounded operations: equal to one rounding of the product
     assert torch.allclose(y.detach(), z.detach() + x.detach() * m, rtol=2e-7, atol=2e-7)
     if p == 0:

@@ -83,3 +83,21 @@ def test_oracle_reproduces_the_reference_extractor_outputs():
     got = oracle.forward(g["obs"].numpy(), packer.packed.numpy(), PolicyPacker.entries(), net.log_std.detach().numpy())
     err = float(np.abs(got["features"] - g["features"].numpy().astype(np.float64)).max())
     assert err <= 2e-5 * max(1.0, float(g["features"].abs().max())), err
+
+
+def test_philox_known_answers_and_keep_rate():
+    """The generator of the dropout-mask checker against Random123's published Philox4x32-10 known-answer vectors (kat_vectors:
+    zero counter and key; all ones; the digits of pi), and the keep rate / scale of the mask it builds."""
+    import dropout_mask_oracle as dm
+    kats = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+            ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+            ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kats:
+        got = dm.philox4x32_10(*[np.uint32(c) for c in ctr], *key)
+        assert tuple(int(x) for x in got) == want, [hex(int(x)) for x in got]
+    m = dm.keep_factors(1 << 20, 0.1, 0x123456789abcdef)
+    thr = round(0.1 * 65536)
+    assert set(np.unique(m).tolist()) == {0.0, float(np.float32(65536.0) / np.float32(65536 - thr))}
+    assert abs(float((m > 0).mean()) - (1 - thr / 65536)) < 2e-3
+    assert not np.array_equal(m, dm.keep_factors(1 << 20, 0.1, 0x123456789abcdf0))
+    assert bool((dm.keep_factors(64, 0.0, 5) == 1.0).all())

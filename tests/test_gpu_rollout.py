@@ -81,3 +81,38 @@ def test_rollout_store_matches_the_reference_class_golden():
         for a, name in zip((s.observations, s.actions, s.old_values, s.old_log_prob, s.advantages, s.returns),
                            ("observations", "actions", "old_values", "old_log_prob", "advantages", "returns")):
             assert np.array_equal(a.cpu().numpy(), g["b%d_%s" % (k, name)]), (k, name)
+
+
+@pytest.mark.gpu
+def test_park_truncated_collects_exactly_the_truncated_envs():
+    """f16_rollout_park_truncated (include/f16_rollout.h; first half of on_policy_algorithm.py:236-245's time-limit bootstrap):
+    every truncated env's terminal observation lands in exactly one slot together with its flat [T][N] reward index, the
+    device counter runs over the steps, entries beyond the capacity are dropped while the count keeps running."""
+    import ctypes as C
+
+    import torch
+
+    from f16_jsb_b200 import _lib
+    L = _lib.load()
+    n, cap = 5000, 700
+    g = torch.Generator(device="cuda").manual_seed(4)
+    p = lambda t: C.c_void_p(t.data_ptr())      # noqa: E731
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    parked = torch.full((cap + 1, 10, 15), -1.0, device="cuda")
+    flat = torch.full((cap + 1,), -1, dtype=torch.int64, device="cuda")
+    count = torch.zeros((), dtype=torch.int64, device="cuda")
+    want = {}
+    for step in (0, 3, 7):
+        term = torch.randn((n, 10, 15), device="cuda", generator=g)
+        trunc = (torch.rand(n, device="cuda", generator=g) < 0.05).to(torch.uint8)
+        _lib.check(L.f16_rollout_park_truncated(n, step, cap, p(trunc), p(term), p(parked), p(flat), p(count), stream), "park")
+        for e in trunc.nonzero().flatten().tolist():
+            want[step * n + e] = term[e].clone()
+    total = int(count.item())
+    assert total == len(want) and total > cap              # three steps x ~250 truncations overflow the 700 slots
+    got_flat = flat[:cap].tolist()
+    assert len(set(got_flat)) == cap and set(got_flat) <= set(want)          # distinct, all of them real truncations
+    for slot in range(0, cap, 37):
+        assert torch.equal(parked[slot], want[got_flat[slot]])
+    assert int(flat[cap]) == -1 and bool((parked[cap] == -1).all())          # nothing written past the capacity
+    assert L.f16_rollout_park_truncated(0, 0, cap, p(trunc), p(term), p(parked), p(flat), p(count), stream) != 0
